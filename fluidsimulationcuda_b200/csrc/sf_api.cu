@@ -1,0 +1,697 @@
+// C ABI (include/stablefluids.h) and the host-side step drivers.
+//
+// The drivers mirror the reference's sequencing (FluidSequential.c:176-186 dens_step, :189-241
+// vel_step) with the local pointer SWAPs written out, plan each lin_solve as a short list of
+// temporally blocked launches, and replay whole steps from captured CUDA graphs.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/stablefluids.h"
+#include "sf_common.cuh"
+
+using namespace sf;
+
+namespace {
+
+struct GraphKey {   // laid out without padding so memcmp is a valid equality
+    uint64_t kind;
+    const void *p[6];
+    float f[4];
+    int iters;
+    int opts[5];
+    bool operator==(const GraphKey &o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    cudaGraph_t graph;
+    unsigned long long kernels;
+    unsigned long long last_use;
+};
+
+}  // namespace
+
+struct sf_context {
+    Geom g;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int arith = SF_ARITH_STRICT;
+    int sweeps_opt = 0;
+    int use_graph = 1;
+    int force_generic = 0;
+    int chunk_rows = 0;
+    float *scratch = nullptr;        // lin_solve ping-pong partner
+    float *red_f = nullptr;          // reduction outputs
+    double *red_d = nullptr;
+    unsigned long long launches = 0;
+    unsigned long long tick = 0;
+    bool capturing = false;
+    std::string err;
+    std::vector<GraphEntry> graphs;
+    // sf_step_host resources
+    float *stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+int fail(sf_context *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+#define SF_CUDA(ctx, call)                                                       \
+    do {                                                                         \
+        cudaError_t e_ = (call);                                                 \
+        if (e_ != cudaSuccess) return fail(ctx, SF_ERR_CUDA, #call, e_);         \
+    } while (0)
+#define SF_REQUIRE(ctx, cond, msg)                                               \
+    do {                                                                         \
+        if (!(cond)) return fail(ctx, SF_ERR_INVALID, msg);                      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+size_t field_cells(const sf_context *c) { return (size_t)c->g.rows * (size_t)c->g.G; }
+bool is_full_grid(const sf_context *c) { return c->g.own_lo == 0 && c->g.own_hi == c->g.G; }
+
+int ensure_scratch(sf_context *c)
+{
+    if (!c->scratch) SF_CUDA(c, cudaMalloc(&c->scratch, field_cells(c) * sizeof(float)));
+    if (!c->red_f) {
+        SF_CUDA(c, cudaMalloc(&c->red_f, sizeof(float)));
+        SF_CUDA(c, cudaMalloc(&c->red_d, sizeof(double)));
+    }
+    return SF_OK;
+}
+
+int arith_mode(const sf_context *c, float alpha, float beta)
+{
+    if (alpha == 1.0f && beta == 4.0f) return MODE_PRESSURE;   // exact identity, see jacobi_cell
+    return c->arith == SF_ARITH_FAST ? MODE_FAST : MODE_STRICT;
+}
+
+int default_sweeps(const sf_context *c)
+{
+    if (c->sweeps_opt >= 1 && c->sweeps_opt <= 8) return c->sweeps_opt;
+    return 8;
+}
+
+// Split `iters` sweeps into launches of at most T sweeps.  The lin_solve ping-pongs between x and
+// the scratch field, so an EVEN number of launches leaves the result in x without a copy.
+std::vector<int> plan_launches(int iters, int T)
+{
+    int L = (iters + T - 1) / T;
+    if ((L & 1) && L + 1 <= iters) ++L;
+    std::vector<int> plan(L, iters / L);
+    for (int k = 0; k < iters % L; ++k) ++plan[k];
+    return plan;
+}
+
+int one_jacobi_launch(sf_context *c, int b, float *xout, const float *xin, const float *x0, float alpha, float beta,
+                      int sweeps, int out_lo, int out_hi, int zero_guess)
+{
+    JacobiLaunch L;
+    L.xin = xin; L.rhs = x0; L.xout = xout;
+    L.alpha = alpha; L.beta = beta; L.b = b; L.sweeps = sweeps;
+    L.mode = arith_mode(c, alpha, beta);
+    L.out_lo = out_lo; L.out_hi = out_hi;
+    L.chunk_rows = c->chunk_rows;
+    L.zero_guess = zero_guess;
+    const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
+    if (stream_ok) {
+        SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, c->stream));
+    } else {
+        SF_REQUIRE(c, sweeps == 1, "generic Jacobi kernel does one sweep per launch");
+        if (zero_guess) {
+            // generic kernel always reads xin
+            SF_CUDA(c, cudaMemsetAsync(const_cast<float *>(xin), 0, field_cells(c) * sizeof(float), c->stream));
+        }
+        SF_CUDA(c, launch_jacobi_generic(c->g, L, c->stream));
+    }
+    ++c->launches;
+    return SF_OK;
+}
+
+// lin_solve: result always ends in x.
+int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess)
+{
+    int rc = ensure_scratch(c);
+    if (rc) return rc;
+    const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
+    const std::vector<int> plan = plan_launches(iters, stream_ok ? default_sweeps(c) : 1);
+    float *cur = x, *nxt = c->scratch;
+    for (size_t k = 0; k < plan.size(); ++k) {
+        rc = one_jacobi_launch(c, b, nxt, cur, x0, alpha, beta, plan[k], c->g.own_lo, c->g.own_hi, zero_guess && k == 0);
+        if (rc) return rc;
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    if (cur != x) SF_CUDA(c, cudaMemcpyAsync(x, cur, field_cells(c) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    return SF_OK;
+}
+
+int check_multi_launch_ok(sf_context *c, int iters)
+{
+    if (is_full_grid(c)) return SF_OK;
+    const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
+    const int L = (int)plan_launches(iters, stream_ok ? default_sweeps(c) : 1).size();
+    if (L > 1)
+        return fail(c, SF_ERR_UNSUPPORTED,
+                    "slab context: a lin_solve of several launches needs a halo exchange between launches; "
+                    "drive it with sf_jacobi_launch");
+    return SF_OK;
+}
+
+// ---- step bodies (enqueue only) --------------------------------------------------------------
+int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters)
+{
+    float *xs[1] = {x};
+    const float *ss[1] = {x0};
+    SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->stream));
+    ++c->launches;
+    const float fN = (float)c->g.N;
+    float alpha = dt * diff;      // FluidSequential.c:179, left to right in binary32
+    alpha = alpha * fN;
+    alpha = alpha * fN;
+    float beta = 4.0f * alpha;    // :180
+    beta = 1.0f + beta;
+    int rc = lin_solve(c, 0, x0, x, alpha, beta, iters, 0);   // SWAP; diffuse(0, x, x0): solves into the old x0
+    if (rc) return rc;
+    SF_CUDA(c, launch_advect(c->g, 0, x, x0, u, v, dt, c->stream));   // SWAP; advect(0, x, x0, u, v)
+    ++c->launches;
+    return SF_OK;
+}
+
+int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters)
+{
+    // the streaming lin_solve can start from an implicit zero guess, so p need not be written here
+    const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
+    SF_CUDA(c, launch_divergence(c->g, u, v, p, div, stream_ok ? 0 : 1, c->stream));
+    ++c->launches;
+    int rc = lin_solve(c, 0, p, div, 1.0f, 4.0f, iters, stream_ok ? 1 : 0);
+    if (rc) return rc;
+    SF_CUDA(c, launch_last_project(c->g, u, v, p, c->stream));
+    ++c->launches;
+    return SF_OK;
+}
+
+int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
+{
+    float *xs[2] = {u, v};
+    const float *ss[2] = {u0, v0};
+    SF_CUDA(c, launch_add_source(c->g, 2, xs, ss, dt, c->stream));
+    ++c->launches;
+    const float fN = (float)c->g.N;
+    float alpha = dt * visc;      // :199
+    alpha = alpha * fN;
+    alpha = alpha * fN;
+    float beta = 4.0f * alpha;    // :200
+    beta = 1.0f + beta;
+    int rc = lin_solve(c, 1, u0, u, alpha, beta, iters, 0);            // :201-204
+    if (rc) return rc;
+    rc = lin_solve(c, 2, v0, v, alpha, beta, iters, 0);                // :209-210
+    if (rc) return rc;
+    rc = enqueue_project(c, u0, v0, u, v, iters);                      // :213-223 (p in u, div in v)
+    if (rc) return rc;
+    SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, c->stream));   // :228-237
+    ++c->launches;
+    return enqueue_project(c, u, v, u0, v0, iters);                    // :238-240 (p in u0, div in v0)
+}
+
+// ---- CUDA graph cache ------------------------------------------------------------------------
+template <class Body>
+int run_graphed(sf_context *c, const GraphKey &key, Body body)
+{
+    if (!c->use_graph || c->capturing) return body();
+    ++c->tick;
+    GraphEntry *seen = nullptr;
+    for (auto &e : c->graphs)
+        if (e.key == key) {
+            e.last_use = c->tick;
+            if (e.exec) {
+                SF_CUDA(c, cudaGraphLaunch(e.exec, c->stream));
+                c->launches += e.kernels;
+                return SF_OK;
+            }
+            seen = &e;
+        }
+    int rc = ensure_scratch(c);
+    if (rc) return rc;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(c->stream, &st);
+    if (st != cudaStreamCaptureStatusNone) return body();   // caller is capturing already
+    if (!seen) {
+        // First sighting of these arguments: launch directly (this also loads the kernels' modules
+        // outside of any capture); the second call with the same arguments captures the graph.
+        if (c->graphs.size() >= 16) {   // evict least recently used
+            size_t victim = 0;
+            for (size_t k = 1; k < c->graphs.size(); ++k)
+                if (c->graphs[k].last_use < c->graphs[victim].last_use) victim = k;
+            if (c->graphs[victim].exec) { cudaGraphExecDestroy(c->graphs[victim].exec); cudaGraphDestroy(c->graphs[victim].graph); }
+            c->graphs.erase(c->graphs.begin() + victim);
+        }
+        c->graphs.push_back(GraphEntry{key, nullptr, nullptr, 0, c->tick});
+        return body();
+    }
+    const unsigned long long before = c->launches;
+    c->capturing = true;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { c->capturing = false; return fail(c, SF_ERR_CUDA, "cudaStreamBeginCapture", e); }
+    rc = body();
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(c->stream, &graph);
+    c->capturing = false;
+    const unsigned long long kernels = c->launches - before;
+    c->launches = before;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(c, SF_ERR_CUDA, "cudaStreamEndCapture", e);
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail(c, SF_ERR_CUDA, "cudaGraphInstantiate", e); }
+    seen->exec = exec; seen->graph = graph; seen->kernels = kernels;
+    SF_CUDA(c, cudaGraphLaunch(exec, c->stream));
+    c->launches += kernels;
+    return SF_OK;
+}
+
+GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const void *> ptrs, float f0, float f1, float f2, int iters)
+{
+    GraphKey k;
+    std::memset(&k, 0, sizeof(k));
+    k.kind = kind;
+    int n = 0;
+    for (const void *p : ptrs) k.p[n++] = p;
+    k.f[0] = f0; k.f[1] = f1; k.f[2] = f2;
+    k.iters = iters;
+    k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
+    return k;
+}
+
+int create_common(sf_context **out, int N, int device, void *stream, bool own_stream, int row_lo, int row_hi, int halo)
+{
+    if (!out) return SF_ERR_INVALID;
+    *out = nullptr;
+    if (N < 1 || N > (1 << 24) - 2) return SF_ERR_INVALID;
+    const int G = N + 2;
+    if (row_lo < 0 || row_hi > G || row_hi <= row_lo || halo < 0) return SF_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SF_ERR_CUDA;
+    sf_context *c = new (std::nothrow) sf_context();
+    if (!c) return SF_ERR_NOMEM;
+    c->g.N = N; c->g.G = G;
+    c->g.own_lo = row_lo; c->g.own_hi = row_hi;
+    c->g.row_base = row_lo - halo;
+    c->g.rows = row_hi - row_lo + 2 * halo;
+    c->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return SF_ERR_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    if (own_stream) {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SF_ERR_CUDA; }
+        c->own_stream = true;
+    } else {
+        c->stream = (cudaStream_t)stream;
+    }
+    *out = c;
+    return SF_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int sf_create(sf_context **out, int N, int device) { return create_common(out, N, device, nullptr, true, 0, N + 2, 0); }
+int sf_create_on_stream(sf_context **out, int N, int device, void *cuda_stream)
+{
+    return create_common(out, N, device, cuda_stream, false, 0, N + 2, 0);
+}
+int sf_create_slab(sf_context **out, int N, int device, void *cuda_stream, int row_lo, int row_hi, int halo)
+{
+    return create_common(out, N, device, cuda_stream, false, row_lo, row_hi, halo);
+}
+
+int sf_destroy(sf_context *c)
+{
+    if (!c) return SF_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &e : c->graphs) if (e.exec) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->red_f) cudaFree(c->red_f);
+    if (c->red_d) cudaFree(c->red_d);
+    for (auto &s : c->stage) if (s) cudaFree(s);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->h2d) cudaStreamDestroy(c->h2d);
+    if (c->d2h) cudaStreamDestroy(c->d2h);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SF_OK;
+}
+
+const char *sf_last_error_string(const sf_context *c) { return c ? c->err.c_str() : "null context"; }
+
+int sf_set_option(sf_context *c, int option, int value)
+{
+    if (!c) return SF_ERR_INVALID;
+    switch (option) {
+        case SF_OPT_ARITHMETIC: SF_REQUIRE(c, value == 0 || value == 1, "arithmetic: 0 strict / 1 fast"); c->arith = value; break;
+        case SF_OPT_SWEEPS_PER_LAUNCH: SF_REQUIRE(c, value >= 0 && value <= 8, "sweeps per launch: 0..8"); c->sweeps_opt = value; break;
+        case SF_OPT_USE_GRAPH: c->use_graph = value ? 1 : 0; break;
+        case SF_OPT_FORCE_GENERIC: c->force_generic = value ? 1 : 0; break;
+        case SF_OPT_CHUNK_ROWS: SF_REQUIRE(c, value >= 0, "chunk rows >= 0"); c->chunk_rows = value; break;
+        default: return fail(c, SF_ERR_INVALID, "unknown option");
+    }
+    return SF_OK;
+}
+
+int sf_get_option(const sf_context *c, int option, int *value)
+{
+    if (!c || !value) return SF_ERR_INVALID;
+    switch (option) {
+        case SF_OPT_ARITHMETIC: *value = c->arith; break;
+        case SF_OPT_SWEEPS_PER_LAUNCH: *value = c->sweeps_opt; break;
+        case SF_OPT_USE_GRAPH: *value = c->use_graph; break;
+        case SF_OPT_FORCE_GENERIC: *value = c->force_generic; break;
+        case SF_OPT_CHUNK_ROWS: *value = c->chunk_rows; break;
+        default: return SF_ERR_INVALID;
+    }
+    return SF_OK;
+}
+
+int sf_synchronize(sf_context *c)
+{
+    if (!c) return SF_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+int sf_launch_count(const sf_context *c, unsigned long long *count)
+{
+    if (!c || !count) return SF_ERR_INVALID;
+    *count = c->launches;
+    return SF_OK;
+}
+
+size_t sf_field_bytes(const sf_context *c) { return c ? field_cells(c) * sizeof(float) : 0; }
+
+int sf_alloc_field(sf_context *c, float **dev_field)
+{
+    if (!c || !dev_field) return SF_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, cudaMalloc(dev_field, field_cells(c) * sizeof(float)));
+    SF_CUDA(c, cudaMemsetAsync(*dev_field, 0, field_cells(c) * sizeof(float), c->stream));
+    return SF_OK;
+}
+
+int sf_free_field(sf_context *c, float *dev_field)
+{
+    if (!c) return SF_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    SF_CUDA(c, cudaFree(dev_field));
+    return SF_OK;
+}
+
+int sf_upload(sf_context *c, float *dev_field, const float *host_field)
+{
+    if (!c || !dev_field || !host_field) return SF_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, cudaMemcpyAsync(dev_field, host_field, field_cells(c) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    return SF_OK;
+}
+
+int sf_download(sf_context *c, float *host_field, const float *dev_field)
+{
+    if (!c || !dev_field || !host_field) return SF_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, cudaMemcpyAsync(host_field, dev_field, field_cells(c) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+int sf_set_bnd(sf_context *c, int b, float *x)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, x && b >= 0 && b <= 2, "set_bnd: null field or b not in 0..2");
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, launch_set_bnd(c->g, b, x, c->stream));
+    ++c->launches;
+    return SF_OK;
+}
+
+int sf_add_source(sf_context *c, float *x, const float *s, float dt)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, x && s, "add_source: null field");
+    DeviceGuard guard(c->device);
+    float *xs[1] = {x};
+    const float *ss[1] = {s};
+    SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->stream));
+    ++c->launches;
+    return SF_OK;
+}
+
+int sf_diffuse(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, x && x0 && x != x0, "diffuse: null or aliased fields");
+    SF_REQUIRE(c, b >= 0 && b <= 2, "diffuse: b not in 0..2");
+    SF_REQUIRE(c, iters >= 1, "diffuse: iters < 1");
+    DeviceGuard guard(c->device);
+    int rc = check_multi_launch_ok(c, iters);
+    if (rc) return rc;
+    return lin_solve(c, b, x, x0, alpha, beta, iters, 0);
+}
+
+int sf_advect(sf_context *c, int b, float *d, const float *d0, const float *u, const float *v, float dt)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, d && d0 && u && v && d != d0 && d != u && d != v, "advect: null fields or output aliases an input");
+    SF_REQUIRE(c, b >= 0 && b <= 2, "advect: b not in 0..2");
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, launch_advect(c->g, b, d, d0, u, v, dt, c->stream));
+    ++c->launches;
+    return SF_OK;
+}
+
+int sf_compute_divergence_and_pressure(sf_context *c, const float *u, const float *v, float *p, float *div)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, u && v && p && div && p != div && p != u && p != v && div != u && div != v, "divergence: null or aliased fields");
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, launch_divergence(c->g, u, v, p, div, 1, c->stream));
+    ++c->launches;
+    return SF_OK;
+}
+
+int sf_last_project(sf_context *c, float *u, float *v, const float *p, const float *div)
+{
+    (void)div;   // unused by the reference too (FluidSequential.c:161-173)
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, u && v && p && u != v && p != u && p != v, "lastProject: null or aliased fields");
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, launch_last_project(c->g, u, v, p, c->stream));
+    ++c->launches;
+    return SF_OK;
+}
+
+int sf_project(sf_context *c, float *u, float *v, float *p, float *div, int iters)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, u && v && p && div && iters >= 1, "project: null field or iters < 1");
+    DeviceGuard guard(c->device);
+    int rc = check_multi_launch_ok(c, iters);
+    if (rc) return rc;
+    return enqueue_project(c, u, v, p, div, iters);
+}
+
+int sf_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, x && x0 && u && v && x != x0, "dens_step: null or aliased fields");
+    SF_REQUIRE(c, iters >= 1, "dens_step: iters < 1");
+    DeviceGuard guard(c->device);
+    int rc = check_multi_launch_ok(c, iters);
+    if (rc) return rc;
+    const GraphKey key = make_key(c, 1, {x, x0, u, v}, diff, dt, 0.f, iters);
+    return run_graphed(c, key, [&] { return enqueue_dens_step(c, x, x0, u, v, diff, dt, iters); });
+}
+
+int sf_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, u && v && u0 && v0 && u != v && u != u0 && u != v0 && v != u0 && v != v0 && u0 != v0, "vel_step: null or aliased fields");
+    SF_REQUIRE(c, iters >= 1, "vel_step: iters < 1");
+    DeviceGuard guard(c->device);
+    int rc = check_multi_launch_ok(c, iters);
+    if (rc) return rc;
+    const GraphKey key = make_key(c, 2, {u, v, u0, v0}, visc, dt, 0.f, iters);
+    return run_graphed(c, key, [&] { return enqueue_vel_step(c, u, v, u0, v0, visc, dt, iters); });
+}
+
+int sf_step(sf_context *c, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev, float visc,
+            float diff, float dt, int iters)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, dens && dens_prev && u && u_prev && v && v_prev, "step: null field");
+    SF_REQUIRE(c, iters >= 1, "step: iters < 1");
+    DeviceGuard guard(c->device);
+    int rc = check_multi_launch_ok(c, iters);
+    if (rc) return rc;
+    const GraphKey key = make_key(c, 3, {dens, dens_prev, u, u_prev, v, v_prev}, visc, diff, dt, iters);
+    return run_graphed(c, key, [&] {
+        int r = enqueue_vel_step(c, u, v, u_prev, v_prev, visc, dt, iters);   // FluidSequential.c:305
+        if (r) return r;
+        return enqueue_dens_step(c, dens, dens_prev, u, v, diff, dt, iters);  // :306
+    });
+}
+
+int sf_step_host(sf_context *c, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev,
+                 float visc, float diff, float dt, int iters, int download_scratch)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, dens && dens_prev && u && u_prev && v && v_prev, "step_host: null field");
+    SF_REQUIRE(c, iters >= 1, "step_host: iters < 1");
+    SF_REQUIRE(c, is_full_grid(c), "step_host: full-grid contexts only");
+    DeviceGuard guard(c->device);
+    const size_t bytes = field_cells(c) * sizeof(float);
+    if (!c->h2d) {
+        SF_CUDA(c, cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+        SF_CUDA(c, cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+        for (auto &e : c->ev) SF_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &s : c->stage) SF_CUDA(c, cudaMalloc(&s, bytes));
+    }
+    int rc = ensure_scratch(c);
+    if (rc) return rc;
+    float *d_dens = c->stage[0], *d_dens0 = c->stage[1], *d_u = c->stage[2], *d_u0 = c->stage[3], *d_v = c->stage[4], *d_v0 = c->stage[5];
+    // the previous call's work on the compute stream must be done before staging is overwritten
+    SF_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    SF_CUDA(c, cudaStreamWaitEvent(c->h2d, c->ev[5], 0));
+    // velocity inputs first: vel_step can start while the density fields are still in flight
+    SF_CUDA(c, cudaMemcpyAsync(d_u, u, bytes, cudaMemcpyHostToDevice, c->h2d));
+    SF_CUDA(c, cudaMemcpyAsync(d_u0, u_prev, bytes, cudaMemcpyHostToDevice, c->h2d));
+    SF_CUDA(c, cudaMemcpyAsync(d_v, v, bytes, cudaMemcpyHostToDevice, c->h2d));
+    SF_CUDA(c, cudaMemcpyAsync(d_v0, v_prev, bytes, cudaMemcpyHostToDevice, c->h2d));
+    SF_CUDA(c, cudaEventRecord(c->ev[0], c->h2d));
+    SF_CUDA(c, cudaMemcpyAsync(d_dens, dens, bytes, cudaMemcpyHostToDevice, c->h2d));
+    SF_CUDA(c, cudaMemcpyAsync(d_dens0, dens_prev, bytes, cudaMemcpyHostToDevice, c->h2d));
+    SF_CUDA(c, cudaEventRecord(c->ev[1], c->h2d));
+
+    SF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[0], 0));
+    rc = sf_vel_step(c, d_u, d_v, d_u0, d_v0, visc, dt, iters);
+    if (rc) return rc;
+    SF_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    SF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[1], 0));
+    rc = sf_dens_step(c, d_dens, d_dens0, d_u, d_v, diff, dt, iters);
+    if (rc) return rc;
+    SF_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+
+    // velocity results drain while dens_step runs
+    SF_CUDA(c, cudaStreamWaitEvent(c->d2h, c->ev[2], 0));
+    SF_CUDA(c, cudaMemcpyAsync(u, d_u, bytes, cudaMemcpyDeviceToHost, c->d2h));
+    SF_CUDA(c, cudaMemcpyAsync(v, d_v, bytes, cudaMemcpyDeviceToHost, c->d2h));
+    if (download_scratch) {
+        SF_CUDA(c, cudaMemcpyAsync(u_prev, d_u0, bytes, cudaMemcpyDeviceToHost, c->d2h));
+        SF_CUDA(c, cudaMemcpyAsync(v_prev, d_v0, bytes, cudaMemcpyDeviceToHost, c->d2h));
+    }
+    SF_CUDA(c, cudaStreamWaitEvent(c->d2h, c->ev[3], 0));
+    SF_CUDA(c, cudaMemcpyAsync(dens, d_dens, bytes, cudaMemcpyDeviceToHost, c->d2h));
+    if (download_scratch) SF_CUDA(c, cudaMemcpyAsync(dens_prev, d_dens0, bytes, cudaMemcpyDeviceToHost, c->d2h));
+    SF_CUDA(c, cudaStreamSynchronize(c->d2h));
+    return SF_OK;
+}
+
+int sf_init_synthetic(sf_context *c, uint64_t seed, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, dens && dens_prev && u && u_prev && v && v_prev, "init_synthetic: null field");
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, launch_init(c->g, seed, dens, dens_prev, u, u_prev, v, v_prev, c->stream));
+    ++c->launches;
+    return SF_OK;
+}
+
+int sf_init_sources(sf_context *c, uint64_t seed, float *dens_prev, float *u_prev, float *v_prev)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, dens_prev && u_prev && v_prev, "init_sources: null field");
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, launch_init(c->g, seed, nullptr, dens_prev, nullptr, u_prev, nullptr, v_prev, c->stream));
+    ++c->launches;
+    return SF_OK;
+}
+
+int sf_reduce_max_abs(sf_context *c, const float *x, float *host_out)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, x && host_out, "reduce_max_abs: null argument");
+    DeviceGuard guard(c->device);
+    int rc = ensure_scratch(c);
+    if (rc) return rc;
+    SF_CUDA(c, launch_max_abs(c->g, x, c->red_f, c->stream));
+    ++c->launches;
+    SF_CUDA(c, cudaMemcpyAsync(host_out, c->red_f, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+int sf_residual_l2(sf_context *c, const float *x, const float *x0, float alpha, float beta, double *host_out)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, x && x0 && host_out, "residual_l2: null argument");
+    DeviceGuard guard(c->device);
+    int rc = ensure_scratch(c);
+    if (rc) return rc;
+    SF_CUDA(c, launch_residual(c->g, x, x0, alpha, beta, c->red_d, c->stream));
+    ++c->launches;
+    double sumsq = 0.0;
+    SF_CUDA(c, cudaMemcpyAsync(&sumsq, c->red_d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    *host_out = sumsq;   // caller takes sqrt after summing over slabs
+    return SF_OK;
+}
+
+int sf_halo_rows_needed(const sf_context *c, int *rows)
+{
+    if (!c || !rows) return SF_ERR_INVALID;
+    *rows = default_sweeps(c);
+    return SF_OK;
+}
+
+int sf_jacobi_launch(sf_context *c, int b, float *xout, const float *xin, const float *x0, float alpha, float beta,
+                     int sweeps, int out_lo, int out_hi)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, xout && xin && x0 && xout != xin && xout != x0, "jacobi_launch: null or aliased fields");
+    SF_REQUIRE(c, b >= 0 && b <= 2, "jacobi_launch: b not in 0..2");
+    SF_REQUIRE(c, sweeps >= 1 && sweeps <= 8, "jacobi_launch: sweeps not in 1..8");
+    if (out_lo < 0 && out_hi < 0) { out_lo = c->g.own_lo; out_hi = c->g.own_hi; }
+    SF_REQUIRE(c, out_lo >= c->g.own_lo && out_hi <= c->g.own_hi && out_lo < out_hi, "jacobi_launch: rows outside the owned range");
+    {   // rows the launch reads: [max(out_lo - sweeps, 0), min(out_hi - 1 + sweeps, G - 1)]
+        const int rd_lo = out_lo - sweeps > 0 ? out_lo - sweeps : 0;
+        const int rd_hi = out_hi - 1 + sweeps < c->g.G - 1 ? out_hi - 1 + sweeps : c->g.G - 1;
+        SF_REQUIRE(c, rd_lo >= c->g.row_base && rd_hi < c->g.row_base + c->g.rows, "jacobi_launch: halo rows too few for this many sweeps");
+    }
+    DeviceGuard guard(c->device);
+    return one_jacobi_launch(c, b, xout, xin, x0, alpha, beta, sweeps, out_lo, out_hi, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// Jacobi lin_solve kernels (replaces the reference's diffuse(): FluidSequential.c:85-104, and the
+// one-sweep-per-launch diffuseOnGPU + host loop, naivePar/FluidParallelBlockPerElement-Naive.cu:121-144,
+// 261-264).  NOT a port: the reference goes to DRAM once per sweep; here T sweeps are fused per
+// launch (temporal blocking) so each field crosses HBM once per T sweeps.
+//
+// jacobi_stream_kernel<T, MODE>  -- the product path (grid width G % 4 == 0)
+//   * Each WARP owns a band of 128 columns (one float4 per lane) and streams down the rows of a
+//     row chunk.  Sweep level t+1 of row a is computed as soon as level t of row a+1 exists, so a
+//     warp carries a T-deep register pipeline: per level two previous rows (2 x float4 per lane).
+//     Left/right neighbours come from the adjacent lanes by warp shuffle; warps never synchronise
+//     with each other (no __syncthreads, no shared-memory exchange): the band carries an 8-column
+//     halo on each side that absorbs the T <= 8 columns invalidated by the missing neighbours.
+//   * Rows of x (level 0) and of the right-hand side x0 are staged global -> shared with
+//     cp.async (LDGSTS, 16 B per lane, L2-only) into per-warp rings several rows ahead, so DRAM
+//     latency is hidden without holding prefetch registers; the rhs ring is read once per level.
+//   * set_bnd is fused: a wall cell at level t+1 is +-(the adjacent interior cell at level t+1),
+//     applied in registers (the wall columns 0 and N+1 share a float4 with columns 1 / N because
+//     G % 4 == 0); wall rows are patched into the next level's window when row 1 / row N are
+//     produced.  Corners are never read by the 5-point stencil and are written with the last level.
+//   * Arithmetic per cell is jacobi_cell<MODE> (sf_common.cuh): same operand order as the reference.
+//
+// jacobi_generic_kernel<MODE> -- one sweep per launch, one thread per cell, any G (fallback for
+//   widths that are not a multiple of 4, e.g. the literal N=128 -> G=130).
+#include "sf_common.cuh"
+
+namespace sf {
+
+namespace {
+
+constexpr int BAND_W = 128;   // columns per warp (32 lanes x float4)
+constexpr int HALO_X = 8;     // band halo columns on each side (>= max T, multiple of 4)
+constexpr int VALID_W = BAND_W - 2 * HALO_X;  // 112 output columns per band
+constexpr int WPC = 4;        // warps per CTA (adjacent bands, same row chunk)
+constexpr int RING_X = 8;     // x-row ring slots per warp (power of two, > PREFETCH)
+constexpr int RING_R = 16;    // rhs-row ring slots per warp (power of two, >= T + PREFETCH + 1)
+constexpr int PREFETCH = 5;   // rows in flight ahead of the row being consumed
+
+struct StreamArgs {
+    const float *xin, *rhs;
+    float *xout;
+    int G, N, row_base;
+    int a_lo, a_hi;      // interior output rows [a_lo, a_hi), subset of [1, N+1)
+    int write_top, write_bot;
+    int chunk_rows, nbands;
+    int zero_guess;
+    float alpha, beta, rbeta, sx, sy;
+};
+
+__device__ __forceinline__ void cp_async16(float4 *smem_dst, const float *gmem_src, int src_bytes)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory"); }
+
+__device__ __forceinline__ float4 scale4(float4 v, float s)
+{
+    return make_float4(__fmul_rn(v.x, s), __fmul_rn(v.y, s), __fmul_rn(v.z, s), __fmul_rn(v.w, s));
+}
+
+// One pipeline tick: row `s` of level 0 enters; for t = 0..T-1 level t+1 of row s-t-1 is produced.
+// PAR selects which of the two window slots holds the older row (compile-time, so the windows
+// stay in registers with no moves).  Returns level T of row s-T in `out`.
+template <int T, int MODE, int PAR>
+__device__ __forceinline__ void pipeline_tick(const StreamArgs &A, int s, float4 in, float4 (&W0)[T], float4 (&W1)[T],
+                                              const float4 *rring, bool ownsL, bool ownsR, float4 &out)
+{
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        float4 &older = PAR ? W1[t] : W0[t];   // row a-1 of level t
+        float4 &newer = PAR ? W0[t] : W1[t];   // row a   of level t
+        const int a = s - t - 1;               // row produced at level t+1
+        const float4 up = older, mid = newer, dn = in;
+        const float4 r = rring[(a & (RING_R - 1)) * 32];
+        const float lft = __shfl_up_sync(0xffffffffu, mid.w, 1);
+        const float rgt = __shfl_down_sync(0xffffffffu, mid.x, 1);
+        float4 o;
+        o.x = jacobi_cell<MODE>(lft, mid.y, up.x, dn.x, r.x, A.alpha, A.beta, A.rbeta);
+        o.y = jacobi_cell<MODE>(mid.x, mid.z, up.y, dn.y, r.y, A.alpha, A.beta, A.rbeta);
+        o.z = jacobi_cell<MODE>(mid.y, mid.w, up.z, dn.z, r.z, A.alpha, A.beta, A.rbeta);
+        o.w = jacobi_cell<MODE>(mid.z, rgt, up.w, dn.w, r.w, A.alpha, A.beta, A.rbeta);
+        // wall columns: x[row][0] = sx * x[row][1], x[row][N+1] = sx * x[row][N]
+        if (ownsL) o.x = __fmul_rn(A.sx, o.y);
+        if (ownsR) o.w = __fmul_rn(A.sx, o.z);
+        // retire the oldest row of level t: its slot takes the incoming row
+        older = dn;
+        if (t + 1 < T) {
+            // wall rows of level t+1 live in the NEXT level's window
+            float4 &nx_newer = PAR ? W0[t + 1] : W1[t + 1];  // row a-1 of level t+1 at this point
+            if (a == A.N + 1) o = scale4(nx_newer, A.sy);     // row N+1 = sy * row N
+            if (a == 1) nx_newer = scale4(o, A.sy);           // row 0   = sy * row 1
+        }
+        in = o;
+    }
+    out = in;
+}
+
+template <int T, int MODE>
+__global__ void __launch_bounds__(WPC * 32) jacobi_stream_kernel(const StreamArgs A)
+{
+    extern __shared__ float4 ring[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int band = blockIdx.x * WPC + warp;
+    if (band >= A.nbands) return;
+    const int a_lo = A.a_lo + blockIdx.y * A.chunk_rows;
+    const int a_hi = min(a_lo + A.chunk_rows, A.a_hi);
+    if (a_lo >= a_hi) return;
+
+    const int c = band * VALID_W - HALO_X + 4 * lane;     // first of this lane's 4 columns
+    const bool indom = (c >= 0) && (c + 4 <= A.G);
+    const bool ownsL = (c == 0), ownsR = (c + 4 == A.G);
+    const bool st_ok = indom && lane >= HALO_X / 4 && lane < 32 - HALO_X / 4;
+    const int cc = indom ? c : 0;
+    const int nbytes = indom ? 16 : 0;
+
+    float4 *xring = ring + (size_t)warp * (RING_X + RING_R) * 32 + lane;
+    float4 *rring = xring + RING_X * 32;
+
+    const int s_lo = max(a_lo - T, 0);
+    const int s_hi = a_hi - 1 + T;                 // inclusive
+    const int load_hi = min(s_hi, A.G - 1);
+    const float *xsrc = A.xin + cc;
+    const float *rsrc = A.rhs + cc;
+    const size_t pitch = (size_t)A.G;
+    const bool zero_guess = A.zero_guess != 0;
+
+    auto issue = [&](int row) {
+        if (row <= load_hi) {
+            const size_t off = (size_t)(row - A.row_base) * pitch;
+            if (!zero_guess) cp_async16(xring + (row & (RING_X - 1)) * 32, xsrc + off, nbytes);
+            cp_async16(rring + (row & (RING_R - 1)) * 32, rsrc + off, nbytes);
+        }
+        cp_async_commit();
+    };
+
+    float4 W0[T], W1[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) W0[t] = W1[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll
+    for (int k = 0; k < PREFETCH; ++k) issue(s_lo + k);
+
+    float *orow = A.xout + cc;
+    auto emit = [&](int a, const float4 &o) {
+        if (a < a_lo || a >= a_hi) return;
+        float4 *dst = reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch);
+        if (st_ok) *dst = o;
+        if (a == 1 && A.write_top) {
+            float4 w = scale4(o, A.sy);
+            if (ownsL) w.x = __fmul_rn(0.5f, __fadd_rn(w.y, o.x));   // x[0][0] = .5*(x[0][1] + x[1][0])
+            if (ownsR) w.w = __fmul_rn(0.5f, __fadd_rn(w.z, o.w));   // x[0][N+1] = .5*(x[0][N] + x[1][N+1])
+            if (st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(0 - A.row_base) * pitch) = w;
+        }
+        if (a == A.N && A.write_bot) {
+            float4 w = scale4(o, A.sy);
+            if (ownsL) w.x = __fmul_rn(0.5f, __fadd_rn(w.y, o.x));   // x[N+1][0] = .5*(x[N+1][1] + x[N][0])
+            if (ownsR) w.w = __fmul_rn(0.5f, __fadd_rn(w.z, o.w));   // x[N+1][N+1] = .5*(x[N+1][N] + x[N][N+1])
+            if (st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(A.N + 1 - A.row_base) * pitch) = w;
+        }
+    };
+
+    int s = s_lo;
+    while (s <= s_hi) {
+        {
+            issue(s + PREFETCH);
+            cp_async_wait<PREFETCH>();
+            float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!zero_guess && s <= load_hi) in = xring[(s & (RING_X - 1)) * 32];
+            float4 o;
+            pipeline_tick<T, MODE, 0>(A, s, in, W0, W1, rring, ownsL, ownsR, o);
+            emit(s - T, o);
+            ++s;
+        }
+        if (s > s_hi) break;
+        {
+            issue(s + PREFETCH);
+            cp_async_wait<PREFETCH>();
+            float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!zero_guess && s <= load_hi) in = xring[(s & (RING_X - 1)) * 32];
+            float4 o;
+            pipeline_tick<T, MODE, 1>(A, s, in, W0, W1, rring, ownsL, ownsR, o);
+            emit(s - T, o);
+            ++s;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---- generic fallback: one sweep, one thread per interior cell, any G -----------------------
+template <int MODE>
+__global__ void jacobi_generic_kernel(const float *__restrict__ xin, const float *__restrict__ rhs,
+                                      float *__restrict__ xout, Geom g, int a_lo, int a_hi, int write_top,
+                                      int write_bot, float alpha, float beta, float rbeta, float sx, float sy)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y + a_lo;
+    if (col > g.N || row >= a_hi) return;
+    const size_t G = (size_t)g.G;
+    const size_t i = (size_t)(row - g.row_base) * G + col;
+    const float o = jacobi_cell<MODE>(xin[i - 1], xin[i + 1], xin[i - G], xin[i + G], rhs[i], alpha, beta, rbeta);
+    xout[i] = o;
+    const float wx = __fmul_rn(sx, o), wy = __fmul_rn(sy, o);
+    const bool L = (col == 1), R = (col == g.N);
+    const bool Tp = (row == 1) && write_top, Bt = (row == g.N) && write_bot;
+    if (L) xout[i - 1] = wx;
+    if (R) xout[i + 1] = wx;
+    if (Tp) xout[i - G] = wy;
+    if (Bt) xout[i + G] = wy;
+    if (L && Tp) xout[i - G - 1] = __fmul_rn(0.5f, __fadd_rn(wy, wx));
+    if (R && Tp) xout[i - G + 1] = __fmul_rn(0.5f, __fadd_rn(wy, wx));
+    if (L && Bt) xout[i + G - 1] = __fmul_rn(0.5f, __fadd_rn(wy, wx));
+    if (R && Bt) xout[i + G + 1] = __fmul_rn(0.5f, __fadd_rn(wy, wx));
+}
+
+template <int T, int MODE>
+cudaError_t launch_stream_T(const StreamArgs &A, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static_assert((size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4) <= 48 * 1024,
+                  "ring fits the default 48 KB dynamic shared memory limit (no attribute call needed)");
+    jacobi_stream_kernel<T, MODE><<<grid, WPC * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_stream_mode(int T, const StreamArgs &A, dim3 grid, size_t smem, cudaStream_t st)
+{
+    switch (T) {
+        case 1: return launch_stream_T<1, MODE>(A, grid, smem, st);
+        case 2: return launch_stream_T<2, MODE>(A, grid, smem, st);
+        case 3: return launch_stream_T<3, MODE>(A, grid, smem, st);
+        case 4: return launch_stream_T<4, MODE>(A, grid, smem, st);
+        case 5: return launch_stream_T<5, MODE>(A, grid, smem, st);
+        case 6: return launch_stream_T<6, MODE>(A, grid, smem, st);
+        case 7: return launch_stream_T<7, MODE>(A, grid, smem, st);
+        case 8: return launch_stream_T<8, MODE>(A, grid, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+bool jacobi_stream_supported(const Geom &g) { return (g.G % 4) == 0 && g.G >= 4; }
+
+cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_count, cudaStream_t st)
+{
+    if (L.sweeps < 1 || L.sweeps > HALO_X) return cudaErrorInvalidValue;
+    StreamArgs A;
+    A.xin = L.xin; A.rhs = L.rhs; A.xout = L.xout;
+    A.G = g.G; A.N = g.N; A.row_base = g.row_base;
+    A.a_lo = max(L.out_lo, 1);
+    A.a_hi = min(L.out_hi, g.N + 1);
+    A.write_top = (L.out_lo == 0);
+    A.write_bot = (L.out_hi == g.G);
+    A.nbands = (g.G + VALID_W - 1) / VALID_W;
+    A.zero_guess = L.zero_guess;
+    A.alpha = L.alpha; A.beta = L.beta; A.rbeta = 1.0f / L.beta;
+    A.sx = (L.b == 1) ? -1.0f : 1.0f;
+    A.sy = (L.b == 2) ? -1.0f : 1.0f;
+    const int rows = A.a_hi - A.a_lo;
+    if (rows <= 0) return cudaSuccess;
+    const int ctas_x = (A.nbands + WPC - 1) / WPC;
+    int chunk = L.chunk_rows;
+    if (chunk <= 0) {
+        // aim at ~3 CTAs per SM in flight, but keep the redundant 2T halo rows under ~1/8 of a chunk
+        int want_chunks = (3 * sm_count + ctas_x - 1) / ctas_x;
+        chunk = (rows + want_chunks - 1) / want_chunks;
+        const int min_chunk = 16 * L.sweeps;
+        if (chunk < min_chunk) chunk = min_chunk;
+    }
+    if (chunk > rows) chunk = rows;
+    A.chunk_rows = chunk;
+    dim3 grid(ctas_x, (rows + chunk - 1) / chunk);
+    const size_t smem = (size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4);
+    switch (L.mode) {
+        case MODE_PRESSURE: return launch_stream_mode<MODE_PRESSURE>(L.sweeps, A, grid, smem, st);
+        case MODE_FAST: return launch_stream_mode<MODE_FAST>(L.sweeps, A, grid, smem, st);
+        default: return launch_stream_mode<MODE_STRICT>(L.sweeps, A, grid, smem, st);
+    }
+}
+
+cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStream_t st)
+{
+    if (L.sweeps != 1) return cudaErrorInvalidValue;
+    const int a_lo = max(L.out_lo, 1), a_hi = min(L.out_hi, g.N + 1);
+    if (a_hi <= a_lo) return cudaSuccess;
+    dim3 block(64, 4), grid((g.N + 63) / 64, (a_hi - a_lo + 3) / 4);
+    const float sx = (L.b == 1) ? -1.0f : 1.0f, sy = (L.b == 2) ? -1.0f : 1.0f, rb = 1.0f / L.beta;
+    const int wt = (L.out_lo == 0), wb = (L.out_hi == g.G);
+    switch (L.mode) {
+        case MODE_PRESSURE:
+            jacobi_generic_kernel<MODE_PRESSURE><<<grid, block, 0, st>>>(L.xin, L.rhs, L.xout, g, a_lo, a_hi, wt, wb, L.alpha, L.beta, rb, sx, sy);
+            break;
+        case MODE_FAST:
+            jacobi_generic_kernel<MODE_FAST><<<grid, block, 0, st>>>(L.xin, L.rhs, L.xout, g, a_lo, a_hi, wt, wb, L.alpha, L.beta, rb, sx, sy);
+            break;
+        default:
+            jacobi_generic_kernel<MODE_STRICT><<<grid, block, 0, st>>>(L.xin, L.rhs, L.xout, g, a_lo, a_hi, wt, wb, L.alpha, L.beta, rb, sx, sy);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace sf

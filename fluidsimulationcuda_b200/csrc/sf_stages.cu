@@ -1,0 +1,368 @@
+// Non-Jacobi stages of the stable-fluids step, each with set_bnd fused in (the thread that
+// produces an interior cell next to a wall also writes the wall cell, and the four threads at
+// the interior corners write the grid corners), so every field is read and written once per stage.
+// Reference semantics: FluidSequential.c:62-82 (set_bnd, add_source), :107-141 (advect),
+// :143-158 (computeDivergenceAndPressure), :161-173 (lastProject), :244-271 (initial condition).
+// All arithmetic uses __f*_rn intrinsics so nvcc cannot contract mul+add into FMA: results are
+// bit-identical to the reference's sequential build.
+#include "sf_common.cuh"
+
+namespace sf {
+namespace {
+
+struct Wall {
+    // which wall/corner cells the thread owning interior cell (row, col) must also write
+    bool L, R, T, B;
+};
+__device__ __forceinline__ Wall wall_of(const Geom &g, int row, int col)
+{
+    Wall w;
+    w.L = (col == 1);
+    w.R = (col == g.N);
+    w.T = (row == 1) && (g.own_lo == 0);
+    w.B = (row == g.N) && (g.own_hi == g.G);
+    return w;
+}
+// write interior value `o` at flat index i plus the wall/corner cells it determines (set_bnd(b))
+__device__ __forceinline__ void store_with_walls(float *x, size_t i, size_t G, float o, const Wall &w, float sx, float sy)
+{
+    x[i] = o;
+    if (w.L | w.R | w.T | w.B) {
+        const float wx = __fmul_rn(sx, o), wy = __fmul_rn(sy, o);
+        const float cn = __fmul_rn(0.5f, __fadd_rn(wy, wx));
+        if (w.L) x[i - 1] = wx;
+        if (w.R) x[i + 1] = wx;
+        if (w.T) x[i - G] = wy;
+        if (w.B) x[i + G] = wy;
+        if (w.L && w.T) x[i - G - 1] = cn;
+        if (w.R && w.T) x[i - G + 1] = cn;
+        if (w.L && w.B) x[i + G - 1] = cn;
+        if (w.R && w.B) x[i + G + 1] = cn;
+    }
+}
+
+// interior rows this slab produces
+__device__ __forceinline__ void interior_rows(const Geom &g, int &lo, int &hi)
+{
+    lo = max(g.own_lo, 1);
+    hi = min(g.own_hi, g.N + 1);
+}
+
+// ---- set_bnd ---------------------------------------------------------------------------------
+__global__ void set_bnd_kernel(float *x, Geom g, float sx, float sy)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;   // 1..N
+    if (k > g.N) return;
+    const size_t G = (size_t)g.G;
+    const int N = g.N;
+    const bool top = (g.own_lo == 0), bot = (g.own_hi == g.G);
+    if (k >= max(g.own_lo, 1) && k < min(g.own_hi, N + 1)) {   // side walls of owned row k
+        const size_t r = (size_t)(k - g.row_base) * G;
+        x[r] = __fmul_rn(sx, x[r + 1]);
+        x[r + N + 1] = __fmul_rn(sx, x[r + N]);
+    }
+    if (top) x[(size_t)(0 - g.row_base) * G + k] = __fmul_rn(sy, x[(size_t)(1 - g.row_base) * G + k]);
+    if (bot) x[(size_t)(N + 1 - g.row_base) * G + k] = __fmul_rn(sy, x[(size_t)(N - g.row_base) * G + k]);
+    // corners: computed from the interior values that define the adjacent wall cells, so no
+    // ordering between threads is needed (x[0][1] = sy*x[1][1], x[1][0] = sx*x[1][1], ...)
+    if (k == 1 || k == N) {
+        const int col = k, wc = (k == 1) ? 0 : N + 1;
+        if (top) {
+            const float a = x[(size_t)(1 - g.row_base) * G + col];
+            x[(size_t)(0 - g.row_base) * G + wc] = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(sy, a), __fmul_rn(sx, a)));
+        }
+        if (bot) {
+            const float a = x[(size_t)(N - g.row_base) * G + col];
+            x[(size_t)(N + 1 - g.row_base) * G + wc] = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(sy, a), __fmul_rn(sx, a)));
+        }
+    }
+}
+
+// ---- add_source: x += dt*s on every owned cell (ring included), up to 3 fields per launch ------
+struct AddSrcArgs {
+    float *x[3];
+    const float *s[3];
+    size_t first, count;   // flat range of owned cells (multiple of G)
+    float dt;
+    int vec;               // 1: first/count/pointers allow float4
+};
+__global__ void add_source_kernel(AddSrcArgs A)
+{
+    float *x = A.x[blockIdx.y];
+    const float *s = A.s[blockIdx.y];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (A.vec) {
+        float4 *x4 = reinterpret_cast<float4 *>(x + A.first);
+        const float4 *s4 = reinterpret_cast<const float4 *>(s + A.first);
+        const size_t n4 = A.count / 4;
+        for (; i < n4; i += stride) {
+            float4 a = x4[i];
+            const float4 b = __ldg(s4 + i);
+            a.x = __fadd_rn(a.x, __fmul_rn(A.dt, b.x));
+            a.y = __fadd_rn(a.y, __fmul_rn(A.dt, b.y));
+            a.z = __fadd_rn(a.z, __fmul_rn(A.dt, b.z));
+            a.w = __fadd_rn(a.w, __fmul_rn(A.dt, b.w));
+            x4[i] = a;
+        }
+    } else {
+        for (; i < A.count; i += stride) x[A.first + i] = __fadd_rn(x[A.first + i], __fmul_rn(A.dt, s[A.first + i]));
+    }
+}
+
+// ---- advect ------------------------------------------------------------------------------------
+// One thread per interior cell.  The gather is data dependent but spatially smooth (neighbouring
+// cells trace back to neighbouring sources), so a warp's four gathers land in a few 128-B lines.
+// NF = 1: d <- advect(b, d0 by u, v).  NF = 2: the two velocity components in one pass
+// (FluidSequential.c:232,237: advect(1,u,u0,u0,v0); advect(2,v,v0,u0,v0)) sharing the back-trace.
+template <int NF>
+__global__ void advect_kernel(float *__restrict__ dA, float *__restrict__ dB, const float *__restrict__ srcA,
+                              const float *__restrict__ srcB, const float *__restrict__ u, const float *__restrict__ v,
+                              Geom g, float dt0, int bA)
+{
+    int lo, hi;
+    interior_rows(g, lo, hi);
+    const int col = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y + lo;
+    if (col > g.N || row >= hi) return;
+    const size_t G = (size_t)g.G;
+    const size_t i = (size_t)(row - g.row_base) * G + col;
+    // FluidSequential.c:114-134
+    float px = __fsub_rn((float)col, __fmul_rn(dt0, u[i]));
+    float py = __fsub_rn((float)row, __fmul_rn(dt0, v[i]));
+    const float hiC = (float)g.N + 0.5f;
+    if (px < 0.5f) px = 0.5f;
+    if (px > hiC) px = hiC;
+    if (py < 0.5f) py = 0.5f;
+    if (py > hiC) py = hiC;
+    const int c0 = (int)px, r0 = (int)py;
+    const float wx1 = __fsub_rn(px, (float)c0), wx0 = __fsub_rn(1.0f, wx1);
+    const float wy1 = __fsub_rn(py, (float)r0), wy0 = __fsub_rn(1.0f, wy1);
+    const size_t j = (size_t)(r0 - g.row_base) * G + c0;
+    const Wall w = wall_of(g, row, col);
+    {
+        const float a00 = __ldg(srcA + j), a10 = __ldg(srcA + j + G), a01 = __ldg(srcA + j + 1), a11 = __ldg(srcA + j + G + 1);
+        const float colA = __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10));
+        const float colB = __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11));
+        const float o = __fadd_rn(__fmul_rn(wx0, colA), __fmul_rn(wx1, colB));
+        store_with_walls(dA, i, G, o, w, bA == 1 ? -1.0f : 1.0f, bA == 2 ? -1.0f : 1.0f);
+    }
+    if (NF == 2) {
+        const float a00 = __ldg(srcB + j), a10 = __ldg(srcB + j + G), a01 = __ldg(srcB + j + 1), a11 = __ldg(srcB + j + G + 1);
+        const float colA = __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10));
+        const float colB = __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11));
+        const float o = __fadd_rn(__fmul_rn(wx0, colA), __fmul_rn(wx1, colB));
+        store_with_walls(dB, i, G, o, w, 1.0f, -1.0f);   // b = 2
+    }
+}
+
+// ---- divergence (+ p = 0) --------------------------------------------------------------------
+__global__ void divergence_kernel(const float *__restrict__ u, const float *__restrict__ v, float *__restrict__ p,
+                                  float *__restrict__ div, Geom g, float scale, int write_p)
+{
+    int lo, hi;
+    interior_rows(g, lo, hi);
+    const int col = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y + lo;
+    if (col > g.N || row >= hi) return;
+    const size_t G = (size_t)g.G;
+    const size_t i = (size_t)(row - g.row_base) * G + col;
+    // FluidSequential.c:151-152: (-0.5f*h) * (((u_r - u_l) + v_d) - v_u)
+    float acc = __fsub_rn(__ldg(u + i + 1), __ldg(u + i - 1));
+    acc = __fadd_rn(acc, __ldg(v + i + G));
+    acc = __fsub_rn(acc, __ldg(v + i - G));
+    const Wall w = wall_of(g, row, col);
+    store_with_walls(div, i, G, __fmul_rn(scale, acc), w, 1.0f, 1.0f);
+    if (write_p) store_with_walls(p, i, G, 0.0f, w, 1.0f, 1.0f);
+}
+
+// ---- lastProject (gradient subtract) ------------------------------------------------------------
+__global__ void last_project_kernel(float *__restrict__ u, float *__restrict__ v, const float *__restrict__ p, Geom g,
+                                    float h)
+{
+    int lo, hi;
+    interior_rows(g, lo, hi);
+    const int col = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y + lo;
+    if (col > g.N || row >= hi) return;
+    const size_t G = (size_t)g.G;
+    const size_t i = (size_t)(row - g.row_base) * G + col;
+    // FluidSequential.c:167-168: u -= (0.5f*(p_r - p_l)) / h
+    const float gx = __fmul_rn(0.5f, __fsub_rn(__ldg(p + i + 1), __ldg(p + i - 1)));
+    const float gy = __fmul_rn(0.5f, __fsub_rn(__ldg(p + i + G), __ldg(p + i - G)));
+    const float nu = __fsub_rn(u[i], __fdiv_rn(gx, h));
+    const float nv = __fsub_rn(v[i], __fdiv_rn(gy, h));
+    const Wall w = wall_of(g, row, col);
+    store_with_walls(u, i, G, nu, w, -1.0f, 1.0f);   // set_bnd(1, u)
+    store_with_walls(v, i, G, nv, w, 1.0f, -1.0f);   // set_bnd(2, v)
+}
+
+// ---- synthetic initial condition ---------------------------------------------------------------
+__global__ void init_kernel(float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev, Geom g,
+                            uint64_t seed)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y + g.own_lo;
+    if (col >= g.G || row >= g.own_hi) return;
+    const size_t cell = (size_t)row * g.G + col;                       // GLOBAL cell id feeds the hash
+    const size_t i = (size_t)(row - g.row_base) * g.G + col;
+    const int mid = g.G / 2, half = g.G / 8;
+    const bool inside = (col < mid + half) && (col >= mid - half) && (row < mid + half) && (row >= mid - half);
+    if (dens_prev) dens_prev[i] = inside ? __fdiv_rn((float)hash100(seed, 0, cell), 1000.0f) : 0.0f;
+    if (u_prev) u_prev[i] = __fdiv_rn((float)hash100(seed, 1, cell), 100.0f);
+    if (v_prev) v_prev[i] = __fdiv_rn((float)hash100(seed, 2, cell), 100.0f);
+    if (dens) dens[i] = 0.0f;
+    if (u) u[i] = 0.0f;
+    if (v) v[i] = 0.0f;
+}
+
+// ---- reductions (warp shuffle, then one atomic per block) ------------------------------------
+__global__ void max_abs_kernel(const float *__restrict__ x, size_t first, size_t count, float *out)
+{
+    float m = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[first + i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0f;
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));  // m >= 0: int order == float order
+    }
+}
+
+__global__ void residual_kernel(const float *__restrict__ x, const float *__restrict__ x0, Geom g, float alpha,
+                                float beta, double *out)
+{
+    int lo, hi;
+    interior_rows(g, lo, hi);
+    double acc = 0.0;
+    const size_t G = (size_t)g.G;
+    for (int row = lo + blockIdx.y; row < hi; row += gridDim.y)
+        for (int col = 1 + blockIdx.x * blockDim.x + threadIdx.x; col <= g.N; col += gridDim.x * blockDim.x) {
+            const size_t i = (size_t)(row - g.row_base) * G + col;
+            const float nb = x[i - 1] + x[i + 1] + x[i - G] + x[i + G];
+            const float r = x0[i] - (beta * x[i] - alpha * nb);
+            acc += (double)r * (double)r;
+        }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) atomicAdd(out, acc);
+    }
+}
+
+inline dim3 cell_grid(const Geom &g, dim3 block, int rows) { return dim3((g.N + block.x - 1) / block.x, (rows + block.y - 1) / block.y); }
+inline int interior_row_count(const Geom &g)
+{
+    const int lo = g.own_lo > 1 ? g.own_lo : 1, hi = g.own_hi < g.N + 1 ? g.own_hi : g.N + 1;
+    return hi > lo ? hi - lo : 0;
+}
+
+}  // namespace
+
+cudaError_t launch_set_bnd(const Geom &g, int b, float *x, cudaStream_t st)
+{
+    set_bnd_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(x, g, b == 1 ? -1.0f : 1.0f, b == 2 ? -1.0f : 1.0f);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_add_source(const Geom &g, int nfields, float *const *x, const float *const *s, float dt, cudaStream_t st)
+{
+    if (nfields < 1 || nfields > 3) return cudaErrorInvalidValue;
+    AddSrcArgs A;
+    for (int k = 0; k < 3; ++k) { A.x[k] = x[k < nfields ? k : 0]; A.s[k] = s[k < nfields ? k : 0]; }
+    A.first = (size_t)(g.own_lo - g.row_base) * g.G;
+    A.count = (size_t)(g.own_hi - g.own_lo) * g.G;
+    A.dt = dt;
+    bool vec = (A.first % 4 == 0) && (A.count % 4 == 0);
+    for (int k = 0; k < nfields; ++k) vec = vec && ((uintptr_t)x[k] % 16 == 0) && ((uintptr_t)s[k] % 16 == 0);
+    A.vec = vec ? 1 : 0;
+    const size_t work = vec ? A.count / 4 : A.count;
+    size_t blocks = (work + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    add_source_kernel<<<dim3((unsigned)blocks, nfields), 256, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const float *u, const float *v, float dt, cudaStream_t st)
+{
+    const int rows = interior_row_count(g);
+    if (rows == 0) return cudaSuccess;
+    const dim3 block(64, 4);
+    const float dt0 = dt * (float)g.N;   // FluidSequential.c:111, rounded once in binary32
+    advect_kernel<1><<<cell_grid(g, block, rows), block, 0, st>>>(d, nullptr, d0, nullptr, u, v, g, dt0, b);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt, cudaStream_t st)
+{
+    const int rows = interior_row_count(g);
+    if (rows == 0) return cudaSuccess;
+    const dim3 block(64, 4);
+    const float dt0 = dt * (float)g.N;
+    advect_kernel<2><<<cell_grid(g, block, rows), block, 0, st>>>(du, dv, u0, v0, u0, v0, g, dt0, 1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_divergence(const Geom &g, const float *u, const float *v, float *p, float *div, int write_p, cudaStream_t st)
+{
+    const int rows = interior_row_count(g);
+    if (rows == 0) return cudaSuccess;
+    const dim3 block(64, 4);
+    const float h = 1.0f / (float)g.N;
+    const float scale = -0.5f * h;
+    divergence_kernel<<<cell_grid(g, block, rows), block, 0, st>>>(u, v, p, div, g, scale, write_p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_last_project(const Geom &g, float *u, float *v, const float *p, cudaStream_t st)
+{
+    const int rows = interior_row_count(g);
+    if (rows == 0) return cudaSuccess;
+    const dim3 block(64, 4);
+    const float h = 1.0f / (float)g.N;
+    last_project_kernel<<<cell_grid(g, block, rows), block, 0, st>>>(u, v, p, g, h);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init(const Geom &g, uint64_t seed, float *dens, float *dens_prev, float *u, float *u_prev, float *v,
+                        float *v_prev, cudaStream_t st)
+{
+    const dim3 block(64, 4);
+    const dim3 grid((g.G + 63) / 64, (g.own_hi - g.own_lo + 3) / 4);
+    init_kernel<<<grid, block, 0, st>>>(dens, dens_prev, u, u_prev, v, v_prev, g, seed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_max_abs(const Geom &g, const float *x, float *dev_out, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(dev_out, 0, sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    const size_t first = (size_t)(g.own_lo - g.row_base) * g.G, count = (size_t)(g.own_hi - g.own_lo) * g.G;
+    size_t blocks = (count + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    max_abs_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, first, count, dev_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_residual(const Geom &g, const float *x, const float *x0, float alpha, float beta, double *dev_out, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(dev_out, 0, sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    const int rows = interior_row_count(g);
+    if (rows == 0) return cudaSuccess;
+    dim3 grid((g.N + 255) / 256 > 8 ? 8 : (g.N + 255) / 256, rows > 1024 ? 1024 : rows);
+    residual_kernel<<<grid, 256, 0, st>>>(x, x0, g, alpha, beta, dev_out);
+    return cudaGetLastError();
+}
+
+}  // namespace sf

@@ -1,0 +1,235 @@
+"""Host-side mirror of the reference's solver interface over the C ABI (include/stablefluids.h).
+
+The reference (ArbiterMob/FluidSimulationCuda) is a set of single-file C/CUDA programs whose
+solver surface is the functions ``set_bnd, add_source, diffuse, advect,
+computeDivergenceAndPressure, lastProject, dens_step, vel_step``
+(project/sequential/FluidSequential.c:62-241).  ``StableFluids`` exposes the same names with the
+same argument order and in/out semantics; what the reference bakes in as macros (N, DT, the
+literal 40 iterations) are constructor / call arguments here.
+
+PyTorch is used only for device memory and streams: fields are float32 CUDA tensors of shape
+(N+2, N+2) (row-major, ``x[row, col]`` = the reference's ``x[col + row*(N+2)]``) and every kernel
+is enqueued on ``torch.cuda.current_stream()`` at construction time.  All arithmetic happens in
+libstablefluids_b200.so (hand-written sm_100a CUDA).  There is no CPU fallback: constructing a
+solver without the library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libstablefluids_b200.so")
+
+SF_OPT_ARITHMETIC = 1
+SF_OPT_SWEEPS_PER_LAUNCH = 2
+SF_OPT_USE_GRAPH = 3
+SF_OPT_FORCE_GENERIC = 4
+SF_OPT_CHUNK_ROWS = 5
+STRICT, FAST = 0, 1
+
+# every symbol include/stablefluids.h declares (tests/test_abi.py checks the library exports them)
+ABI_SYMBOLS = [
+    "sf_create", "sf_create_on_stream", "sf_create_slab", "sf_destroy", "sf_last_error_string",
+    "sf_set_option", "sf_get_option", "sf_synchronize", "sf_launch_count", "sf_field_bytes",
+    "sf_alloc_field", "sf_free_field", "sf_upload", "sf_download",
+    "sf_set_bnd", "sf_add_source", "sf_diffuse", "sf_advect", "sf_compute_divergence_and_pressure",
+    "sf_last_project", "sf_project", "sf_dens_step", "sf_vel_step", "sf_step", "sf_step_host",
+    "sf_init_synthetic", "sf_init_sources", "sf_reduce_max_abs", "sf_residual_l2",
+    "sf_halo_rows_needed", "sf_jacobi_launch",
+]
+
+_lib = None
+
+
+class StableFluidsError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """Load libstablefluids_b200.so (built in-tree by fluidsimulationcuda_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise StableFluidsError(
+            f"{LIB_PATH} is missing: run `python -m fluidsimulationcuda_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i, f, u64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64
+    L.sf_create.argtypes = [C.POINTER(vp), i, i]
+    L.sf_create_on_stream.argtypes = [C.POINTER(vp), i, i, vp]
+    L.sf_create_slab.argtypes = [C.POINTER(vp), i, i, vp, i, i, i]
+    L.sf_destroy.argtypes = [vp]
+    L.sf_last_error_string.argtypes = [vp]
+    L.sf_last_error_string.restype = C.c_char_p
+    L.sf_set_option.argtypes = [vp, i, i]
+    L.sf_get_option.argtypes = [vp, i, C.POINTER(i)]
+    L.sf_synchronize.argtypes = [vp]
+    L.sf_launch_count.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    L.sf_field_bytes.argtypes = [vp]
+    L.sf_field_bytes.restype = C.c_size_t
+    L.sf_alloc_field.argtypes = [vp, C.POINTER(vp)]
+    L.sf_free_field.argtypes = [vp, vp]
+    L.sf_upload.argtypes = [vp, vp, vp]
+    L.sf_download.argtypes = [vp, vp, vp]
+    L.sf_set_bnd.argtypes = [vp, i, vp]
+    L.sf_add_source.argtypes = [vp, vp, vp, f]
+    L.sf_diffuse.argtypes = [vp, i, vp, vp, f, f, i]
+    L.sf_advect.argtypes = [vp, i, vp, vp, vp, vp, f]
+    L.sf_compute_divergence_and_pressure.argtypes = [vp, vp, vp, vp, vp]
+    L.sf_last_project.argtypes = [vp, vp, vp, vp, vp]
+    L.sf_project.argtypes = [vp, vp, vp, vp, vp, i]
+    L.sf_dens_step.argtypes = [vp, vp, vp, vp, vp, f, f, i]
+    L.sf_vel_step.argtypes = [vp, vp, vp, vp, vp, f, f, i]
+    L.sf_step.argtypes = [vp] + [vp] * 6 + [f, f, f, i]
+    L.sf_step_host.argtypes = [vp] + [vp] * 6 + [f, f, f, i, i]
+    L.sf_init_synthetic.argtypes = [vp, u64] + [vp] * 6
+    L.sf_init_sources.argtypes = [vp, u64] + [vp] * 3
+    L.sf_reduce_max_abs.argtypes = [vp, vp, C.POINTER(f)]
+    L.sf_residual_l2.argtypes = [vp, vp, vp, f, f, C.POINTER(C.c_double)]
+    L.sf_halo_rows_needed.argtypes = [vp, C.POINTER(i)]
+    L.sf_jacobi_launch.argtypes = [vp, i, vp, vp, vp, f, f, i, i, i]
+    for name in ABI_SYMBOLS:
+        if name not in ("sf_last_error_string", "sf_field_bytes"):
+            getattr(L, name).restype = i
+    _lib = L
+    return L
+
+
+class StableFluids:
+    """One solver context = the reference's N plus a CUDA stream.
+
+    ``row_lo/row_hi/halo`` select a row slab for domain decomposition (see
+    fluidsimulationcuda_b200.slab); the defaults are the whole grid."""
+
+    def __init__(self, N: int, device: Optional[int] = None, *, row_lo: int = 0, row_hi: Optional[int] = None,
+                 halo: int = 0, arithmetic: int = STRICT, sweeps_per_launch: int = 0, use_graph: bool = True):
+        import torch
+        if not torch.cuda.is_available():
+            raise StableFluidsError("no CUDA device: the stable-fluids path has no CPU fallback")
+        self.torch = torch
+        self.L = load_library()
+        self.N, self.G = int(N), int(N) + 2
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.row_lo = int(row_lo)
+        self.row_hi = self.G if row_hi is None else int(row_hi)
+        self.halo = int(halo)
+        self.local_rows = self.row_hi - self.row_lo + 2 * self.halo
+        self._stream = torch.cuda.current_stream(self.device)
+        h = C.c_void_p()
+        rc = self.L.sf_create_slab(C.byref(h), self.N, self.device, C.c_void_p(self._stream.cuda_stream),
+                                   self.row_lo, self.row_hi, self.halo)
+        if rc != 0:
+            raise StableFluidsError(f"sf_create_slab failed with status {rc}")
+        self.h = h
+        self.set_option(SF_OPT_ARITHMETIC, arithmetic)
+        self.set_option(SF_OPT_SWEEPS_PER_LAUNCH, sweeps_per_launch)
+        self.set_option(SF_OPT_USE_GRAPH, 1 if use_graph else 0)
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self.L.sf_last_error_string(self.h)
+            raise StableFluidsError(f"status {rc}: {msg.decode() if msg else '?'}")
+
+    def _p(self, t):
+        torch = self.torch
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise StableFluidsError("fields must be contiguous float32 CUDA tensors")
+        if t.numel() != self.local_rows * self.G:
+            raise StableFluidsError(f"field has {t.numel()} cells, expected {self.local_rows}x{self.G}")
+        return C.c_void_p(t.data_ptr())
+
+    def set_option(self, opt: int, value: int):
+        self._check(self.L.sf_set_option(self.h, opt, int(value)))
+
+    def new_field(self):
+        return self.torch.zeros((self.local_rows, self.G), dtype=self.torch.float32, device=f"cuda:{self.device}")
+
+    def synchronize(self):
+        self._check(self.L.sf_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_ulonglong(0)
+        self._check(self.L.sf_launch_count(self.h, C.byref(n)))
+        return int(n.value)
+
+    # -- the reference's stage functions (FluidSequential.c:62-173) ---------------------------
+    def set_bnd(self, b, x):
+        self._check(self.L.sf_set_bnd(self.h, b, self._p(x)))
+
+    def add_source(self, x, s, dt):
+        self._check(self.L.sf_add_source(self.h, self._p(x), self._p(s), dt))
+
+    def diffuse(self, b, x, x0, alpha, beta, iters):
+        self._check(self.L.sf_diffuse(self.h, b, self._p(x), self._p(x0), alpha, beta, iters))
+
+    def advect(self, b, d, d0, u, v, dt):
+        self._check(self.L.sf_advect(self.h, b, self._p(d), self._p(d0), self._p(u), self._p(v), dt))
+
+    def computeDivergenceAndPressure(self, u, v, p, div):
+        self._check(self.L.sf_compute_divergence_and_pressure(self.h, self._p(u), self._p(v), self._p(p), self._p(div)))
+
+    def lastProject(self, u, v, p, div):
+        self._check(self.L.sf_last_project(self.h, self._p(u), self._p(v), self._p(p), self._p(div)))
+
+    def project(self, u, v, p, div, iters):
+        self._check(self.L.sf_project(self.h, self._p(u), self._p(v), self._p(p), self._p(div), iters))
+
+    # -- step drivers (FluidSequential.c:176-241, :305-306) -----------------------------------
+    def dens_step(self, x, x0, u, v, diff, dt, iters):
+        self._check(self.L.sf_dens_step(self.h, self._p(x), self._p(x0), self._p(u), self._p(v), diff, dt, iters))
+
+    def vel_step(self, u, v, u0, v0, visc, dt, iters):
+        self._check(self.L.sf_vel_step(self.h, self._p(u), self._p(v), self._p(u0), self._p(v0), visc, dt, iters))
+
+    def step(self, dens, dens_prev, u, u_prev, v, v_prev, visc, diff, dt, iters):
+        self._check(self.L.sf_step(self.h, self._p(dens), self._p(dens_prev), self._p(u), self._p(u_prev),
+                                   self._p(v), self._p(v_prev), visc, diff, dt, iters))
+
+    def step_host(self, dens, dens_prev, u, u_prev, v, v_prev, visc, diff, dt, iters, download_scratch=False):
+        """Same loop body with HOST fields (numpy float32 arrays or CPU tensors, ideally pinned)."""
+        def hp(a):
+            if hasattr(a, "data_ptr"):
+                assert not a.is_cuda and a.is_contiguous() and a.numel() == self.G * self.G
+                return C.c_void_p(a.data_ptr())
+            assert a.dtype.name == "float32" and a.flags["C_CONTIGUOUS"] and a.size == self.G * self.G
+            return C.c_void_p(a.ctypes.data)
+        self._check(self.L.sf_step_host(self.h, hp(dens), hp(dens_prev), hp(u), hp(u_prev), hp(v), hp(v_prev),
+                                        visc, diff, dt, iters, 1 if download_scratch else 0))
+
+    # -- synthetic data and diagnostics ------------------------------------------------------
+    def init_synthetic(self, seed, dens, dens_prev, u, u_prev, v, v_prev):
+        self._check(self.L.sf_init_synthetic(self.h, seed, self._p(dens), self._p(dens_prev), self._p(u),
+                                             self._p(u_prev), self._p(v), self._p(v_prev)))
+
+    def init_sources(self, seed, dens_prev, u_prev, v_prev):
+        self._check(self.L.sf_init_sources(self.h, seed, self._p(dens_prev), self._p(u_prev), self._p(v_prev)))
+
+    def reduce_max_abs(self, x) -> float:
+        out = C.c_float(0)
+        self._check(self.L.sf_reduce_max_abs(self.h, self._p(x), C.byref(out)))
+        return float(out.value)
+
+    def residual_sumsq(self, x, x0, alpha, beta) -> float:
+        out = C.c_double(0)
+        self._check(self.L.sf_residual_l2(self.h, self._p(x), self._p(x0), alpha, beta, C.byref(out)))
+        return float(out.value)
+
+    def jacobi_launch(self, b, xout, xin, x0, alpha, beta, sweeps, out_lo=-1, out_hi=-1):
+        self._check(self.L.sf_jacobi_launch(self.h, b, self._p(xout), self._p(xin), self._p(x0), alpha, beta,
+                                            sweeps, out_lo, out_hi))

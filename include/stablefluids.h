@@ -1,0 +1,158 @@
+/*
+ * stablefluids.h -- C ABI of the B200-native stable-fluids time step.
+ *
+ * Drop-in boundary for the solver entry points of ArbiterMob/FluidSimulationCuda.  The reference
+ * has no library or FFI: its boundary is the C function-call surface inside each single-file
+ * program.  Every entry point below names the reference function it replaces
+ * (paths relative to the reference's project/ directory; "seq" = sequential/FluidSequential.c,
+ * "gpu" = naivePar/FluidParallelBlockPerElement-Naive.cu).
+ *
+ * Conventions kept from the reference:
+ *   - a field is a flat float array of (N+2)*(N+2) cells, index  col + row*(N+2)  (seq:24,95),
+ *     interior 1..N, one-cell wall ring;
+ *   - results land in the FIRST-named buffers; the *0 / *_prev buffers are clobbered scratch with
+ *     the reference's post-conditions (vel_step: u0 = last pressure, v0 = last divergence;
+ *     dens_step: x0 = diffused density) -- seq:176-241;
+ *   - the caller owns every field; the context owns scratch, streams and captured graphs.
+ * What the reference hard-codes and this ABI takes as run-time arguments (north star): grid size N
+ * (seq:6), dt (seq:7), viscosity / diffusion (seq:8-9) and the Jacobi iteration count (seq:91,
+ * literal 40).  Any iteration count >= 1 works (the reference is only correct for even counts).
+ *
+ * All field pointers are DEVICE pointers unless the function name ends in _host.  Calls are
+ * asynchronous with respect to the host and ordered on the context's stream; a context is not
+ * thread-safe, distinct contexts are independent.  Every function returns SF_OK (0) or a negative
+ * sf_status; sf_last_error_string() describes the last failure.  Nothing here ever calls exit()
+ * (the reference's CHECK macro does, gpu:26-35).
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * SF_ERR_CUDA.
+ */
+#ifndef STABLEFLUIDS_H
+#define STABLEFLUIDS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sf_context sf_context;
+
+typedef enum sf_status {
+    SF_OK = 0,
+    SF_ERR_INVALID = -1,     /* bad argument (N < 1, null pointer, iters < 1, unknown option ...) */
+    SF_ERR_CUDA = -2,        /* CUDA runtime error; text in sf_last_error_string */
+    SF_ERR_NOMEM = -3,
+    SF_ERR_UNSUPPORTED = -4
+} sf_status;
+
+/* Options for sf_set_option. */
+enum {
+    /* 0 (default) = STRICT: every operation rounded exactly like the reference's sequential
+     * build (no FMA contraction, IEEE division): results are BIT-IDENTICAL to seq.
+     * 1 = FAST: x0 + alpha*sum contracted to one FMA and the division replaced by a multiply with
+     * 1/beta; rel-L2 <= 1e-6 per field per step against seq (tests/test_parity_gpu.py). */
+    SF_OPT_ARITHMETIC = 1,
+    /* Jacobi sweeps fused per kernel launch (temporal blocking depth), 1..8; 0 = automatic. */
+    SF_OPT_SWEEPS_PER_LAUNCH = 2,
+    /* 1 (default) = replay sf_vel_step/sf_dens_step/sf_step from a captured CUDA graph when the
+     * same arguments recur; 0 = launch kernels directly. */
+    SF_OPT_USE_GRAPH = 3,
+    /* 1 = force the generic one-sweep-per-launch kernels even when the grid width allows the
+     * streaming kernels (testing aid). */
+    SF_OPT_FORCE_GENERIC = 4,
+    /* interior rows per streaming chunk (0 = automatic). */
+    SF_OPT_CHUNK_ROWS = 5
+};
+enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
+
+/* ---- context -------------------------------------------------------------------------------- */
+
+/* Create a context for an (N+2)^2 grid on CUDA device `device`, with its own stream.
+ * Replaces the reference's file-scope N / __constant__ N (seq:6, gpu:11-20, gpu:386-389). */
+int sf_create(sf_context **out, int N, int device);
+/* Same, but every kernel is enqueued on the caller's CUDA stream (a cudaStream_t passed as
+ * void*), e.g. PyTorch's current stream. */
+int sf_create_on_stream(sf_context **out, int N, int device, void *cuda_stream);
+/* Slab context for domain decomposition along rows: this context owns global
+ * rows [row_lo, row_hi) of the (N+2)-row grid and every field passed to it is a LOCAL array of
+ * (row_hi - row_lo + 2*halo) rows x (N+2) columns whose first row is global row row_lo - halo.
+ * The caller fills the halo rows (neighbour exchange) before each call that reads them; see
+ * sf_halo_rows_needed.  row_lo = 0, row_hi = N+2, halo = 0 is the single-GPU layout. */
+int sf_create_slab(sf_context **out, int N, int device, void *cuda_stream, int row_lo, int row_hi, int halo);
+int sf_destroy(sf_context *ctx);
+const char *sf_last_error_string(const sf_context *ctx);
+int sf_set_option(sf_context *ctx, int option, int value);
+int sf_get_option(const sf_context *ctx, int option, int *value);
+int sf_synchronize(sf_context *ctx);
+/* Number of kernels this context has launched (graph replays count their kernel nodes). */
+int sf_launch_count(const sf_context *ctx, unsigned long long *count);
+size_t sf_field_bytes(const sf_context *ctx);      /* bytes of one (local) field */
+
+/* ---- fields (replace malloc/cudaMalloc/cudaMemcpy in the reference's main, gpu:375-384) ------ */
+int sf_alloc_field(sf_context *ctx, float **dev_field);
+int sf_free_field(sf_context *ctx, float *dev_field);
+int sf_upload(sf_context *ctx, float *dev_field, const float *host_field);
+int sf_download(sf_context *ctx, float *host_field, const float *dev_field);
+
+/* ---- stage functions ---------------------------------------------------------------------------
+ * set_bnd(b, x)                          seq:62-75   gpu:83-104 */
+int sf_set_bnd(sf_context *ctx, int b, float *x);
+/* add_source(x, s): x += dt*s on all (N+2)^2 cells   seq:78-82   gpu:108-118 */
+int sf_add_source(sf_context *ctx, float *x, const float *s, float dt);
+/* diffuse(b, x, x0, alpha, beta) = lin_solve: `iters` Jacobi sweeps + set_bnd(b) each
+ *                                        seq:85-104  gpu:121-144 + host loop gpu:261-264 */
+int sf_diffuse(sf_context *ctx, int b, float *x, const float *x0, float alpha, float beta, int iters);
+/* advect(b, d, d0, u, v)                 seq:107-141 gpu:147-196 */
+int sf_advect(sf_context *ctx, int b, float *d, const float *d0, const float *u, const float *v, float dt);
+/* computeDivergenceAndPressure(u, v, p, div)   seq:143-158 gpu:199-225 */
+int sf_compute_divergence_and_pressure(sf_context *ctx, const float *u, const float *v, float *p, float *div);
+/* lastProject(u, v, p, div)              seq:161-173 gpu:228-252 */
+int sf_last_project(sf_context *ctx, float *u, float *v, const float *p, const float *div);
+/* The projection triple as the reference sequences it (seq:213-223): divergence, lin_solve(0,
+ * p, div, 1, 4), gradient subtract. */
+int sf_project(sf_context *ctx, float *u, float *v, float *p, float *div, int iters);
+
+/* ---- step drivers ------------------------------------------------------------------------------
+ * dens_step(x, x0, u, v, diff)           seq:176-186 gpu:255-268 */
+int sf_dens_step(sf_context *ctx, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters);
+/* vel_step(u, v, u0, v0, visc, z)        seq:189-241 gpu:271-311 (z only indexed timers) */
+int sf_vel_step(sf_context *ctx, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters);
+/* One iteration of the reference's main loop body (seq:305-306): vel_step then dens_step. */
+int sf_step(sf_context *ctx, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev,
+            float visc, float diff, float dt, int iters);
+/* Same loop body for a caller whose six fields live in HOST memory (the reference's CPU path,
+ * seq:277-282): uploads the six fields, runs the step on the device, downloads dens, u, v (and,
+ * if download_scratch != 0, the three clobbered *_prev fields) and returns when the host buffers
+ * are valid.  Pinned host memory makes the copies overlap the compute. */
+int sf_step_host(sf_context *ctx, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev,
+                 float visc, float diff, float dt, int iters, int download_scratch);
+
+/* ---- synthetic initial conditions (seq:244-271 value distributions, counter-based) ---------- */
+int sf_init_synthetic(sf_context *ctx, uint64_t seed, float *dens, float *dens_prev, float *u, float *u_prev,
+                      float *v, float *v_prev);
+/* Only the three source fields (what the reference's loop refreshes every step, seq:298-302). */
+int sf_init_sources(sf_context *ctx, uint64_t seed, float *dens_prev, float *u_prev, float *v_prev);
+
+/* ---- diagnostics (warp-shuffle reductions) ------------------------------------------------- */
+/* max |x| over the owned cells; result written to *host_out after an internal synchronize. */
+int sf_reduce_max_abs(sf_context *ctx, const float *x, float *host_out);
+/* || x0 - (beta*x - alpha*sum_nb(x)) ||_2 over the interior: the lin_solve residual. */
+int sf_residual_l2(sf_context *ctx, const float *x, const float *x0, float alpha, float beta, double *host_out);
+
+/* ---- slab support --------------------------------------------------------------------------- */
+/* Halo rows each call reads beyond the owned rows: lin_solve reads `sweeps_per_launch` rows per
+ * launch, divergence / gradient 1 row.  *rows = temporal-blocking depth currently configured. */
+int sf_halo_rows_needed(const sf_context *ctx, int *rows);
+/* One temporally blocked launch of the lin_solve: `sweeps` (1..8) Jacobi sweeps from xin into
+ * xout (different buffers), restricted to owned rows [out_lo, out_hi) (global row numbers; pass
+ * -1, -1 for all owned rows).  xin must hold valid rows [out_lo - sweeps, out_hi + sweeps).
+ * Building block for halo-exchange overlap: boundary strips first, interior while halos fly. */
+int sf_jacobi_launch(sf_context *ctx, int b, float *xout, const float *xin, const float *x0, float alpha, float beta,
+                     int sweeps, int out_lo, int out_hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STABLEFLUIDS_H */

@@ -1,0 +1,231 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle.
+
+Bar (north star / SURVEY.md section 8c): STRICT arithmetic is BIT-IDENTICAL to the reference's
+sequential path for every field, every stage, every step.  FAST arithmetic (opt-in) is held to
+rel-L2 <= 1e-6 and max-abs <= 1e-6 * max|ref| per field per step."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from gpu_util import bits_equal, dev, host, mismatch_report, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DT, VIS, DIFF = 0.016, 0.0025, 0.1
+
+
+@pytest.fixture(scope="module")
+def SF():
+    from fluidsimulationcuda_b200 import solver
+    return solver
+
+
+def rnd(rng, G, lo=-1.0, hi=1.0):
+    return rng.uniform(lo, hi, (G, G)).astype(np.float32)
+
+
+def assert_same(got, want, name):
+    assert bits_equal(got, want), mismatch_report(got, want, name)
+
+
+# ---- stage functions --------------------------------------------------------------------------
+# widths: 16/32 (one band), 128, 224 (= exactly two 112-column bands), 228, 256, 512 and the
+# literal-N sizes 13, 128 (G = 15 / 130: not a multiple of 4 -> generic kernels)
+STAGE_N = [14, 30, 126, 222, 226, 254, 510, 13, 128]
+
+
+@pytest.mark.parametrize("N", STAGE_N)
+def test_set_bnd_add_source(SF, oracle, N):
+    G = N + 2
+    rng = np.random.default_rng(N)
+    s = SF.StableFluids(N)
+    for b in (0, 1, 2):
+        x = rnd(rng, G); want = x.copy(); oracle.set_bnd(N, b, want)
+        dx = dev(x); s.set_bnd(b, dx); assert_same(host(dx), want, f"set_bnd b={b}")
+    x, src = rnd(rng, G), rnd(rng, G)
+    want = x.copy(); oracle.add_source(N, want, src, DT)
+    dx = dev(x); s.add_source(dx, dev(src), DT); assert_same(host(dx), want, "add_source")
+
+
+@pytest.mark.parametrize("N", STAGE_N)
+def test_advect_divergence_project(SF, oracle, N):
+    G = N + 2
+    rng = np.random.default_rng(100 + N)
+    s = SF.StableFluids(N)
+    amp = 3.0 / (DT * N)                      # back-traces of up to ~3 cells, clamps hit at the walls
+    for b in (0, 1, 2):
+        d0, u, v = rnd(rng, G), rnd(rng, G, -amp, amp), rnd(rng, G, -amp, amp)
+        want = np.zeros((G, G), np.float32); oracle.advect(N, b, want, d0, u, v, DT)
+        dd = dev(rnd(rng, G)); s.advect(b, dd, dev(d0), dev(u), dev(v), DT)
+        assert_same(host(dd), want, f"advect b={b}")
+    u, v = rnd(rng, G), rnd(rng, G)
+    p, div = rnd(rng, G), rnd(rng, G)
+    wp, wd = p.copy(), div.copy(); oracle.computeDivergenceAndPressure(N, u, v, wp, wd)
+    dp, dd = dev(p), dev(div); s.computeDivergenceAndPressure(dev(u), dev(v), dp, dd)
+    assert_same(host(dd), wd, "divergence"); assert_same(host(dp), wp, "pressure zero")
+    u, v, p = rnd(rng, G), rnd(rng, G), rnd(rng, G)
+    wu, wv = u.copy(), v.copy(); oracle.lastProject(N, wu, wv, p, np.zeros_like(p))
+    du, dv = dev(u), dev(v); s.lastProject(du, dv, dev(p), dev(p))
+    assert_same(host(du), wu, "lastProject u"); assert_same(host(dv), wv, "lastProject v")
+
+
+# ---- lin_solve: every temporal-blocking depth, boundary kind, arithmetic path -----------------
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("N,chunk", [(30, 0), (126, 0), (222, 16), (254, 24), (510, 0)])
+def test_diffuse_all_depths(SF, oracle, N, chunk, T):
+    G = N + 2
+    rng = np.random.default_rng(1000 * T + N)
+    s = SF.StableFluids(N, sweeps_per_launch=T)
+    s.set_option(SF.SF_OPT_CHUNK_ROWS, chunk)
+    for b, (alpha, beta), iters in ((0, (1.0, 4.0), 2 * T + 1), (1, (0.635, 3.54), 3 * T), (2, (2683.2, 10733.8), T + 2),
+                                    (0, (107322.0, 429289.0), 40)):
+        x, x0 = rnd(rng, G), rnd(rng, G)
+        want = x.copy(); oracle.diffuse(N, b, want, x0, alpha, beta, iters)
+        dx = dev(x); s.diffuse(b, dx, dev(x0), alpha, beta, iters)
+        assert_same(host(dx), want, f"diffuse N={N} T={T} b={b} alpha={alpha} iters={iters}")
+
+
+@pytest.mark.parametrize("N", [13, 128, 30])
+def test_diffuse_generic_path(SF, oracle, N):
+    G = N + 2
+    rng = np.random.default_rng(N)
+    s = SF.StableFluids(N)
+    s.set_option(SF.SF_OPT_FORCE_GENERIC, 1)
+    for b, (alpha, beta), iters in ((0, (1.0, 4.0), 5), (1, (0.635, 3.54), 20), (2, (41.8, 168.2), 1)):
+        x, x0 = rnd(rng, G), rnd(rng, G)
+        want = x.copy(); oracle.diffuse(N, b, want, x0, alpha, beta, iters)
+        dx = dev(x); s.diffuse(b, dx, dev(x0), alpha, beta, iters)
+        assert_same(host(dx), want, f"generic diffuse N={N} b={b}")
+
+
+def test_diffuse_subnormal_and_zero_fields(SF, oracle):
+    """Density decays into the subnormal range within ~50 reference steps: no FTZ."""
+    N = 62; G = N + 2
+    rng = np.random.default_rng(5)
+    s = SF.StableFluids(N)
+    x = (rnd(rng, G, 0, 1) * 1e-41).astype(np.float32); x0 = (rnd(rng, G, 0, 1) * 3e-39).astype(np.float32)
+    x[10:20, :] = 0.0; x0[:, 30:40] = 0.0
+    want = x.copy(); oracle.diffuse(N, 0, want, x0, 6.15, 25.6, 20)
+    dx = dev(x); s.diffuse(0, dx, dev(x0), 6.15, 25.6, 20)
+    assert np.any((want != 0) & (np.abs(want) < 1.17e-38)), "test must exercise subnormals"
+    assert_same(host(dx), want, "subnormal diffuse")
+
+
+# ---- steps ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,K", [(30, 4), (62, 20), (126, 40), (254, 20), (130, 6)])
+def test_vel_and_dens_step(SF, oracle, N, K):
+    G = N + 2
+    rng = np.random.default_rng(N + K)
+    s = SF.StableFluids(N)
+    u, v, u0, v0 = rnd(rng, G, -.1, .1), rnd(rng, G, -.1, .1), rnd(rng, G, 0, 1), rnd(rng, G, 0, 1)
+    wu, wv, wu0, wv0 = (a.copy() for a in (u, v, u0, v0))
+    oracle.vel_step(N, wu, wv, wu0, wv0, VIS, DT, K)
+    du, dv, du0, dv0 = (dev(a) for a in (u, v, u0, v0))
+    for rep in range(2):   # second round replays the captured graph on restored inputs
+        du.copy_(dev(u)); dv.copy_(dev(v)); du0.copy_(dev(u0)); dv0.copy_(dev(v0))
+        s.vel_step(du, dv, du0, dv0, VIS, DT, K)
+        for g, w, nm in ((du, wu, "u"), (dv, wv, "v"), (du0, wu0, "u0=p"), (dv0, wv0, "v0=div")):
+            assert_same(host(g), w, f"vel_step {nm} rep{rep}")
+    x, x0 = rnd(rng, G, 0, 1), rnd(rng, G, 0, 1)
+    wx, wx0 = x.copy(), x0.copy(); oracle.dens_step(N, wx, wx0, wu, wv, DIFF, DT, K)
+    dx, dx0 = dev(x), dev(x0); s.dens_step(dx, dx0, du, dv, DIFF, DT, K)
+    assert_same(host(dx), wx, "dens_step x"); assert_same(host(dx0), wx0, "dens_step x0")
+
+
+@pytest.mark.parametrize("name", ["run_N14_K40", "run_N62_K20", "run_N126_K20", "run_N126_K40"])
+def test_reference_run_fixture(SF, name):
+    """The reference program's own run (glibc rand() initial condition, sources zeroed after step 0)
+    -- BASELINE config 1 is run_N126_K20 (G=128, 20 iterations, 100 steps) -- straight against the
+    fixtures the reference build produced."""
+    import torch
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    N, K = (int(v) for v in g["meta_N_K"])
+    s = SF.StableFluids(N)
+    dens, u, v = s.new_field(), s.new_field(), s.new_field()
+    dens_prev, u_prev, v_prev = dev(g["ic_dens_prev"]), dev(g["ic_u_prev"]), dev(g["ic_v_prev"])
+    done = 0
+    for upto in (int(x) for x in g["steps"]):
+        for k in range(done, upto):
+            if k > 0:
+                dens_prev.zero_(); u_prev.zero_(); v_prev.zero_()
+            s.step(dens, dens_prev, u, u_prev, v, v_prev, VIS, DIFF, DT, K)
+        done = upto
+        torch.cuda.synchronize()
+        for f, t in (("dens", dens), ("u", u), ("v", v)):
+            assert_same(host(t), g[f"{f}_step{upto}"], f"{name} {f} step {upto}")
+
+
+def test_step_1024_against_oracle(SF, oracle_mt):
+    """BASELINE config 2 size (G=1024, 20 iterations), synthetic hash initial condition generated
+    on the device and on the host from the same formula."""
+    N, K = 1022, 20
+    s = SF.StableFluids(N)
+    f = {k: s.new_field() for k in ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")}
+    s.init_synthetic(3, f["dens"], f["dens_prev"], f["u"], f["u_prev"], f["v"], f["v_prev"])
+    w = oracle_mt.init_synthetic(N, 3)
+    for k in w:
+        assert_same(host(f[k]), w[k], f"synthetic IC {k}")
+    for step in range(3):
+        if step > 0:
+            for k in ("dens_prev", "u_prev", "v_prev"):
+                f[k].zero_()
+        s.step(f["dens"], f["dens_prev"], f["u"], f["u_prev"], f["v"], f["v_prev"], VIS, DIFF, DT, K)
+        oracle_mt.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=step)
+        for k in w:
+            assert_same(host(f[k]), w[k], f"step {step} {k}")
+
+
+def test_fast_mode_tolerance(SF, oracle):
+    N, K = 254, 20
+    s = SF.StableFluids(N, arithmetic=SF.FAST)
+    w = oracle.init_synthetic(N, 11)
+    f = {k: dev(a) for k, a in w.items()}
+    for step in range(5):
+        if step > 0:
+            for k in ("dens_prev", "u_prev", "v_prev"):
+                f[k].zero_()
+        s.step(f["dens"], f["dens_prev"], f["u"], f["u_prev"], f["v"], f["v_prev"], VIS, DIFF, DT, K)
+        oracle.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=step)
+        for k in ("dens", "u", "v"):
+            got, want = host(f[k]), w[k]
+            assert rel_l2(got, want) <= 1e-6, (k, step, rel_l2(got, want))
+            assert np.abs(got - want).max() <= 1e-6 * max(np.abs(want).max(), 1e-30), (k, step)
+
+
+def test_step_host_matches_device_step(SF, oracle):
+    N, K = 126, 8
+    s = SF.StableFluids(N)
+    w = oracle.init_synthetic(N, 5)
+    h = {k: a.copy() for k, a in w.items()}
+    for step in range(2):
+        s.step_host(h["dens"], h["dens_prev"], h["u"], h["u_prev"], h["v"], h["v_prev"], VIS, DIFF, DT, K,
+                    download_scratch=True)
+        oracle.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=0)   # sources stay live: host passes them in
+        for k in w:
+            assert_same(h[k], w[k], f"step_host {k} step {step}")
+
+
+def test_errors_are_reported_not_fatal(SF):
+    s = SF.StableFluids(30)
+    x = s.new_field()
+    with pytest.raises(SF.StableFluidsError):
+        s.diffuse(0, x, x, 1.0, 4.0, 4)            # aliased
+    with pytest.raises(SF.StableFluidsError):
+        s.diffuse(3, x, s.new_field(), 1.0, 4.0, 4)  # bad b
+    with pytest.raises(SF.StableFluidsError):
+        s.diffuse(0, x, s.new_field(), 1.0, 4.0, 0)  # iters < 1
+    s.diffuse(0, x, s.new_field(), 1.0, 4.0, 1)      # context still usable
+
+
+def test_launch_counter_counts_kernels(SF):
+    s = SF.StableFluids(126)
+    f = [s.new_field() for _ in range(6)]
+    n0 = s.launch_count
+    s.step(*f, VIS, DIFF, DT, 40)
+    per_step = s.launch_count - n0
+    # 5 lin_solves of 6 launches (40 sweeps as 7,7,7,7,6,6) + add(2) + div(2) + grad(2) + advect(2)
+    assert per_step == 5 * 6 + 8, per_step
+    s.step(*f, VIS, DIFF, DT, 40); s.step(*f, VIS, DIFF, DT, 40)   # direct, then captured+replayed
+    assert s.launch_count - n0 == 3 * per_step
