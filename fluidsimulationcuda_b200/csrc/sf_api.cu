@@ -39,7 +39,9 @@ struct GraphEntry {
 struct sf_context {
     Geom g;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // the stream results are ordered on (own or caller's)
+    cudaStream_t work = nullptr;     // where launches go: == stream, or cap_stream while capturing
+    cudaStream_t cap_stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
     int arith = SF_ARITH_STRICT;
@@ -103,7 +105,15 @@ int ensure_scratch(sf_context *c)
 int arith_mode(const sf_context *c, float alpha, float beta)
 {
     if (alpha == 1.0f && beta == 4.0f) return MODE_PRESSURE;   // exact identity, see jacobi_cell
-    return c->arith == SF_ARITH_FAST ? MODE_FAST : MODE_STRICT;
+    if (c->arith == SF_ARITH_FAST) return MODE_FAST;
+    // STRICT: the 3-instruction exact division is used only for a beta that has been checked
+    // against __fdiv_rn over all 2^32 numerators (cached); the check cannot run inside a capture.
+    bool can_run = !c->capturing;
+    if (can_run) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(c->work, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) can_run = false;
+    }
+    return division_validated(beta, can_run, c->work) ? MODE_STRICT : MODE_IEEE;
 }
 
 int default_sweeps(const sf_context *c)
@@ -135,14 +145,14 @@ int one_jacobi_launch(sf_context *c, int b, float *xout, const float *xin, const
     L.zero_guess = zero_guess;
     const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
     if (stream_ok) {
-        SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, c->stream));
+        SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, c->work));
     } else {
         SF_REQUIRE(c, sweeps == 1, "generic Jacobi kernel does one sweep per launch");
         if (zero_guess) {
             // generic kernel always reads xin
-            SF_CUDA(c, cudaMemsetAsync(const_cast<float *>(xin), 0, field_cells(c) * sizeof(float), c->stream));
+            SF_CUDA(c, cudaMemsetAsync(const_cast<float *>(xin), 0, field_cells(c) * sizeof(float), c->work));
         }
-        SF_CUDA(c, launch_jacobi_generic(c->g, L, c->stream));
+        SF_CUDA(c, launch_jacobi_generic(c->g, L, c->work));
     }
     ++c->launches;
     return SF_OK;
@@ -161,7 +171,7 @@ int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, floa
         if (rc) return rc;
         float *t = cur; cur = nxt; nxt = t;
     }
-    if (cur != x) SF_CUDA(c, cudaMemcpyAsync(x, cur, field_cells(c) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    if (cur != x) SF_CUDA(c, cudaMemcpyAsync(x, cur, field_cells(c) * sizeof(float), cudaMemcpyDeviceToDevice, c->work));
     return SF_OK;
 }
 
@@ -182,7 +192,7 @@ int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const 
 {
     float *xs[1] = {x};
     const float *ss[1] = {x0};
-    SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->stream));
+    SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->work));
     ++c->launches;
     const float fN = (float)c->g.N;
     float alpha = dt * diff;      // FluidSequential.c:179, left to right in binary32
@@ -192,7 +202,7 @@ int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const 
     beta = 1.0f + beta;
     int rc = lin_solve(c, 0, x0, x, alpha, beta, iters, 0);   // SWAP; diffuse(0, x, x0): solves into the old x0
     if (rc) return rc;
-    SF_CUDA(c, launch_advect(c->g, 0, x, x0, u, v, dt, c->stream));   // SWAP; advect(0, x, x0, u, v)
+    SF_CUDA(c, launch_advect(c->g, 0, x, x0, u, v, dt, c->work));   // SWAP; advect(0, x, x0, u, v)
     ++c->launches;
     return SF_OK;
 }
@@ -201,11 +211,11 @@ int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int
 {
     // the streaming lin_solve can start from an implicit zero guess, so p need not be written here
     const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
-    SF_CUDA(c, launch_divergence(c->g, u, v, p, div, stream_ok ? 0 : 1, c->stream));
+    SF_CUDA(c, launch_divergence(c->g, u, v, p, div, stream_ok ? 0 : 1, c->work));
     ++c->launches;
     int rc = lin_solve(c, 0, p, div, 1.0f, 4.0f, iters, stream_ok ? 1 : 0);
     if (rc) return rc;
-    SF_CUDA(c, launch_last_project(c->g, u, v, p, c->stream));
+    SF_CUDA(c, launch_last_project(c->g, u, v, p, c->work));
     ++c->launches;
     return SF_OK;
 }
@@ -214,7 +224,7 @@ int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, fl
 {
     float *xs[2] = {u, v};
     const float *ss[2] = {u0, v0};
-    SF_CUDA(c, launch_add_source(c->g, 2, xs, ss, dt, c->stream));
+    SF_CUDA(c, launch_add_source(c->g, 2, xs, ss, dt, c->work));
     ++c->launches;
     const float fN = (float)c->g.N;
     float alpha = dt * visc;      // :199
@@ -228,7 +238,7 @@ int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, fl
     if (rc) return rc;
     rc = enqueue_project(c, u0, v0, u, v, iters);                      // :213-223 (p in u, div in v)
     if (rc) return rc;
-    SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, c->stream));   // :228-237
+    SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, c->work));   // :228-237
     ++c->launches;
     return enqueue_project(c, u, v, u0, v0, iters);                    // :238-240 (p in u0, div in v0)
 }
@@ -268,13 +278,18 @@ int run_graphed(sf_context *c, const GraphKey &key, Body body)
         c->graphs.push_back(GraphEntry{key, nullptr, nullptr, 0, c->tick});
         return body();
     }
+    // Capture on a private stream: the caller's stream may be the legacy default stream, which
+    // cannot be captured.  The instantiated graph is then launched on the caller's stream.
+    if (!c->cap_stream) SF_CUDA(c, cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
     const unsigned long long before = c->launches;
     c->capturing = true;
-    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    cudaError_t e = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { c->capturing = false; return fail(c, SF_ERR_CUDA, "cudaStreamBeginCapture", e); }
+    c->work = c->cap_stream;
     rc = body();
+    c->work = c->stream;
     cudaGraph_t graph = nullptr;
-    e = cudaStreamEndCapture(c->stream, &graph);
+    e = cudaStreamEndCapture(c->cap_stream, &graph);
     c->capturing = false;
     const unsigned long long kernels = c->launches - before;
     c->launches = before;
@@ -328,6 +343,7 @@ int create_common(sf_context **out, int N, int device, void *stream, bool own_st
     } else {
         c->stream = (cudaStream_t)stream;
     }
+    c->work = c->stream;
     *out = c;
     return SF_OK;
 }
@@ -360,6 +376,7 @@ int sf_destroy(sf_context *c)
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->h2d) cudaStreamDestroy(c->h2d);
     if (c->d2h) cudaStreamDestroy(c->d2h);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return SF_OK;
@@ -666,6 +683,16 @@ int sf_residual_l2(sf_context *c, const float *x, const float *x0, float alpha, 
     SF_CUDA(c, cudaMemcpyAsync(&sumsq, c->red_d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SF_CUDA(c, cudaStreamSynchronize(c->stream));
     *host_out = sumsq;   // caller takes sqrt after summing over slabs
+    return SF_OK;
+}
+
+int sf_division_check(sf_context *c, float beta, int *exact)
+{
+    if (!c || !exact) return SF_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    const bool can_run = cudaStreamIsCapturing(c->stream, &st) == cudaSuccess && st == cudaStreamCaptureStatusNone;
+    *exact = division_validated(beta, can_run, c->stream) ? 1 : 0;
     return SF_OK;
 }
 

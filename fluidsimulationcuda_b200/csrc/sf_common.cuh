@@ -17,23 +17,90 @@ struct Geom {
     int rows;      // rows stored locally (own_hi - own_lo + 2*halo)
 };
 
-enum ArithMode { MODE_STRICT = 0, MODE_PRESSURE = 1, MODE_FAST = 2 };
+enum ArithMode {
+    MODE_STRICT = 0,    // bit-identical; division by the constant beta via the exact FMA sequence below
+    MODE_PRESSURE = 1,  // bit-identical; alpha == 1, beta == 4
+    MODE_FAST = 2,      // opt-in: FMA contraction + reciprocal multiply (not bit-identical)
+    MODE_IEEE = 3       // bit-identical; plain __fdiv_rn (used when beta has not been validated)
+};
+
+// ---- correctly rounded division by a constant ---------------------------------------------------
+// a / b for a divisor that is constant over a launch, with y = RN(1/b) precomputed on the host.
+//  fast path (binary32, 3 FMA-pipe instructions):  q0 = RN(a*y);  e = RN(b*q0 - a) (exact);
+//     q1 = RN(q0 - e*y)  -- Markstein's FMA division step.  q1 == RN(a/b) whenever no intermediate
+//     under/overflows, which the range guard ensures (|a| in [1e-30, 1e30], or a == +-0: writing
+//     the residual as e = b*q0 - a makes zeros come out with the right sign).
+//  slow path (numerators in the subnormal-result range or huge): the same step in binary64 and one
+//     rounding to binary32.  The binary64 quotient is exact when a/b is representable and within
+//     2^-52 otherwise, while a binary32 quotient is never closer than 2^-49 (relative) to a
+//     rounding boundary, so the final rounding is the correct one.  Straight-line code: the decaying
+//     diffusion front of a density field (values of 1e-30 .. 1e-45) costs a few DP instructions per
+//     cell instead of the IEEE division's call-based special-case path, which made single warps
+//     ~8x slower than their neighbours and stretched whole launches.
+//  Neither path is trusted on paper: before a beta is used the library compares div_const with
+//  __fdiv_rn for ALL 2^32 numerator bit patterns on the device (validate_division in sf_jacobi.cu,
+//  ~5 ms, cached per beta); a beta that fails, or cannot be checked, runs MODE_IEEE.
+#define SF_DIV_LO 1e-30f
+#define SF_DIV_HI 1e30f
+struct DivConst {
+    float b, y;      // divisor, RN32(1/b)
+    double bd, yd;   // (double)b, RN64(1/b)
+};
+inline DivConst make_div_const(float b)
+{
+    DivConst d;
+    d.b = b; d.y = 1.0f / b;
+    d.bd = (double)b; d.yd = 1.0 / (double)b;
+    return d;
+}
+__device__ __forceinline__ float div_const_fast(float a, const DivConst &d)
+{
+    const float q0 = __fmul_rn(a, d.y);
+    const float e = __fmaf_rn(d.b, q0, -a);
+    return __fmaf_rn(-e, d.y, q0);
+}
+__device__ __forceinline__ bool div_in_range(float a)
+{
+    const float m = fabsf(a);
+    return ((m >= SF_DIV_LO) || (a == 0.0f)) && (m <= SF_DIV_HI);
+}
+__device__ __forceinline__ float div_const_slow(float a, const DivConst &d)
+{
+    if (!(fabsf(a) <= 3.4028234664e38f)) return __fmul_rn(a, d.y);   // +-inf, NaN
+    const double A = (double)a;
+    const double q0 = __dmul_rn(A, d.yd);
+    const double r = __fma_rn(-d.bd, q0, A);
+    return __double2float_rn(__fma_rn(r, d.yd, q0));
+}
+__device__ __forceinline__ float div_const(float a, const DivConst &d)
+{
+    const float q = div_const_fast(a, d);
+    return div_in_range(a) ? q : div_const_slow(a, d);
+}
 
 // One Jacobi cell update with the reference's operand order (FluidSequential.c:95-96):
 //   ((left + right) + up) + down ;  x0 + alpha*sum ;  / beta.
-// __fadd_rn/__fmul_rn are never contracted into FMAs by nvcc; __fdiv_rn is the IEEE division.
+// __fadd_rn/__fmul_rn are never contracted into FMAs by nvcc.
 //   MODE_PRESSURE: alpha == 1, beta == 4 exactly: 1*sum == sum and /4 == *0.25f are exact
 //                  identities in binary32 (also for subnormal results), so this is bit-identical
-//                  to the STRICT formula at a third of the instructions.
-//   MODE_FAST:     FMA + reciprocal multiply (opt-in, not bit-identical).
+//                  to the general formula at a fraction of the instructions.
+template <int MODE>
+__device__ __forceinline__ float jacobi_numerator(float l, float r, float up, float dn, float b, float alpha)
+{
+    const float s = __fadd_rn(__fadd_rn(__fadd_rn(l, r), up), dn);
+    if (MODE == MODE_PRESSURE) return __fadd_rn(b, s);
+    if (MODE == MODE_FAST) return __fmaf_rn(alpha, s, b);
+    return __fadd_rn(b, __fmul_rn(alpha, s));
+}
 template <int MODE>
 __device__ __forceinline__ float jacobi_cell(float l, float r, float up, float dn, float b, float alpha,
-                                             float beta, float rbeta)
+                                             const DivConst &d)
 {
-    float s = __fadd_rn(__fadd_rn(__fadd_rn(l, r), up), dn);
-    if (MODE == MODE_PRESSURE) return __fmul_rn(__fadd_rn(b, s), 0.25f);
-    if (MODE == MODE_FAST) return __fmul_rn(__fmaf_rn(alpha, s, b), rbeta);
-    return __fdiv_rn(__fadd_rn(b, __fmul_rn(alpha, s)), beta);
+    const float a = jacobi_numerator<MODE>(l, r, up, dn, b, alpha);
+    if (MODE == MODE_PRESSURE) return __fmul_rn(a, 0.25f);
+    if (MODE == MODE_FAST) return __fmul_rn(a, d.y);
+    if (MODE == MODE_STRICT) return div_const(a, d);
+    return __fdiv_rn(a, d.b);
 }
 
 __host__ __device__ __forceinline__ uint32_t hash100(uint64_t seed, uint64_t field, uint64_t cell)
@@ -61,6 +128,10 @@ struct JacobiLaunch {
 cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_count, cudaStream_t st);
 cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStream_t st);
 bool jacobi_stream_supported(const Geom &g);
+// Exhaustive device check of div_const against __fdiv_rn for this beta (cached per process).
+// Returns true when MODE_STRICT may be used.  Synchronises `st`; must not be called while `st`
+// is being captured (pass allow_run = false to only consult the cache).
+bool division_validated(float beta, bool allow_run, cudaStream_t st);
 
 cudaError_t launch_set_bnd(const Geom &g, int b, float *x, cudaStream_t st);
 cudaError_t launch_add_source(const Geom &g, int nfields, float *const *x, const float *const *s, float dt,

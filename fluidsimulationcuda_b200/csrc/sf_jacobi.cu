@@ -17,10 +17,17 @@
 //     applied in registers (the wall columns 0 and N+1 share a float4 with columns 1 / N because
 //     G % 4 == 0); wall rows are patched into the next level's window when row 1 / row N are
 //     produced.  Corners are never read by the 5-point stencil and are written with the last level.
+//     All of that lives in the WALLS=true instantiation of the tick, which only the two edge bands
+//     and the <= T+1 ticks next to the top/bottom walls execute; everything else runs the
+//     WALLS=false tick: per level 2 shuffles + 1 LDS.128 + the cell arithmetic.
 //   * Arithmetic per cell is jacobi_cell<MODE> (sf_common.cuh): same operand order as the reference.
 //
 // jacobi_generic_kernel<MODE> -- one sweep per launch, one thread per cell, any G (fallback for
 //   widths that are not a multiple of 4, e.g. the literal N=128 -> G=130).
+#include <cstring>
+#include <map>
+#include <mutex>
+
 #include "sf_common.cuh"
 
 namespace sf {
@@ -41,9 +48,10 @@ struct StreamArgs {
     int G, N, row_base;
     int a_lo, a_hi;      // interior output rows [a_lo, a_hi), subset of [1, N+1)
     int write_top, write_bot;
-    int chunk_rows, nbands;
+    int chunk_rows, nchunks, nbands;
     int zero_guess;
-    float alpha, beta, rbeta, sx, sy;
+    float alpha, sx, sy;
+    DivConst div;        // beta and its reciprocals
 };
 
 __device__ __forceinline__ void cp_async16(float4 *smem_dst, const float *gmem_src, int src_bytes)
@@ -60,51 +68,81 @@ __device__ __forceinline__ float4 scale4(float4 v, float s)
     return make_float4(__fmul_rn(v.x, s), __fmul_rn(v.y, s), __fmul_rn(v.z, s), __fmul_rn(v.w, s));
 }
 
+// Four adjacent cells of one row at one level.
+template <int MODE>
+__device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rgt, const float4 &up, const float4 &dn,
+                                          const float4 &r, float alpha, const DivConst &d)
+{
+    float4 o;
+    if (MODE == MODE_STRICT) {
+        const float a0 = jacobi_numerator<MODE>(lft, mid.y, up.x, dn.x, r.x, alpha);
+        const float a1 = jacobi_numerator<MODE>(mid.x, mid.z, up.y, dn.y, r.y, alpha);
+        const float a2 = jacobi_numerator<MODE>(mid.y, mid.w, up.z, dn.z, r.z, alpha);
+        const float a3 = jacobi_numerator<MODE>(mid.z, rgt, up.w, dn.w, r.w, alpha);
+        o.x = div_const_fast(a0, d);
+        o.y = div_const_fast(a1, d);
+        o.z = div_const_fast(a2, d);
+        o.w = div_const_fast(a3, d);
+        const bool ok0 = div_in_range(a0), ok1 = div_in_range(a1), ok2 = div_in_range(a2), ok3 = div_in_range(a3);
+        if (!(ok0 & ok1 & ok2 & ok3)) {   // subnormal-range or huge numerators: binary64 step, lane by lane
+            if (!ok0) o.x = div_const_slow(a0, d);
+            if (!ok1) o.y = div_const_slow(a1, d);
+            if (!ok2) o.z = div_const_slow(a2, d);
+            if (!ok3) o.w = div_const_slow(a3, d);
+        }
+    } else {
+        o.x = jacobi_cell<MODE>(lft, mid.y, up.x, dn.x, r.x, alpha, d);
+        o.y = jacobi_cell<MODE>(mid.x, mid.z, up.y, dn.y, r.y, alpha, d);
+        o.z = jacobi_cell<MODE>(mid.y, mid.w, up.z, dn.z, r.z, alpha, d);
+        o.w = jacobi_cell<MODE>(mid.z, rgt, up.w, dn.w, r.w, alpha, d);
+    }
+    return o;
+}
+
 // One pipeline tick: row `s` of level 0 enters; for t = 0..T-1 level t+1 of row s-t-1 is produced.
-// PAR selects which of the two window slots holds the older row (compile-time, so the windows
-// stay in registers with no moves).  Returns level T of row s-T in `out`.
-template <int T, int MODE, int PAR>
-__device__ __forceinline__ void pipeline_tick(const StreamArgs &A, int s, float4 in, float4 (&W0)[T], float4 (&W1)[T],
+// Each level keeps a window of three row slots W[t][0..2] that rotate with period 3: at phase PH
+// slot PH holds row a-1 (up), slot PH+1 row a (mid) and slot PH+2 receives row a+1 (dn), written by
+// the level below in this same tick.  PH is a compile-time constant, so after three ticks every
+// row is back in the register it started in and the hot loop contains no register moves.
+// WALLS adds the fused set_bnd handling.  Returns level T of row s-T in `out`.
+template <int T, int MODE, int PH, bool WALLS>
+__device__ __forceinline__ void pipeline_tick(const StreamArgs &A, int s, const float4 &row_in, float4 (&W)[T][3],
                                               const float4 *rring, bool ownsL, bool ownsR, float4 &out)
 {
+    constexpr int UP = PH % 3, MID = (PH + 1) % 3, DN = (PH + 2) % 3;
+    W[0][DN] = row_in;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        float4 &older = PAR ? W1[t] : W0[t];   // row a-1 of level t
-        float4 &newer = PAR ? W0[t] : W1[t];   // row a   of level t
         const int a = s - t - 1;               // row produced at level t+1
-        const float4 up = older, mid = newer, dn = in;
+        const float4 up = W[t][UP], mid = W[t][MID], dn = W[t][DN];
         const float4 r = rring[(a & (RING_R - 1)) * 32];
         const float lft = __shfl_up_sync(0xffffffffu, mid.w, 1);
         const float rgt = __shfl_down_sync(0xffffffffu, mid.x, 1);
-        float4 o;
-        o.x = jacobi_cell<MODE>(lft, mid.y, up.x, dn.x, r.x, A.alpha, A.beta, A.rbeta);
-        o.y = jacobi_cell<MODE>(mid.x, mid.z, up.y, dn.y, r.y, A.alpha, A.beta, A.rbeta);
-        o.z = jacobi_cell<MODE>(mid.y, mid.w, up.z, dn.z, r.z, A.alpha, A.beta, A.rbeta);
-        o.w = jacobi_cell<MODE>(mid.z, rgt, up.w, dn.w, r.w, A.alpha, A.beta, A.rbeta);
-        // wall columns: x[row][0] = sx * x[row][1], x[row][N+1] = sx * x[row][N]
-        if (ownsL) o.x = __fmul_rn(A.sx, o.y);
-        if (ownsR) o.w = __fmul_rn(A.sx, o.z);
-        // retire the oldest row of level t: its slot takes the incoming row
-        older = dn;
-        if (t + 1 < T) {
-            // wall rows of level t+1 live in the NEXT level's window
-            float4 &nx_newer = PAR ? W0[t + 1] : W1[t + 1];  // row a-1 of level t+1 at this point
-            if (a == A.N + 1) o = scale4(nx_newer, A.sy);     // row N+1 = sy * row N
-            if (a == 1) nx_newer = scale4(o, A.sy);           // row 0   = sy * row 1
+        float4 o = jacobi4<MODE>(lft, mid, rgt, up, dn, r, A.alpha, A.div);
+        if (WALLS) {
+            // wall columns: x[row][0] = sx * x[row][1], x[row][N+1] = sx * x[row][N]
+            if (ownsL) o.x = __fmul_rn(A.sx, o.y);
+            if (ownsR) o.w = __fmul_rn(A.sx, o.z);
+            if (t + 1 < T) {
+                // wall rows of level t+1 live in the NEXT level's window: its MID slot is row a-1
+                if (a == A.N + 1) o = scale4(W[t + 1][MID], A.sy);     // row N+1 = sy * row N
+                if (a == 1) W[t + 1][MID] = scale4(o, A.sy);           // row 0   = sy * row 1
+            }
         }
-        in = o;
+        if (t + 1 < T) W[t + 1][DN] = o; else out = o;
     }
-    out = in;
 }
 
 template <int T, int MODE>
-__global__ void __launch_bounds__(WPC * 32) jacobi_stream_kernel(const StreamArgs A)
+__global__ void __launch_bounds__(WPC * 32, 4) jacobi_stream_kernel(const StreamArgs A)
 {
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int band = blockIdx.x * WPC + warp;
-    if (band >= A.nbands) return;
-    const int a_lo = A.a_lo + blockIdx.y * A.chunk_rows;
+    // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk
+    const int item = blockIdx.x * WPC + warp;
+    if (item >= A.nbands * A.nchunks) return;
+    const int band = item % A.nbands, chunk = item / A.nbands;
+    const int a_lo = A.a_lo + chunk * A.chunk_rows;
     const int a_hi = min(a_lo + A.chunk_rows, A.a_hi);
     if (a_lo >= a_hi) return;
 
@@ -112,6 +150,7 @@ __global__ void __launch_bounds__(WPC * 32) jacobi_stream_kernel(const StreamArg
     const bool indom = (c >= 0) && (c + 4 <= A.G);
     const bool ownsL = (c == 0), ownsR = (c + 4 == A.G);
     const bool st_ok = indom && lane >= HALO_X / 4 && lane < 32 - HALO_X / 4;
+    const bool edge_band = (band == 0) || (band == A.nbands - 1);   // the bands holding columns 0 / N+1
     const int cc = indom ? c : 0;
     const int nbytes = indom ? 16 : 0;
 
@@ -134,19 +173,28 @@ __global__ void __launch_bounds__(WPC * 32) jacobi_stream_kernel(const StreamArg
         }
         cp_async_commit();
     };
+    auto fetch = [&](int row) -> float4 {   // level-0 row `row` (after its cp.async group landed)
+        issue(row + PREFETCH);
+        cp_async_wait<PREFETCH>();
+        float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!zero_guess && row <= load_hi) in = xring[(row & (RING_X - 1)) * 32];
+        return in;
+    };
 
-    float4 W0[T], W1[T];
+    float4 W[T][3];
 #pragma unroll
-    for (int t = 0; t < T; ++t) W0[t] = W1[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) W[t][0] = W[t][1] = W[t][2] = make_float4(0.f, 0.f, 0.f, 0.f);
 
 #pragma unroll
     for (int k = 0; k < PREFETCH; ++k) issue(s_lo + k);
 
     float *orow = A.xout + cc;
-    auto emit = [&](int a, const float4 &o) {
+    auto emit_plain = [&](int a, const float4 &o) {
+        if (a >= a_lo && a < a_hi && st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
+    };
+    auto emit_walls = [&](int a, const float4 &o) {
         if (a < a_lo || a >= a_hi) return;
-        float4 *dst = reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch);
-        if (st_ok) *dst = o;
+        if (st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
         if (a == 1 && A.write_top) {
             float4 w = scale4(o, A.sy);
             if (ownsL) w.x = __fmul_rn(0.5f, __fadd_rn(w.y, o.x));   // x[0][0] = .5*(x[0][1] + x[1][0])
@@ -160,30 +208,32 @@ __global__ void __launch_bounds__(WPC * 32) jacobi_stream_kernel(const StreamArg
             if (st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(A.N + 1 - A.row_base) * pitch) = w;
         }
     };
+    // The wall logic is needed when some level produces row 1 or row N+1 (s-t-1 in {1, N+1}, t < T),
+    // when the last level emits row 1 or row N (s = T+1, s = N+T), or in an edge band; i.e. for
+    // s <= T+1, for s > N, and for every tick of the two edge bands.  Everything else runs the
+    // wall-free tick in groups of three (one full rotation of the windows).
+    const int fast_lo = T + 2;
+    const int fast_hi = edge_band ? -1 : min(s_hi, A.N);
 
     int s = s_lo;
     while (s <= s_hi) {
-        {
-            issue(s + PREFETCH);
-            cp_async_wait<PREFETCH>();
-            float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!zero_guess && s <= load_hi) in = xring[(s & (RING_X - 1)) * 32];
-            float4 o;
-            pipeline_tick<T, MODE, 0>(A, s, in, W0, W1, rring, ownsL, ownsR, o);
-            emit(s - T, o);
-            ++s;
+        float4 o;
+        if (s >= fast_lo && s + 2 <= fast_hi) {
+            pipeline_tick<T, MODE, 0, false>(A, s, fetch(s), W, rring, false, false, o);
+            emit_plain(s - T, o);
+            pipeline_tick<T, MODE, 1, false>(A, s + 1, fetch(s + 1), W, rring, false, false, o);
+            emit_plain(s + 1 - T, o);
+            pipeline_tick<T, MODE, 2, false>(A, s + 2, fetch(s + 2), W, rring, false, false, o);
+            emit_plain(s + 2 - T, o);
+            s += 3;
+            continue;
         }
-        if (s > s_hi) break;
-        {
-            issue(s + PREFETCH);
-            cp_async_wait<PREFETCH>();
-            float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!zero_guess && s <= load_hi) in = xring[(s & (RING_X - 1)) * 32];
-            float4 o;
-            pipeline_tick<T, MODE, 1>(A, s, in, W0, W1, rring, ownsL, ownsR, o);
-            emit(s - T, o);
-            ++s;
-        }
+        // general tick at phase 0, then rotate the windows back to phase 0 by moving registers
+        pipeline_tick<T, MODE, 0, true>(A, s, fetch(s), W, rring, ownsL, ownsR, o);
+        emit_walls(s - T, o);
+#pragma unroll
+        for (int t = 0; t < T; ++t) { W[t][0] = W[t][1]; W[t][1] = W[t][2]; }
+        ++s;
     }
     cp_async_wait<0>();
 }
@@ -192,14 +242,14 @@ __global__ void __launch_bounds__(WPC * 32) jacobi_stream_kernel(const StreamArg
 template <int MODE>
 __global__ void jacobi_generic_kernel(const float *__restrict__ xin, const float *__restrict__ rhs,
                                       float *__restrict__ xout, Geom g, int a_lo, int a_hi, int write_top,
-                                      int write_bot, float alpha, float beta, float rbeta, float sx, float sy)
+                                      int write_bot, float alpha, DivConst d, float sx, float sy)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int row = blockIdx.y * blockDim.y + threadIdx.y + a_lo;
     if (col > g.N || row >= a_hi) return;
     const size_t G = (size_t)g.G;
     const size_t i = (size_t)(row - g.row_base) * G + col;
-    const float o = jacobi_cell<MODE>(xin[i - 1], xin[i + 1], xin[i - G], xin[i + G], rhs[i], alpha, beta, rbeta);
+    const float o = jacobi_cell<MODE>(xin[i - 1], xin[i + 1], xin[i - G], xin[i + G], rhs[i], alpha, d);
     xout[i] = o;
     const float wx = __fmul_rn(sx, o), wy = __fmul_rn(sy, o);
     const bool L = (col == 1), R = (col == g.N);
@@ -212,6 +262,21 @@ __global__ void jacobi_generic_kernel(const float *__restrict__ xin, const float
     if (R && Tp) xout[i - G + 1] = __fmul_rn(0.5f, __fadd_rn(wy, wx));
     if (L && Bt) xout[i + G - 1] = __fmul_rn(0.5f, __fadd_rn(wy, wx));
     if (R && Bt) xout[i + G + 1] = __fmul_rn(0.5f, __fadd_rn(wy, wx));
+}
+
+// ---- exhaustive validation of div_const for one beta ----------------------------------------
+__global__ void validate_division_kernel(DivConst d, unsigned long long *mismatches)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u < (1ull << 32); u += stride) {
+        const float a = __uint_as_float((unsigned)u);
+        if (a != a) continue;   // NaN numerators: payload propagation is not part of the contract
+        const float want = __fdiv_rn(a, d.b);
+        const float got = div_const(a, d);
+        bad += (__float_as_uint(want) != __float_as_uint(got));
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 template <int T, int MODE>
@@ -239,9 +304,37 @@ cudaError_t launch_stream_mode(int T, const StreamArgs &A, dim3 grid, size_t sme
     }
 }
 
+std::mutex g_div_mutex;
+std::map<uint32_t, bool> g_div_ok;   // beta bits -> div_const verified bit-identical to __fdiv_rn
+
 }  // namespace
 
 bool jacobi_stream_supported(const Geom &g) { return (g.G % 4) == 0 && g.G >= 4; }
+
+bool division_validated(float beta, bool allow_run, cudaStream_t st)
+{
+    if (!(beta > 0.0f) || !(beta < 3.0e38f) || beta < 1.2e-38f) return false;
+    uint32_t key;
+    std::memcpy(&key, &beta, sizeof(key));
+    std::lock_guard<std::mutex> lock(g_div_mutex);
+    auto it = g_div_ok.find(key);
+    if (it != g_div_ok.end()) return it->second;
+    if (!allow_run) return false;
+    unsigned long long *dev = nullptr, host = ~0ull;
+    bool ok = false;
+    if (cudaMalloc(&dev, sizeof(*dev)) == cudaSuccess) {
+        if (cudaMemsetAsync(dev, 0, sizeof(*dev), st) == cudaSuccess) {
+            validate_division_kernel<<<148 * 16, 256, 0, st>>>(make_div_const(beta), dev);
+            if (cudaGetLastError() == cudaSuccess &&
+                cudaMemcpyAsync(&host, dev, sizeof(host), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                cudaStreamSynchronize(st) == cudaSuccess)
+                ok = (host == 0);
+        }
+        cudaFree(dev);
+    }
+    g_div_ok[key] = ok;
+    return ok;
+}
 
 cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_count, cudaStream_t st)
 {
@@ -255,28 +348,34 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     A.write_bot = (L.out_hi == g.G);
     A.nbands = (g.G + VALID_W - 1) / VALID_W;
     A.zero_guess = L.zero_guess;
-    A.alpha = L.alpha; A.beta = L.beta; A.rbeta = 1.0f / L.beta;
+    A.alpha = L.alpha; A.div = make_div_const(L.beta);
     A.sx = (L.b == 1) ? -1.0f : 1.0f;
     A.sy = (L.b == 2) ? -1.0f : 1.0f;
     const int rows = A.a_hi - A.a_lo;
     if (rows <= 0) return cudaSuccess;
-    const int ctas_x = (A.nbands + WPC - 1) / WPC;
     int chunk = L.chunk_rows;
     if (chunk <= 0) {
-        // aim at ~3 CTAs per SM in flight, but keep the redundant 2T halo rows under ~1/8 of a chunk
-        int want_chunks = (3 * sm_count + ctas_x - 1) / ctas_x;
+        // One work item (band x chunk) per resident warp: 16 warps per SM (4 CTAs of 4 warps).  All
+        // items cost about the same, so a single full wave has no tail; chunks are kept >= 16 T rows so
+        // that the 2T redundant halo rows stay a small share.
+        const int slots = sm_count * 4 * WPC;
+        int want_chunks = slots / A.nbands;
+        if (want_chunks < 1) want_chunks = 1;
         chunk = (rows + want_chunks - 1) / want_chunks;
         const int min_chunk = 16 * L.sweeps;
         if (chunk < min_chunk) chunk = min_chunk;
     }
     if (chunk > rows) chunk = rows;
     A.chunk_rows = chunk;
-    dim3 grid(ctas_x, (rows + chunk - 1) / chunk);
+    A.nchunks = (rows + chunk - 1) / chunk;
+    const int items = A.nbands * A.nchunks;
+    dim3 grid((items + WPC - 1) / WPC);
     const size_t smem = (size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4);
     switch (L.mode) {
         case MODE_PRESSURE: return launch_stream_mode<MODE_PRESSURE>(L.sweeps, A, grid, smem, st);
         case MODE_FAST: return launch_stream_mode<MODE_FAST>(L.sweeps, A, grid, smem, st);
-        default: return launch_stream_mode<MODE_STRICT>(L.sweeps, A, grid, smem, st);
+        case MODE_STRICT: return launch_stream_mode<MODE_STRICT>(L.sweeps, A, grid, smem, st);
+        default: return launch_stream_mode<MODE_IEEE>(L.sweeps, A, grid, smem, st);
     }
 }
 
@@ -286,17 +385,18 @@ cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStre
     const int a_lo = max(L.out_lo, 1), a_hi = min(L.out_hi, g.N + 1);
     if (a_hi <= a_lo) return cudaSuccess;
     dim3 block(64, 4), grid((g.N + 63) / 64, (a_hi - a_lo + 3) / 4);
-    const float sx = (L.b == 1) ? -1.0f : 1.0f, sy = (L.b == 2) ? -1.0f : 1.0f, rb = 1.0f / L.beta;
+    const float sx = (L.b == 1) ? -1.0f : 1.0f, sy = (L.b == 2) ? -1.0f : 1.0f;
+    const DivConst dc = make_div_const(L.beta);
     const int wt = (L.out_lo == 0), wb = (L.out_hi == g.G);
     switch (L.mode) {
         case MODE_PRESSURE:
-            jacobi_generic_kernel<MODE_PRESSURE><<<grid, block, 0, st>>>(L.xin, L.rhs, L.xout, g, a_lo, a_hi, wt, wb, L.alpha, L.beta, rb, sx, sy);
+            jacobi_generic_kernel<MODE_PRESSURE><<<grid, block, 0, st>>>(L.xin, L.rhs, L.xout, g, a_lo, a_hi, wt, wb, L.alpha, dc, sx, sy);
             break;
         case MODE_FAST:
-            jacobi_generic_kernel<MODE_FAST><<<grid, block, 0, st>>>(L.xin, L.rhs, L.xout, g, a_lo, a_hi, wt, wb, L.alpha, L.beta, rb, sx, sy);
+            jacobi_generic_kernel<MODE_FAST><<<grid, block, 0, st>>>(L.xin, L.rhs, L.xout, g, a_lo, a_hi, wt, wb, L.alpha, dc, sx, sy);
             break;
-        default:
-            jacobi_generic_kernel<MODE_STRICT><<<grid, block, 0, st>>>(L.xin, L.rhs, L.xout, g, a_lo, a_hi, wt, wb, L.alpha, L.beta, rb, sx, sy);
+        default:   // STRICT and IEEE: the fallback kernel is not a hot path, use the plain IEEE division
+            jacobi_generic_kernel<MODE_IEEE><<<grid, block, 0, st>>>(L.xin, L.rhs, L.xout, g, a_lo, a_hi, wt, wb, L.alpha, dc, sx, sy);
     }
     return cudaGetLastError();
 }

@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "sf_set_bnd", "sf_add_source", "sf_diffuse", "sf_advect", "sf_compute_divergence_and_pressure",
     "sf_last_project", "sf_project", "sf_dens_step", "sf_vel_step", "sf_step", "sf_step_host",
     "sf_init_synthetic", "sf_init_sources", "sf_reduce_max_abs", "sf_residual_l2",
-    "sf_halo_rows_needed", "sf_jacobi_launch",
+    "sf_division_check", "sf_halo_rows_needed", "sf_jacobi_launch",
 ]
 
 _lib = None
@@ -89,6 +89,7 @@ def load_library() -> C.CDLL:
     L.sf_init_sources.argtypes = [vp, u64] + [vp] * 3
     L.sf_reduce_max_abs.argtypes = [vp, vp, C.POINTER(f)]
     L.sf_residual_l2.argtypes = [vp, vp, vp, f, f, C.POINTER(C.c_double)]
+    L.sf_division_check.argtypes = [vp, f, C.POINTER(i)]
     L.sf_halo_rows_needed.argtypes = [vp, C.POINTER(i)]
     L.sf_jacobi_launch.argtypes = [vp, i, vp, vp, vp, f, f, i, i, i]
     for name in ABI_SYMBOLS:
@@ -229,6 +230,11 @@ class StableFluids:
         out = C.c_double(0)
         self._check(self.L.sf_residual_l2(self.h, self._p(x), self._p(x0), alpha, beta, C.byref(out)))
         return float(out.value)
+
+    def division_check(self, beta) -> bool:
+        out = C.c_int(0)
+        self._check(self.L.sf_division_check(self.h, beta, C.byref(out)))
+        return bool(out.value)
 
     def jacobi_launch(self, b, xout, xin, x0, alpha, beta, sweeps, out_lo=-1, out_hi=-1):
         self._check(self.L.sf_jacobi_launch(self.h, b, self._p(xout), self._p(xin), self._p(x0), alpha, beta,
