@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the stable-fluids time step (vel_step + dens_step) -- the BASELINE.json metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid G] [--iters K]
+
+One "step" = one pass of the reference's main-loop body (FluidSequential.c:289-312): refresh the
+three source fields, vel_step, dens_step, on synthetic fields of the named size.
+  N = 1 : G = 8192 (N = 8190 interior), 40 Jacobi iterations per lin_solve -- BASELINE configs[2],
+          the configuration the metric is quoted on.
+  N > 1 : G = 32768, 40 iterations, row slabs over the N ranks with neighbour halo exchange
+          (BASELINE configs[3]); launched by torchrun, one rank per GPU, NCCL.
+metric = Jacobi cell-updates/s = 5 * iters * N^2 * steps / time (five lin_solves per step); the
+whole step (add_source, advect, divergence, gradient subtract, set_bnd) is inside the timed region.
+
+Rank 0 prints ONE JSON line.  --impl reference times the reference's own sequential CPU code
+(oracle/_ref, built from the reference's source) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT, VIS, DIFF = 0.016, 0.0025, 0.1        # the reference's literals (FluidSequential.c:7-9)
+HBM_FALLBACK_GBS = 6650.0                  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for n, val in zip(names, s[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        # "under load": the upper half of the samples (the sampler also sees the idle lead-in)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own sequential CPU implementation, one thread (it has no threading).
+    Each "step" is a bounded sample of the workload: one dens_step (add_source + one `iters`-sweep
+    lin_solve + advect = 1/5 of a step's Jacobi work) at the full grid size."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle.pyoracle import Oracle, ReferenceSeq
+    G, K = args.grid, args.iters
+    N = G - 2
+    if ReferenceSeq.available(N, K):
+        ref, kind = ReferenceSeq(N, K), "reference"
+        step = lambda x, x0, u, v: ref.dens_step(x, x0, u, v, DIFF)
+    else:   # no build of the reference for this (N, K): the pinned restatement
+        orc, kind = Oracle(), "port"
+        step = lambda x, x0, u, v: orc.dens_step(N, x, x0, u, v, DIFF, DT, K)
+    o = Oracle(threads=True)
+    f = o.init_synthetic(N, 1)
+    x, u, v = f["dens"], f["u_prev"] * np.float32(0.5), f["v_prev"] * np.float32(0.5)
+    times = []
+    for i in range(args.warmup + args.steps):
+        x0 = f["dens_prev"].copy()           # live sources every step (early-step values: no subnormals)
+        t = time.perf_counter(); step(x, x0, u, v); dt_ = time.perf_counter() - t
+        if i >= args.warmup:
+            times.append(dt_)
+    total = sum(times)
+    value = K * N * N * len(times) / total
+    sample = f"dens_step (add_source + {K}-sweep lin_solve + advect) at G={G}: 1/5 of a step's Jacobi work per sample"
+    print(json.dumps({
+        "impl": "reference", "metric": "jacobi_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"stable-fluids step G={G} (N={N}), {K} Jacobi iterations", "grid": G, "iters": K},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def cpu_baseline(G, K):
+    """Reference sequential path (and its SIMD-SSE program) on this box's host cores, bounded sample."""
+    import numpy as np
+    from oracle.pyoracle import Oracle, ReferenceSeq
+    N = G - 2
+    out = {}
+    try:
+        o = Oracle(threads=True)
+        f = o.init_synthetic(N, 1)
+        x, x0 = f["dens"], f["dens_prev"]
+        u, v = f["u_prev"] * np.float32(0.5), f["v_prev"] * np.float32(0.5)
+        if ReferenceSeq.available(N, K):
+            ref, kind = ReferenceSeq(N, K), "reference"
+            t = time.perf_counter(); ref.dens_step(x, x0, u, v, DIFF); dt_ = time.perf_counter() - t
+        else:
+            kind = "port"
+            orc = Oracle()
+            t = time.perf_counter(); orc.dens_step(N, x, x0, u, v, DIFF, DT, K); dt_ = time.perf_counter() - t
+        out = {"value": K * N * N / dt_, "unit": "cell-updates/s", "cores": 1, "kind": kind,
+               "sample": f"one dens_step (add_source + {K}-sweep lin_solve + advect) at G={G}, {dt_:.2f} s, "
+                         f"sequential reference, 1 thread (the reference has no threading)",
+               "host_cpus": os.cpu_count()}
+    except Exception as e:   # the baseline is reported, never fatal
+        out = {"value": None, "unit": "cell-updates/s", "cores": 1, "kind": "unavailable", "sample": repr(e)}
+    simd = os.path.join(ROOT, "oracle", "_ref", f"ref_simd_N{N}_K{K}")
+    if os.path.exists(simd):
+        try:
+            t = time.perf_counter()
+            r = subprocess.run([simd], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=120)
+            dt_ = time.perf_counter() - t
+            el = [l for l in r.stdout.splitlines() if "elapsed" in l]
+            if el:
+                dt_ = float(el[-1].split("elapsed")[1].split()[0])
+            out["simd_sse"] = {"value": 5 * K * N * N / dt_, "unit": "cell-updates/s", "cores": 1,
+                               "sample": f"the reference's SIMD-SSE program, one full step incl. its rand() init at G={G}, "
+                                         f"{dt_:.2f} s (timing only: its interior lanes are numerically wrong as shipped)"}
+        except Exception as e:
+            out["simd_sse"] = {"value": None, "sample": repr(e)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fluidsimulationcuda_b200 import build
+    from fluidsimulationcuda_b200 import solver as SF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    build.build()
+    G, K = args.grid, args.iters
+    N = G - 2
+    cells = G * G
+    peak, peak_how = measured_peak()
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        from fluidsimulationcuda_b200.slab import SlabSolver
+        sim = SlabSolver(N, rank, world, iters=K, arithmetic=SF.STRICT)
+        step = lambda seed: sim.step(seed, VIS, DIFF, DT)
+        sync = lambda: (torch.cuda.synchronize(), dist.barrier())
+        launches = lambda: sim.launch_count
+    else:
+        s = SF.StableFluids(N)
+        f = [s.new_field() for _ in range(6)]       # dens, dens_prev, u, u_prev, v, v_prev
+        s.init_synthetic(1, *f)
+
+        def step(seed):
+            s.init_sources(seed, f[1], f[3], f[5])  # the loop's per-step source refresh, on the device
+            s.step(*f, VIS, DIFF, DT, K)
+        sync = torch.cuda.synchronize
+        launches = lambda: s.launch_count
+
+    for i in range(args.warmup):
+        step(100 + i)
+    sync()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = launches()
+    sync()
+    ev0.record()
+    for i in range(args.steps):
+        step(1000 + i)
+    ev1.record()
+    sync()
+    ms = ev0.elapsed_time(ev1)
+    n_launch = launches() - n0
+    clocks = sampler.finish() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tl = torch.tensor([n_launch], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        n_launch = int(tl.item())
+    ms_step = ms / args.steps
+    value = 5.0 * K * N * N / (ms_step * 1e-3)
+    step_bytes = (60.0 * K + 148.0) * cells          # algorithmic bytes per step
+    eff_gbs = step_bytes / (ms_step * 1e-3) / 1e9
+
+    out = {
+        "metric": "jacobi_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"stable-fluids step (vel_step + dens_step) G={G} (N={N}), {K} Jacobi iterations per lin_solve, "
+                               f"STRICT arithmetic (bit-identical to the reference's sequential path)",
+                   "grid": G, "iters": K, "parallelism": f"row slabs x{world}" if world > 1 else "single GPU",
+                   "l2": "every field (G^2*4 B = %.0f MiB) is larger than the 126 MB L2; 9 fields live" % (cells * 4 / 2**20),
+                   "per_step": "device-side source refresh + vel_step + dens_step, replayed from a CUDA graph"},
+        "full_step_cells_per_s": cells / (ms_step * 1e-3),
+        "effective_hbm_gbs": eff_gbs, "effective_hbm_frac_of_measured_peak": eff_gbs / (peak * world),
+        "gpu_launches": n_launch, "clocks": clocks,
+    }
+
+    if world == 1:
+        # ---- roofline of the dominant kernel: jacobi_stream_kernel, timed per lin_solve with CUDA events on
+        # the context's stream (graphs off for this instrumented pass; same kernels, same launch plan)
+        sr = SF.StableFluids(N, use_graph=False)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        import numpy as np
+        f32 = np.float32
+        al = f32(DT) * f32(VIS); al = al * f32(N); al = al * f32(N); be = f32(1) + f32(4) * al
+        n0 = sr.launch_count
+        tot_ms, sweeps = 0.0, 0
+        for rep in range(3):
+            for (b_, x, x0, alpha, beta) in ((1, f[3], f[2], float(al), float(be)), (0, f[1], f[0], 1.0, 4.0)):
+                a.record(); sr.diffuse(b_, x, x0, alpha, beta, K); b.record(); torch.cuda.synchronize()
+                if rep > 0:
+                    tot_ms += a.elapsed_time(b); sweeps += K
+        jl = (sr.launch_count - n0) // 3 // 2
+        alg_bytes_per_launch = 12.0 * cells * K / jl
+        achieved = 12.0 * cells * sweeps / (tot_ms * 1e-3) / 1e9
+        out["roofline"] = {
+            "kernel": "jacobi_stream_kernel (temporally blocked lin_solve)", "bound": "hbm",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_how,
+            "traffic": PROFILED_DRAM_BYTES_PER_LAUNCH.get(G),
+            "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launches_per_lin_solve": jl,
+            "avg_launch_ms": tot_ms / (sweeps / K) / jl,
+            "note": "algorithmic bytes = 12 B per cell per sweep (read x, read x0, write x'); one launch fuses "
+                    f"{K}/{jl} sweeps, so achieved exceeds the DRAM peak by design; traffic = ncu dram bytes per launch",
+        }
+        sr.close()
+        # ---- end to end through the host-buffer entry point (sf_step_host): pinned host fields,
+        # H2D of all six fields and D2H of dens,u,v inside the timed region, every step
+        try:
+            hf = [torch.empty((G, G), dtype=torch.float32).pin_memory() for _ in range(6)]
+            for h, d in zip(hf, f):
+                h.copy_(d)
+            for _ in range(2):
+                s.step_host(*hf, VIS, DIFF, DT, K)
+            torch.cuda.synchronize()
+            n_e2e = max(3, min(args.steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                s.step_host(*hf, VIS, DIFF, DT, K)
+            torch.cuda.synchronize()
+            dt_ = (time.perf_counter() - t0) / n_e2e
+            out["e2e"] = {"value": 5.0 * K * N * N / dt_, "unit": "cell-updates/s", "ms_per_step": dt_ * 1e3,
+                          "h2d_bytes_per_step": 6 * cells * 4, "d2h_bytes_per_step": 3 * cells * 4,
+                          "api": "sf_step_host (C ABI): six pinned host fields in, dens/u/v out, copies overlapped with compute"}
+            del hf
+        except Exception as e:
+            out["e2e"] = {"value": None, "unit": "cell-updates/s", "error": repr(e)}
+        out["cpu_baseline"] = cpu_baseline(G, K)
+    elif rank == 0:
+        out["e2e"] = {"value": None, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                      "note": "host-buffer entry point is single-GPU; see the N=1 line"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ncu `dram__bytes_read.sum + dram__bytes_write.sum` per jacobi_stream_kernel launch, from the
+# committed capture profiles/ (see profiles/README.md); None until a capture exists for that size.
+PROFILED_DRAM_BYTES_PER_LAUNCH = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as _f:
+        PROFILED_DRAM_BYTES_PER_LAUNCH = {int(k): v for k, v in json.load(_f).items()}
+except Exception:
+    pass
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=0, help="full grid width G = N+2 (default 8192 at 1 GPU, 32768 at >1)")
+    ap.add_argument("--iters", type=int, default=40)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.grid == 0:
+            args.grid = 8192      # the reference arm always samples the single-GPU configuration
+        run_reference(args)
+        return
+    if args.grid == 0:
+        args.grid = 8192 if world == 1 else 32768
+    args.warmup = max(args.warmup, 3)
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

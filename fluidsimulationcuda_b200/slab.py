@@ -1,0 +1,341 @@
+"""Row-slab domain decomposition of the stable-fluids step over the GPUs of one box.
+
+The reference has no multi-GPU path; this is the north star's slab scheme:
+rank r owns global rows [r*G/p, (r+1)*G/p) of every field and stores them with `halo` ghost rows
+above and below.  Every stage is a radius-1 stencil or a bounded-reach gather, so the only
+communication is a NEIGHBOUR exchange of a few contiguous rows:
+
+  lin_solve  T rows of the iterate per temporally blocked launch of T sweeps (plus T rows of the
+             right-hand side once per solve); the two T-row boundary strips are computed first,
+             their exchange is put in flight (NCCL send/recv on NCCL's own stream) and the interior
+             launch runs meanwhile;
+  divergence / gradient subtract   1 row;
+  advect     W = ceil(dt*N*max|vel|) + 2 rows of the advected field, W from a MAX all-reduce.
+
+Results are independent of the partition (no reduction enters the update): every p gives the
+bit-identical fields of the single-GPU path (tests/test_slab_gpu.py).
+
+The arithmetic runs in libstablefluids_b200.so through slab contexts (sf_create_slab,
+sf_jacobi_launch); this module only sequences launches and exchanges.  ``SlabSolver.step_gen`` is a
+generator that yields the communication requests, so that the same code is driven by NCCL
+(one process per GPU, ``TorchDistComm``) or in lock-step inside one process for tests
+(``run_lockstep``: p emulated ranks on one GPU, halos copied directly).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import solver as SF
+
+
+def partition_rows(G: int, world: int) -> List[Tuple[int, int]]:
+    """Owned row ranges [lo, hi) per rank: contiguous, covering [0, G), sizes differ by at most 1."""
+    if world < 1 or G < 2 * world:
+        raise ValueError("need at least two rows per rank")
+    return [(r * G // world, (r + 1) * G // world) for r in range(world)]
+
+
+def plan_launches(iters: int, T: int) -> List[int]:
+    """Split `iters` sweeps into launches of at most T sweeps; an even number of launches leaves
+    the result of the x <-> scratch ping-pong in x (mirrors plan_launches in csrc/sf_api.cu)."""
+    L = (iters + T - 1) // T
+    if (L & 1) and L + 1 <= iters:
+        L += 1
+    plan = [iters // L] * L
+    for k in range(iters % L):
+        plan[k] += 1
+    return plan
+
+
+def f32_coeffs(dt: float, coef: float, N: int) -> Tuple[float, float]:
+    """alpha = dt*coef*N*N and beta = 1 + 4*alpha evaluated left to right in binary32
+    (FluidSequential.c:179-180, :199-200)."""
+    f = np.float32
+    a = f(dt) * f(coef)
+    a = a * f(N)
+    a = a * f(N)
+    return float(a), float(f(1) + f(4) * a)
+
+
+class HaloSpec:
+    """`rows` ghost rows of `field` are to be refreshed from the neighbours' owned rows."""
+    __slots__ = ("field", "rows")
+
+    def __init__(self, field, rows: int):
+        self.field, self.rows = field, int(rows)
+
+
+class SlabLayout:
+    """Which rows a rank owns and where its ghost rows sit in a local field of
+    (own_rows + 2*halo, G) cells.  Pure index arithmetic (no device needed)."""
+
+    def __init__(self, G: int, rank: int, world: int, halo: int):
+        self.G, self.rank, self.world, self.halo = G, rank, world, halo
+        self.row_lo, self.row_hi = partition_rows(G, world)[rank]
+
+    @property
+    def own_rows(self) -> int:
+        return self.row_hi - self.row_lo
+
+    def local(self, global_row: int) -> int:
+        return global_row - (self.row_lo - self.halo)
+
+    def owned(self, field):
+        return field[self.halo: self.halo + self.own_rows]
+
+    # contiguous row blocks that travel
+    def send_up(self, field, h):      # my first h owned rows -> rank-1's lower ghost rows
+        return field[self.halo: self.halo + h]
+
+    def send_down(self, field, h):    # my last h owned rows -> rank+1's upper ghost rows
+        e = self.halo + self.own_rows
+        return field[e - h: e]
+
+    def recv_up(self, field, h):      # ghost rows above my slab <- rank-1's last h owned rows
+        return field[self.halo - h: self.halo]
+
+    def recv_down(self, field, h):    # ghost rows below my slab <- rank+1's first h owned rows
+        e = self.halo + self.own_rows
+        return field[e: e + h]
+
+
+class SlabSolver(SlabLayout):
+    """One rank's slab.  Fields are local tensors of (own_rows + 2*halo, G)."""
+
+    def __init__(self, N: int, rank: int, world: int, *, iters: int = 40, halo: int = 0, arithmetic: int = SF.STRICT,
+                 sweeps_per_launch: int = 8, device: Optional[int] = None, comm=None, allocate: bool = True):
+        SlabLayout.__init__(self, N + 2, rank, world, 0)
+        self.N = N
+        self.iters = iters
+        self.T = sweeps_per_launch
+        own = self.row_hi - self.row_lo
+        if halo <= 0:
+            # room for the advection reach: ~1/8 of a slab, at least 64 rows, never more than a slab
+            halo = max(64, min(own, 1024, (own // 8 + 7) // 8 * 8))
+        if world == 1:
+            halo = 0
+        if world > 1 and halo < self.T:
+            raise ValueError("halo must cover the temporal-blocking depth")
+        if world > 1 and own < 2 * self.T:
+            raise ValueError("slab thinner than two boundary strips")
+        self.halo = halo
+        self.ctx = SF.StableFluids(N, device, row_lo=self.row_lo, row_hi=self.row_hi, halo=halo,
+                                   arithmetic=arithmetic, sweeps_per_launch=sweeps_per_launch, use_graph=(world == 1))
+        self.comm = comm
+        self.names = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
+        if allocate:
+            self.f = {k: self.ctx.new_field() for k in self.names}
+            self.scratch = self.ctx.new_field()
+        self._max = None
+
+    @property
+    def launch_count(self) -> int:
+        return self.ctx.launch_count
+
+    # ---- the step as a generator of communication requests ---------------------------------------
+    # yields ("exchange", [HaloSpec...])            blocking neighbour exchange
+    #        ("exchange_begin", [HaloSpec...])      start it, keep computing
+    #        ("exchange_end", None)                 wait for the one in flight
+    #        ("allreduce_max", value) -> send(max)  scalar MAX over ranks
+    def _lin_solve(self, b, x, x0, alpha, beta):
+        c, T = self.ctx, self.T
+        plan = plan_launches(self.iters, T)
+        lo, hi = self.row_lo, self.row_hi
+        if self.world == 1:
+            c.diffuse(b, x, x0, alpha, beta, self.iters)
+            return
+        yield ("exchange", [HaloSpec(x, plan[0]), HaloSpec(x0, T)])
+        cur, nxt = x, self.scratch
+        for k, sweeps in enumerate(plan):
+            need_next = plan[k + 1] if k + 1 < len(plan) else 1   # after the solve: 1 row for the stencils that follow
+            strip = max(need_next, 1)
+            # boundary strips first (only the sides that have a neighbour), then the interior while they travel
+            top_hi = lo + strip if self.rank > 0 else lo
+            bot_lo = hi - strip if self.rank < self.world - 1 else hi
+            if top_hi > lo:
+                c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, lo, top_hi)
+            if bot_lo < hi:
+                c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, bot_lo, hi)
+            yield ("exchange_begin", [HaloSpec(nxt, strip)])
+            c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, top_hi, bot_lo)
+            yield ("exchange_end", None)
+            cur, nxt = nxt, cur
+        if cur is not x:
+            x.copy_(cur)
+
+    def _project(self, u, v, p, div):
+        c = self.ctx
+        if self.world == 1:
+            c.project(u, v, p, div, self.iters)
+            return
+        p.zero_()                                   # zero guess including the ghost rows
+        c.computeDivergenceAndPressure(u, v, p, div)  # u, v ghost rows (1) are valid on entry
+        yield from self._lin_solve(0, p, div, 1.0, 4.0)
+        c.lastProject(u, v, p, div)                 # p ghost row valid after the solve's last exchange
+
+    def _advect_reach(self, *vel):
+        """Ghost rows the gather can touch: |dt*N*v| rounded up, +2 for the bilinear footprint."""
+        m = 0.0
+        for t in vel:
+            m = max(m, self.ctx.reduce_max_abs(t))
+        m = yield ("allreduce_max", m)
+        return m
+
+    def step_gen(self, visc: float, diff: float, dt: float):
+        c, f = self.ctx, self.f
+        u, v, u0, v0, d, d0 = f["u"], f["v"], f["u_prev"], f["v_prev"], f["dens"], f["dens_prev"]
+        multi = self.world > 1
+        # ---- vel_step (FluidSequential.c:189-241) ----
+        c.add_source(u, u0, dt)
+        c.add_source(v, v0, dt)
+        alpha, beta = f32_coeffs(dt, visc, self.N)
+        yield from self._lin_solve(1, u0, u, alpha, beta)
+        yield from self._lin_solve(2, v0, v, alpha, beta)
+        yield from self._project(u0, v0, u, v)
+        if multi:
+            m = yield from self._advect_reach(u0, v0)
+            W = self._reach_rows(m, dt)
+            yield ("exchange", [HaloSpec(u0, W), HaloSpec(v0, W)])
+        c.advect(1, u, u0, u0, v0, dt)
+        c.advect(2, v, v0, u0, v0, dt)
+        if multi:
+            yield ("exchange", [HaloSpec(u, 1), HaloSpec(v, 1)])
+        yield from self._project(u, v, u0, v0)
+        # ---- dens_step (:176-186) ----
+        c.add_source(d, d0, dt)
+        alpha, beta = f32_coeffs(dt, diff, self.N)
+        yield from self._lin_solve(0, d0, d, alpha, beta)
+        if multi:
+            m = yield from self._advect_reach(u, v)
+            W = self._reach_rows(m, dt)
+            yield ("exchange", [HaloSpec(d0, W)])
+        c.advect(0, d, d0, u, v, dt)
+
+    def _reach_rows(self, max_vel: float, dt: float) -> int:
+        dt0 = float(np.float32(dt) * np.float32(self.N))
+        W = int(math.ceil(dt0 * max_vel)) + 2
+        if W > self.halo:
+            raise SF.StableFluidsError(
+                f"advection reaches {W} rows beyond the slab but only {self.halo} ghost rows are allocated; "
+                f"create the SlabSolver with halo >= {W}")
+        return max(W, 1)
+
+    # ---- drivers -----------------------------------------------------------------------------
+    def init_synthetic(self, seed: int):
+        self.ctx.init_synthetic(seed, *[self.f[k] for k in self.names])
+
+    def step(self, seed: Optional[int], visc: float, diff: float, dt: float):
+        """One loop-body iteration driven by this rank's communicator (NCCL in production)."""
+        if seed is not None:
+            self.ctx.init_sources(seed, self.f["dens_prev"], self.f["u_prev"], self.f["v_prev"])
+        if self.world == 1:
+            for _ in self.step_gen(visc, diff, dt):
+                raise AssertionError("single-slab steps do not communicate")
+            return
+        gen = self.step_gen(visc, diff, dt)
+        reply = None
+        while True:
+            try:
+                kind, arg = gen.send(reply)
+            except StopIteration:
+                break
+            reply = self.comm.serve(self, kind, arg)
+
+
+class TorchDistComm:
+    """Neighbour exchange over torch.distributed point-to-point ops (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.pending = None
+
+    def _post(self, s: SlabLayout, specs: Sequence[HaloSpec]):
+        dist = self.dist
+        ops = []
+        for sp in specs:
+            h = sp.rows
+            if h <= 0:
+                continue
+            if s.rank > 0:
+                ops.append(dist.P2POp(dist.isend, s.send_up(sp.field, h), s.rank - 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, s.recv_up(sp.field, h), s.rank - 1, self.group))
+            if s.rank < s.world - 1:
+                ops.append(dist.P2POp(dist.isend, s.send_down(sp.field, h), s.rank + 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, s.recv_down(sp.field, h), s.rank + 1, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def serve(self, s: SlabLayout, kind: str, arg):
+        if kind == "exchange":
+            for r in self._post(s, arg):
+                r.wait()
+        elif kind == "exchange_begin":
+            self.pending = self._post(s, arg)
+        elif kind == "exchange_end":
+            for r in self.pending or []:
+                r.wait()
+            self.pending = None
+        elif kind == "allreduce_max":
+            import torch
+            t = torch.tensor([arg], dtype=torch.float32, device=s.f["u"].device if hasattr(s, "f") else "cpu")
+            if self.dist.get_backend(self.group) == "nccl" and not t.is_cuda:
+                t = t.cuda()
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+            return float(t.item())
+        else:
+            raise ValueError(kind)
+        return None
+
+
+def exchange_lockstep(solvers: Sequence[SlabSolver], specs_per_rank: Sequence[Sequence[HaloSpec]]):
+    """All ranks exchange the same list of fields (by position); direct copies between slabs."""
+    for r, s in enumerate(solvers):
+        for i, sp in enumerate(specs_per_rank[r]):
+            h = sp.rows
+            if h <= 0:
+                continue
+            if r > 0:
+                nb = solvers[r - 1]
+                s.recv_up(sp.field, h).copy_(nb.send_down(specs_per_rank[r - 1][i].field, h))
+            if r < len(solvers) - 1:
+                nb = solvers[r + 1]
+                s.recv_down(sp.field, h).copy_(nb.send_up(specs_per_rank[r + 1][i].field, h))
+
+
+def run_lockstep(solvers: Sequence[SlabSolver], visc: float, diff: float, dt: float):
+    """Advance p emulated ranks (one process, one device) through one step in lock-step, serving
+    their communication requests with direct copies.  Test-only driver."""
+    gens = [s.step_gen(visc, diff, dt) for s in solvers]
+    replies = [None] * len(gens)
+    pending = None
+    while True:
+        reqs = []
+        for g, rep in zip(gens, replies):
+            try:
+                reqs.append(g.send(rep))
+            except StopIteration:
+                reqs.append(None)
+        if all(r is None for r in reqs):
+            return
+        assert all(r is not None for r in reqs), "ranks left the step at different points"
+        kinds = {r[0] for r in reqs}
+        assert len(kinds) == 1, f"ranks diverged: {kinds}"
+        kind = kinds.pop()
+        replies = [None] * len(gens)
+        if kind == "exchange":
+            exchange_lockstep(solvers, [r[1] for r in reqs])
+        elif kind == "exchange_begin":
+            # every rank has enqueued its boundary strips (same device, stream order): copy now
+            exchange_lockstep(solvers, [r[1] for r in reqs])
+            pending = True
+        elif kind == "exchange_end":
+            pending = None
+        elif kind == "allreduce_max":
+            m = max(r[1] for r in reqs)
+            replies = [m] * len(gens)
+        else:
+            raise ValueError(kind)
