@@ -53,7 +53,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -248,7 +248,7 @@ def run_ours(args):
         "gpu_launches": n_launch, "clocks": clocks,
     }
 
-    if world == 1:
+    if world == 1 and not args.skip_extras:
         # ---- roofline of the dominant kernel: jacobi_stream_kernel, timed per lin_solve with CUDA events on
         # the context's stream (graphs off for this instrumented pass; same kernels, same launch plan)
         sr = SF.StableFluids(N, use_graph=False)
@@ -320,11 +320,13 @@ except Exception:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=0, help="full grid width G = N+2 (default 8192 at 1 GPU, 32768 at >1)")
     ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--skip-extras", action="store_true",
+                    help="only the timed region (no roofline / e2e / cpu_baseline passes): for ncu launch lists")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
