@@ -189,8 +189,9 @@ def run_ours(args):
 
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        from fluidsimulationcuda_b200.slab import SlabSolver
-        sim = SlabSolver(N, rank, world, iters=K, arithmetic=SF.STRICT)
+        from fluidsimulationcuda_b200.slab import SlabSolver, TorchDistComm
+        sim = SlabSolver(N, rank, world, iters=K, arithmetic=SF.STRICT, comm=TorchDistComm())
+        sim.init_synthetic(1)
         step = lambda seed: sim.step(seed, VIS, DIFF, DT)
         sync = lambda: (torch.cuda.synchronize(), dist.barrier())
         launches = lambda: sim.launch_count

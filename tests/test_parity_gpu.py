@@ -244,3 +244,31 @@ def test_launch_counter_counts_kernels(SF):
     assert per_step == 5 * 6 + 8, per_step
     s.step(*f, VIS, DIFF, DT, 40); s.step(*f, VIS, DIFF, DT, 40)   # direct, then captured+replayed
     assert s.launch_count - n0 == 3 * per_step
+
+
+def test_c_example_with_reference_names(oracle, tmp_path):
+    """examples/fluid_main.c drives the library through stablefluids_compat.h (the reference's own
+    function names) from plain C; its density checksum must equal the oracle's."""
+    import shutil, subprocess
+    from conftest import ROOT
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "fluid_main")
+    lib = os.path.join(ROOT, "fluidsimulationcuda_b200")
+    subprocess.check_call([cc if not os.path.exists("/usr/bin/gcc") else "/usr/bin/gcc", "-O2", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "fluid_main.c"), "-L" + lib, "-lstablefluids_b200",
+                           "-Wl,-rpath," + lib, "-o", exe])
+    N, steps, K = 62, 3, 40
+    out = subprocess.run([exe, str(N), str(steps)], stdout=subprocess.PIPE, text=True, check=True).stdout
+    got = float(out.split("sum(dens)")[1])
+    # same schedule on the oracle: synthetic IC seed 1, sources re-seeded with 1+z before step z>0
+    w = oracle.init_synthetic(N, 1)
+    for z in range(steps):
+        if z > 0:
+            fresh = oracle.init_synthetic(N, 1 + z)
+            for k in ("dens_prev", "u_prev", "v_prev"):
+                w[k][...] = fresh[k]
+        oracle.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=0)
+    want = float(w["dens"].astype(np.float64).sum())
+    assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (got, want)
