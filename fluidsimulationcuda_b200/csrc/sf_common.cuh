@@ -30,8 +30,8 @@ enum ArithMode {
 //     q1 = RN(q0 - e*y)  -- Markstein's FMA division step.  q1 == RN(a/b) whenever no intermediate
 //     under/overflows, which the range guard ensures (|a| in [1e-30, 1e30], or a == +-0: writing
 //     the residual as e = b*q0 - a makes zeros come out with the right sign).
-//  slow path (numerators in the subnormal-result range or huge): the same step in binary64 and one
-//     rounding to binary32.  The binary64 quotient is exact when a/b is representable and within
+//  slow path (numerators in the subnormal-result range or huge; also used for whole ticks once a
+//     warp has met such a numerator): the same step in binary64 and one rounding to binary32.  The binary64 quotient is exact when a/b is representable and within
 //     2^-52 otherwise, while a binary32 quotient is never closer than 2^-49 (relative) to a
 //     rounding boundary, so the final rounding is the correct one.  Straight-line code: the decaying
 //     diffusion front of a density field (values of 1e-30 .. 1e-45) costs a few DP instructions per
@@ -59,18 +59,24 @@ __device__ __forceinline__ float div_const_fast(float a, const DivConst &d)
     const float e = __fmaf_rn(d.b, q0, -a);
     return __fmaf_rn(-e, d.y, q0);
 }
-__device__ __forceinline__ bool div_in_range(float a)
+// lower side of the guard in two integer instructions: 2*bits - 1 drops the sign bit and wraps
+// +-0 to 0xffffffff, so "zero or |a| >= LO" is one unsigned compare
+__device__ __forceinline__ bool div_low_ok(float a)
 {
-    const float m = fabsf(a);
-    return ((m >= SF_DIV_LO) || (a == 0.0f)) && (m <= SF_DIV_HI);
+    const unsigned t = 2u * __float_as_uint(a) - 1u;
+    return t >= 2u * 0x0DA24260u - 1u;   // 0x0DA24260 = bits of 1e-30f
 }
+__device__ __forceinline__ bool div_high_ok(float a) { return fabsf(a) <= SF_DIV_HI; }
+__device__ __forceinline__ bool div_in_range(float a) { return div_low_ok(a) && div_high_ok(a); }
+// binary64 step: exact for EVERY binary32 numerator (validated exhaustively like the fast path), no
+// range guard, straight-line.  Same residual form so +-0 keep their sign; +-inf passes through.
 __device__ __forceinline__ float div_const_slow(float a, const DivConst &d)
 {
-    if (!(fabsf(a) <= 3.4028234664e38f)) return __fmul_rn(a, d.y);   // +-inf, NaN
     const double A = (double)a;
     const double q0 = __dmul_rn(A, d.yd);
-    const double r = __fma_rn(-d.bd, q0, A);
-    return __double2float_rn(__fma_rn(r, d.yd, q0));
+    const double e = __fma_rn(d.bd, q0, -A);
+    const float q = __double2float_rn(__fma_rn(-e, d.yd, q0));
+    return (fabsf(a) <= 3.4028234664e38f) ? q : __fmul_rn(a, d.y);   // +-inf (and NaN) numerators
 }
 __device__ __forceinline__ float div_const(float a, const DivConst &d)
 {

@@ -24,6 +24,7 @@
 //
 // jacobi_generic_kernel<MODE> -- one sweep per launch, one thread per cell, any G (fallback for
 //   widths that are not a multiple of 4, e.g. the literal N=128 -> G=130).
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -37,10 +38,21 @@ namespace {
 constexpr int BAND_W = 128;   // columns per warp (32 lanes x float4)
 constexpr int HALO_X = 8;     // band halo columns on each side (>= max T, multiple of 4)
 constexpr int VALID_W = BAND_W - 2 * HALO_X;  // 112 output columns per band
-constexpr int WPC = 4;        // warps per CTA (adjacent bands, same row chunk)
-constexpr int RING_X = 8;     // x-row ring slots per warp (power of two, > PREFETCH)
-constexpr int RING_R = 16;    // rhs-row ring slots per warp (power of two, >= T + PREFETCH + 1)
-constexpr int PREFETCH = 5;   // rows in flight ahead of the row being consumed
+#ifndef SF_WPC
+#define SF_WPC 4
+#define SF_RING_X 8
+#define SF_RING_R 16
+#define SF_PREFETCH 5
+#endif
+constexpr int WPC = SF_WPC;            // warps per CTA (adjacent bands, same row chunk)
+constexpr int RING_X = SF_RING_X;      // x-row ring slots per warp (power of two, >= PREFETCH + 3)
+constexpr int RING_R = SF_RING_R;      // rhs-row ring slots per warp (power of two, >= T + PREFETCH + 3)
+constexpr int PREFETCH = SF_PREFETCH;  // rows in flight ahead of the row being consumed
+// CTAs per SM the register allocation is bounded for.  The branch-free strict tick keeps more values
+// in flight: at T >= 6 it needs ~150 registers, so it runs 3 CTAs (12 warps) per SM instead of 4 --
+// measured faster than spilling at 128 registers (1.78 vs 2.18 ms per 40-sweep solve at G=8192).
+template <int T, int MODE>
+constexpr int min_ctas() { return ((MODE == MODE_STRICT || MODE == MODE_IEEE) && T >= 6) ? 3 : 4; }
 
 struct StreamArgs {
     const float *xin, *rhs;
@@ -51,6 +63,7 @@ struct StreamArgs {
     int chunk_rows, nchunks, nbands;
     int zero_guess;
     float alpha, sx, sy;
+    float hi_in;         // level-0 magnitudes up to this keep every numerator of the launch <= SF_DIV_HI
     DivConst div;        // beta and its reciprocals
 };
 
@@ -69,9 +82,16 @@ __device__ __forceinline__ float4 scale4(float4 v, float s)
 }
 
 // Four adjacent cells of one row at one level.
-template <int MODE>
+// MODE_STRICT, GUARDED = true : the binary64 division step for every cell (general tick): exact for
+//                               all numerators, no range test at all.
+// MODE_STRICT, GUARDED = false: optimistic -- always the 3-instruction division, and only the LOW end
+//                               of the range is tested (2 integer instructions per cell) and AND-ed
+//                               into `ok`; no branch sits between the sweep levels.  The caller votes
+//                               once per tick and redoes the tick GUARDED if any lane failed (the high
+//                               end is proved per fetched row, see row_is_big).
+template <int MODE, bool GUARDED>
 __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rgt, const float4 &up, const float4 &dn,
-                                          const float4 &r, float alpha, const DivConst &d)
+                                          const float4 &r, float alpha, const DivConst &d, bool &ok)
 {
     float4 o;
     if (MODE == MODE_STRICT) {
@@ -79,16 +99,22 @@ __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rg
         const float a1 = jacobi_numerator<MODE>(mid.x, mid.z, up.y, dn.y, r.y, alpha);
         const float a2 = jacobi_numerator<MODE>(mid.y, mid.w, up.z, dn.z, r.z, alpha);
         const float a3 = jacobi_numerator<MODE>(mid.z, rgt, up.w, dn.w, r.w, alpha);
-        o.x = div_const_fast(a0, d);
-        o.y = div_const_fast(a1, d);
-        o.z = div_const_fast(a2, d);
-        o.w = div_const_fast(a3, d);
-        const bool ok0 = div_in_range(a0), ok1 = div_in_range(a1), ok2 = div_in_range(a2), ok3 = div_in_range(a3);
-        if (!(ok0 & ok1 & ok2 & ok3)) {   // subnormal-range or huge numerators: binary64 step, lane by lane
-            if (!ok0) o.x = div_const_slow(a0, d);
-            if (!ok1) o.y = div_const_slow(a1, d);
-            if (!ok2) o.z = div_const_slow(a2, d);
-            if (!ok3) o.w = div_const_slow(a3, d);
+        if (!GUARDED) {
+            o.x = div_const_fast(a0, d);
+            o.y = div_const_fast(a1, d);
+            o.z = div_const_fast(a2, d);
+            o.w = div_const_fast(a3, d);
+        }
+        if (GUARDED) {
+            // binary64 step for all four cells: exact for every numerator, no branches, and the four
+            // chains overlap (a lone warp in this mode runs about as fast as a warp on the fast tick
+            // because the conversion/FP64 pipes are otherwise idle)
+            o.x = div_const_slow(a0, d);
+            o.y = div_const_slow(a1, d);
+            o.z = div_const_slow(a2, d);
+            o.w = div_const_slow(a3, d);
+        } else {
+            ok = ok & div_low_ok(a0) & div_low_ok(a1) & div_low_ok(a2) & div_low_ok(a3);
         }
     } else {
         o.x = jacobi_cell<MODE>(lft, mid.y, up.x, dn.x, r.x, alpha, d);
@@ -106,9 +132,10 @@ __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rg
 // row is back in the register it started in and the hot loop contains no register moves.
 // WALLS adds the fused set_bnd handling.  Returns level T of row s-T in `out`.
 template <int T, int MODE, int PH, bool WALLS>
-__device__ __forceinline__ void pipeline_tick(const StreamArgs &A, int s, const float4 &row_in, float4 (&W)[T][3],
+__device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const float4 &row_in, float4 (&W)[T][3],
                                               const float4 *rring, bool ownsL, bool ownsR, float4 &out)
 {
+    bool ok = true;
     constexpr int UP = PH % 3, MID = (PH + 1) % 3, DN = (PH + 2) % 3;
     W[0][DN] = row_in;
 #pragma unroll
@@ -118,11 +145,12 @@ __device__ __forceinline__ void pipeline_tick(const StreamArgs &A, int s, const 
         const float4 r = rring[(a & (RING_R - 1)) * 32];
         const float lft = __shfl_up_sync(0xffffffffu, mid.w, 1);
         const float rgt = __shfl_down_sync(0xffffffffu, mid.x, 1);
-        float4 o = jacobi4<MODE>(lft, mid, rgt, up, dn, r, A.alpha, A.div);
+        float4 o = jacobi4<MODE, WALLS>(lft, mid, rgt, up, dn, r, A.alpha, A.div, ok);
+        // wall columns: x[row][0] = sx * x[row][1], x[row][N+1] = sx * x[row][N]  (two predicated
+        // multiplies; only the lanes holding columns 0 / N+1 of the two edge bands execute them)
+        if (ownsL) o.x = __fmul_rn(A.sx, o.y);
+        if (ownsR) o.w = __fmul_rn(A.sx, o.z);
         if (WALLS) {
-            // wall columns: x[row][0] = sx * x[row][1], x[row][N+1] = sx * x[row][N]
-            if (ownsL) o.x = __fmul_rn(A.sx, o.y);
-            if (ownsR) o.w = __fmul_rn(A.sx, o.z);
             if (t + 1 < T) {
                 // wall rows of level t+1 live in the NEXT level's window: its MID slot is row a-1
                 if (a == A.N + 1) o = scale4(W[t + 1][MID], A.sy);     // row N+1 = sy * row N
@@ -131,10 +159,11 @@ __device__ __forceinline__ void pipeline_tick(const StreamArgs &A, int s, const 
         }
         if (t + 1 < T) W[t + 1][DN] = o; else out = o;
     }
+    return ok;
 }
 
 template <int T, int MODE>
-__global__ void __launch_bounds__(WPC * 32, 4) jacobi_stream_kernel(const StreamArgs A)
+__global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
 {
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -150,7 +179,6 @@ __global__ void __launch_bounds__(WPC * 32, 4) jacobi_stream_kernel(const Stream
     const bool indom = (c >= 0) && (c + 4 <= A.G);
     const bool ownsL = (c == 0), ownsR = (c + 4 == A.G);
     const bool st_ok = indom && lane >= HALO_X / 4 && lane < 32 - HALO_X / 4;
-    const bool edge_band = (band == 0) || (band == A.nbands - 1);   // the bands holding columns 0 / N+1
     const int cc = indom ? c : 0;
     const int nbytes = indom ? 16 : 0;
 
@@ -180,6 +208,23 @@ __global__ void __launch_bounds__(WPC * 32, 4) jacobi_stream_kernel(const Stream
         if (!zero_guess && row <= load_hi) in = xring[(row & (RING_X - 1)) * 32];
         return in;
     };
+    auto xrow = [&](int row) -> float4 {    // level-0 row already landed
+        float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!zero_guess && row <= load_hi) in = xring[(row & (RING_X - 1)) * 32];
+        return in;
+    };
+    // MODE_STRICT only: the wall-free tick guards just the LOW end of the exact division's range per
+    // cell.  The high end follows from a maximum principle: |numerator| <= (1 + 4|alpha|) * max|input|,
+    // so rows whose magnitudes stay below A.hi_in can never produce a numerator above SF_DIV_HI.
+    // Every row is checked when it is fetched; one outlier switches the warp to the fully guarded
+    // tick for the rest of its chunk.
+    auto row_is_big = [&](int row) -> bool {
+        if (MODE != MODE_STRICT || row > load_hi) return false;
+        const float4 a = xrow(row), b = rring[(row & (RING_R - 1)) * 32];
+        const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                              fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        return !(m <= A.hi_in);   // NaN counts as big
+    };
 
     float4 W[T][3];
 #pragma unroll
@@ -208,31 +253,70 @@ __global__ void __launch_bounds__(WPC * 32, 4) jacobi_stream_kernel(const Stream
             if (st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(A.N + 1 - A.row_base) * pitch) = w;
         }
     };
-    // The wall logic is needed when some level produces row 1 or row N+1 (s-t-1 in {1, N+1}, t < T),
-    // when the last level emits row 1 or row N (s = T+1, s = N+T), or in an edge band; i.e. for
-    // s <= T+1, for s > N, and for every tick of the two edge bands.  Everything else runs the
-    // wall-free tick in groups of three (one full rotation of the windows).
+    // The row-wall logic is needed when some level produces row 1 or row N+1 (s-t-1 in {1, N+1}, t < T)
+    // or when the last level emits row 1 or row N (s = T+1, s = N+T): for s <= T+1 and for s > N.
+    // Everything else runs the wall-free tick in groups of three (one full rotation of the windows).
     const int fast_lo = T + 2;
-    const int fast_hi = edge_band ? -1 : min(s_hi, A.N);
+    const int fast_hi = min(s_hi, A.N);
+    bool slow = false;   // sticky: an out-of-range numerator or an outlier row was seen in this chunk
+
+    // general tick at phase 0 followed by the register rotation that restores phase 0
+    auto general_tick = [&](int s_, const float4 &row_in) {
+        float4 o;
+        pipeline_tick<T, MODE, 0, true>(A, s_, row_in, W, rring, ownsL, ownsR, o);
+        emit_walls(s_ - T, o);
+#pragma unroll
+        for (int t = 0; t < T; ++t) { W[t][0] = W[t][1]; W[t][1] = W[t][2]; }
+    };
 
     int s = s_lo;
     while (s <= s_hi) {
-        float4 o;
-        if (s >= fast_lo && s + 2 <= fast_hi) {
-            pipeline_tick<T, MODE, 0, false>(A, s, fetch(s), W, rring, false, false, o);
-            emit_plain(s - T, o);
-            pipeline_tick<T, MODE, 1, false>(A, s + 1, fetch(s + 1), W, rring, false, false, o);
-            emit_plain(s + 1 - T, o);
-            pipeline_tick<T, MODE, 2, false>(A, s + 2, fetch(s + 2), W, rring, false, false, o);
-            emit_plain(s + 2 - T, o);
-            s += 3;
+        if (!slow && s >= fast_lo && s + 2 <= fast_hi) {
+            issue(s + PREFETCH); issue(s + PREFETCH + 1); issue(s + PREFETCH + 2);
+            cp_async_wait<PREFETCH>();       // rows <= s+2 have landed
+            if (MODE == MODE_STRICT) slow = __any_sync(0xffffffffu, row_is_big(s) | row_is_big(s + 1) | row_is_big(s + 2));
+            if (!slow) {
+                float4 o;
+                bool ok = pipeline_tick<T, MODE, 0, false>(A, s, xrow(s), W, rring, ownsL, ownsR, o);
+                if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
+                    slow = true;                       // windows are still at phase 0: redo guarded
+                    general_tick(s, xrow(s)); s += 1;
+                    general_tick(s, xrow(s)); s += 1;  // the two other rows of this group are in flight already
+                    general_tick(s, xrow(s)); s += 1;
+                    continue;
+                }
+                emit_plain(s - T, o);
+                ok = pipeline_tick<T, MODE, 1, false>(A, s + 1, xrow(s + 1), W, rring, ownsL, ownsR, o);
+                if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
+                    slow = true;                       // phase 1 -> phase 0: up = slot 1, mid = slot 2
+#pragma unroll
+                    for (int t = 0; t < T; ++t) { W[t][0] = W[t][1]; W[t][1] = W[t][2]; }
+                    general_tick(s + 1, xrow(s + 1));
+                    general_tick(s + 2, xrow(s + 2));
+                    s += 3;
+                    continue;
+                }
+                emit_plain(s + 1 - T, o);
+                ok = pipeline_tick<T, MODE, 2, false>(A, s + 2, xrow(s + 2), W, rring, ownsL, ownsR, o);
+                if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
+                    slow = true;                       // phase 2 -> phase 0: up = slot 2, mid = slot 0
+#pragma unroll
+                    for (int t = 0; t < T; ++t) { const float4 m = W[t][0]; W[t][0] = W[t][2]; W[t][1] = m; }
+                    general_tick(s + 2, xrow(s + 2));
+                    s += 3;
+                    continue;
+                }
+                emit_plain(s + 2 - T, o);
+                s += 3;
+                continue;
+            }
+            // outlier row: the three rows of this group are already in flight; run them guarded
+            general_tick(s, xrow(s)); s += 1;
+            general_tick(s, xrow(s)); s += 1;
+            general_tick(s, xrow(s)); s += 1;
             continue;
         }
-        // general tick at phase 0, then rotate the windows back to phase 0 by moving registers
-        pipeline_tick<T, MODE, 0, true>(A, s, fetch(s), W, rring, ownsL, ownsR, o);
-        emit_walls(s - T, o);
-#pragma unroll
-        for (int t = 0; t < T; ++t) { W[t][0] = W[t][1]; W[t][1] = W[t][2]; }
+        general_tick(s, fetch(s));
         ++s;
     }
     cp_async_wait<0>();
@@ -272,9 +356,9 @@ __global__ void validate_division_kernel(DivConst d, unsigned long long *mismatc
     for (unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u < (1ull << 32); u += stride) {
         const float a = __uint_as_float((unsigned)u);
         if (a != a) continue;   // NaN numerators: payload propagation is not part of the contract
-        const float want = __fdiv_rn(a, d.b);
-        const float got = div_const(a, d);
-        bad += (__float_as_uint(want) != __float_as_uint(got));
+        const unsigned want = __float_as_uint(__fdiv_rn(a, d.b));
+        bad += (want != __float_as_uint(div_const(a, d)));        // guarded fast path + slow path outside the range
+        bad += (want != __float_as_uint(div_const_slow(a, d)));   // the binary64 step on its own, every numerator
     }
     if (bad) atomicAdd(mismatches, bad);
 }
@@ -349,6 +433,14 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     A.nbands = (g.G + VALID_W - 1) / VALID_W;
     A.zero_guess = L.zero_guess;
     A.alpha = L.alpha; A.div = make_div_const(L.beta);
+    {   // see row_is_big: bound on level-0 magnitudes that keeps all numerators of T sweeps in range
+        const double F = 1.0 + 4.0 * fabs((double)L.alpha);
+        double g = F / fabs((double)L.beta) * 1.000001;
+        if (g < 1.0) g = 1.0;
+        double hi = (double)SF_DIV_HI / (F * 1.01);
+        for (int t = 0; t < L.sweeps; ++t) hi /= g;
+        A.hi_in = (float)hi;
+    }
     A.sx = (L.b == 1) ? -1.0f : 1.0f;
     A.sy = (L.b == 2) ? -1.0f : 1.0f;
     const int rows = A.a_hi - A.a_lo;
@@ -358,7 +450,8 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
         // One work item (band x chunk) per resident warp: 16 warps per SM (4 CTAs of 4 warps).  All
         // items cost about the same, so a single full wave has no tail; chunks are kept >= 16 T rows so
         // that the 2T redundant halo rows stay a small share.
-        const int slots = sm_count * 4 * WPC;
+        const bool heavy = (L.mode == MODE_STRICT || L.mode == MODE_IEEE) && L.sweeps >= 6;   // min_ctas<T, MODE>()
+        const int slots = sm_count * (heavy ? 3 : 4) * WPC;
         int want_chunks = slots / A.nbands;
         if (want_chunks < 1) want_chunks = 1;
         chunk = (rows + want_chunks - 1) / want_chunks;

@@ -5,6 +5,8 @@
 // :143-158 (computeDivergenceAndPressure), :161-173 (lastProject), :244-271 (initial condition).
 // All arithmetic uses __f*_rn intrinsics so nvcc cannot contract mul+add into FMA: results are
 // bit-identical to the reference's sequential build.
+#include <initializer_list>
+
 #include "sf_common.cuh"
 
 namespace sf {
@@ -258,6 +260,163 @@ __global__ void residual_kernel(const float *__restrict__ x, const float *__rest
     }
 }
 
+// ================================================================================================
+// Row-vectorised variants for G % 4 == 0 (every BASELINE width): one thread owns four adjacent
+// columns [c, c+4) of one row, c % 4 == 0, so every access is an aligned float4 and the wall
+// columns 0 / N+1 sit in the same thread as interior columns 1 / N (set_bnd on columns is a
+// register operation).  Horizontal neighbours c-1 / c+4 come from the adjacent lanes by shuffle;
+// only the first / last lane of a warp loads them as scalars.  A warp covers 128 consecutive
+// columns of a row (512 contiguous bytes per access).
+struct Row4 {
+    float4 v;
+    float l, r;   // values at columns c-1 and c+4 (0 outside the grid)
+};
+__device__ __forceinline__ Row4 load_row4(const float *__restrict__ row, int c, int G, int lane)
+{
+    Row4 o;
+    o.v = __ldg(reinterpret_cast<const float4 *>(row + c));
+    o.l = __shfl_up_sync(0xffffffffu, o.v.w, 1);
+    o.r = __shfl_down_sync(0xffffffffu, o.v.x, 1);
+    if (lane == 0) o.l = (c > 0) ? __ldg(row + c - 1) : 0.0f;
+    if (lane == 31) o.r = (c + 4 < G) ? __ldg(row + c + 4) : 0.0f;
+    return o;
+}
+// store four interior-row values plus the wall cells they determine (set_bnd(b) fused)
+__device__ __forceinline__ void store_row4_walls(float *__restrict__ x, const Geom &g, int row, int c, float4 o, float sx, float sy)
+{
+    const size_t G = (size_t)g.G;
+    const bool ownsL = (c == 0), ownsR = (c + 4 == g.G);
+    if (ownsL) o.x = __fmul_rn(sx, o.y);
+    if (ownsR) o.w = __fmul_rn(sx, o.z);
+    float *dst = x + (size_t)(row - g.row_base) * G + c;
+    *reinterpret_cast<float4 *>(dst) = o;
+    const bool top = (row == 1) && (g.own_lo == 0), bot = (row == g.N) && (g.own_hi == g.G);
+    if (top | bot) {
+        float4 w = make_float4(__fmul_rn(sy, o.x), __fmul_rn(sy, o.y), __fmul_rn(sy, o.z), __fmul_rn(sy, o.w));
+        if (ownsL) w.x = __fmul_rn(0.5f, __fadd_rn(w.y, o.x));
+        if (ownsR) w.w = __fmul_rn(0.5f, __fadd_rn(w.z, o.w));
+        if (top) *reinterpret_cast<float4 *>(dst - G) = w;
+        if (bot) *reinterpret_cast<float4 *>(dst + G) = w;
+    }
+}
+#define SF_ROW4_PROLOGUE                                                      \
+    int lo, hi;                                                               \
+    interior_rows(g, lo, hi);                                                 \
+    const int lane = threadIdx.x & 31;                                        \
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;                \
+    const int row = blockIdx.y * blockDim.y + threadIdx.y + lo;               \
+    if (row >= hi) return;            /* uniform per warp: a warp is one row */\
+    const bool active = c < g.G;                                              \
+    const int cs = active ? c : g.G - 4;   /* idle lanes mirror the last float4: loads stay legal */ \
+    const size_t G = (size_t)g.G;                                             \
+    const size_t rowoff = (size_t)(row - g.row_base) * G;
+
+__global__ void __launch_bounds__(256) divergence4_kernel(const float *__restrict__ u, const float *__restrict__ v,
+                                                          float *__restrict__ p, float *__restrict__ div, Geom g,
+                                                          float scale, int write_p)
+{
+    SF_ROW4_PROLOGUE
+    const Row4 U = load_row4(u + rowoff, cs, g.G, lane);
+    const float4 vd = __ldg(reinterpret_cast<const float4 *>(v + rowoff + G + cs));
+    const float4 vu = __ldg(reinterpret_cast<const float4 *>(v + rowoff - G + cs));
+    if (!active) return;
+    // FluidSequential.c:151-152: (-0.5f*h) * (((u_r - u_l) + v_d) - v_u)
+    float4 o;
+    o.x = __fmul_rn(scale, __fsub_rn(__fadd_rn(__fsub_rn(U.v.y, U.l), vd.x), vu.x));
+    o.y = __fmul_rn(scale, __fsub_rn(__fadd_rn(__fsub_rn(U.v.z, U.v.x), vd.y), vu.y));
+    o.z = __fmul_rn(scale, __fsub_rn(__fadd_rn(__fsub_rn(U.v.w, U.v.y), vd.z), vu.z));
+    o.w = __fmul_rn(scale, __fsub_rn(__fadd_rn(__fsub_rn(U.r, U.v.z), vd.w), vu.w));
+    store_row4_walls(div, g, row, c, o, 1.0f, 1.0f);
+    if (write_p) store_row4_walls(p, g, row, c, make_float4(0.f, 0.f, 0.f, 0.f), 1.0f, 1.0f);
+}
+
+__global__ void __launch_bounds__(256) last_project4_kernel(float *__restrict__ u, float *__restrict__ v,
+                                                            const float *__restrict__ p, Geom g, float h)
+{
+    SF_ROW4_PROLOGUE
+    const Row4 P = load_row4(p + rowoff, cs, g.G, lane);
+    const float4 pd = __ldg(reinterpret_cast<const float4 *>(p + rowoff + G + cs));
+    const float4 pu = __ldg(reinterpret_cast<const float4 *>(p + rowoff - G + cs));
+    if (!active) return;
+    float4 uu = *reinterpret_cast<const float4 *>(u + rowoff + c);
+    float4 vv = *reinterpret_cast<const float4 *>(v + rowoff + c);
+    // FluidSequential.c:167-168: u -= (0.5f*(p_r - p_l)) / h ; v -= (0.5f*(p_d - p_u)) / h
+    uu.x = __fsub_rn(uu.x, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(P.v.y, P.l)), h));
+    uu.y = __fsub_rn(uu.y, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(P.v.z, P.v.x)), h));
+    uu.z = __fsub_rn(uu.z, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(P.v.w, P.v.y)), h));
+    uu.w = __fsub_rn(uu.w, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(P.r, P.v.z)), h));
+    vv.x = __fsub_rn(vv.x, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(pd.x, pu.x)), h));
+    vv.y = __fsub_rn(vv.y, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(pd.y, pu.y)), h));
+    vv.z = __fsub_rn(vv.z, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(pd.z, pu.z)), h));
+    vv.w = __fsub_rn(vv.w, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(pd.w, pu.w)), h));
+    store_row4_walls(u, g, row, c, uu, -1.0f, 1.0f);   // set_bnd(1, u)
+    store_row4_walls(v, g, row, c, vv, 1.0f, -1.0f);   // set_bnd(2, v)
+}
+
+// one back-trace + bilinear gather (FluidSequential.c:114-137); NF source fields share the trace
+template <int NF>
+__device__ __forceinline__ void advect_cell(const float *__restrict__ srcA, const float *__restrict__ srcB, const Geom &g,
+                                            int row, int col, float uu, float vv, float dt0, float hiC, float &oA, float &oB)
+{
+    float px = __fsub_rn((float)col, __fmul_rn(dt0, uu));
+    float py = __fsub_rn((float)row, __fmul_rn(dt0, vv));
+    if (px < 0.5f) px = 0.5f;
+    if (px > hiC) px = hiC;
+    if (py < 0.5f) py = 0.5f;
+    if (py > hiC) py = hiC;
+    const int c0 = (int)px, r0 = (int)py;
+    const float wx1 = __fsub_rn(px, (float)c0), wx0 = __fsub_rn(1.0f, wx1);
+    const float wy1 = __fsub_rn(py, (float)r0), wy0 = __fsub_rn(1.0f, wy1);
+    const size_t G = (size_t)g.G;
+    const size_t j = (size_t)(r0 - g.row_base) * G + c0;
+    {
+        const float a00 = __ldg(srcA + j), a10 = __ldg(srcA + j + G), a01 = __ldg(srcA + j + 1), a11 = __ldg(srcA + j + G + 1);
+        oA = __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
+                       __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
+    }
+    if (NF == 2) {
+        const float a00 = __ldg(srcB + j), a10 = __ldg(srcB + j + G), a01 = __ldg(srcB + j + 1), a11 = __ldg(srcB + j + G + 1);
+        oB = __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
+                       __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
+    }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256) advect4_kernel(float *__restrict__ dA, float *__restrict__ dB,
+                                                      const float *__restrict__ srcA, const float *__restrict__ srcB,
+                                                      const float *__restrict__ u, const float *__restrict__ v, Geom g,
+                                                      float dt0, int bA)
+{
+    SF_ROW4_PROLOGUE
+    (void)lane; (void)cs;
+    if (!active) return;
+    const float4 uu = __ldg(reinterpret_cast<const float4 *>(u + rowoff + c));
+    const float4 vv = __ldg(reinterpret_cast<const float4 *>(v + rowoff + c));
+    const float hiC = (float)g.N + 0.5f;
+    float4 oA = make_float4(0.f, 0.f, 0.f, 0.f), oB = oA;
+    // columns 0 and N+1 are wall cells: their lanes are overwritten by store_row4_walls, but the
+    // trace still has to stay inside the array, which the clamp to [0.5, N+0.5] guarantees
+    advect_cell<NF>(srcA, srcB, g, row, c + 0, uu.x, vv.x, dt0, hiC, oA.x, oB.x);
+    advect_cell<NF>(srcA, srcB, g, row, c + 1, uu.y, vv.y, dt0, hiC, oA.y, oB.y);
+    advect_cell<NF>(srcA, srcB, g, row, c + 2, uu.z, vv.z, dt0, hiC, oA.z, oB.z);
+    advect_cell<NF>(srcA, srcB, g, row, c + 3, uu.w, vv.w, dt0, hiC, oA.w, oB.w);
+    store_row4_walls(dA, g, row, c, oA, bA == 1 ? -1.0f : 1.0f, bA == 2 ? -1.0f : 1.0f);
+    if (NF == 2) store_row4_walls(dB, g, row, c, oB, 1.0f, -1.0f);   // b = 2
+}
+
+inline bool row4_ok(const Geom &g, std::initializer_list<const void *> ptrs)
+{
+    if (g.G % 4 != 0) return false;
+    for (const void *p : ptrs)
+        if ((uintptr_t)p % 16 != 0) return false;
+    return true;
+}
+inline dim3 row4_grid(const Geom &g, dim3 block, int rows)
+{
+    const int per_block = block.x * 4;
+    return dim3((g.G + per_block - 1) / per_block, (rows + block.y - 1) / block.y);
+}
+
 inline dim3 cell_grid(const Geom &g, dim3 block, int rows) { return dim3((g.N + block.x - 1) / block.x, (rows + block.y - 1) / block.y); }
 inline int interior_row_count(const Geom &g)
 {
@@ -298,6 +457,11 @@ cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const
     if (rows == 0) return cudaSuccess;
     const dim3 block(64, 4);
     const float dt0 = dt * (float)g.N;   // FluidSequential.c:111, rounded once in binary32
+    if (row4_ok(g, {d, d0, u, v})) {
+        const dim3 b4(32, 8);
+        advect4_kernel<1><<<row4_grid(g, b4, rows), b4, 0, st>>>(d, nullptr, d0, nullptr, u, v, g, dt0, b);
+        return cudaGetLastError();
+    }
     advect_kernel<1><<<cell_grid(g, block, rows), block, 0, st>>>(d, nullptr, d0, nullptr, u, v, g, dt0, b);
     return cudaGetLastError();
 }
@@ -308,6 +472,11 @@ cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u
     if (rows == 0) return cudaSuccess;
     const dim3 block(64, 4);
     const float dt0 = dt * (float)g.N;
+    if (row4_ok(g, {du, dv, u0, v0})) {
+        const dim3 b4(32, 8);
+        advect4_kernel<2><<<row4_grid(g, b4, rows), b4, 0, st>>>(du, dv, u0, v0, u0, v0, g, dt0, 1);
+        return cudaGetLastError();
+    }
     advect_kernel<2><<<cell_grid(g, block, rows), block, 0, st>>>(du, dv, u0, v0, u0, v0, g, dt0, 1);
     return cudaGetLastError();
 }
@@ -319,6 +488,11 @@ cudaError_t launch_divergence(const Geom &g, const float *u, const float *v, flo
     const dim3 block(64, 4);
     const float h = 1.0f / (float)g.N;
     const float scale = -0.5f * h;
+    if (row4_ok(g, {u, v, p, div})) {
+        const dim3 b4(32, 8);
+        divergence4_kernel<<<row4_grid(g, b4, rows), b4, 0, st>>>(u, v, p, div, g, scale, write_p);
+        return cudaGetLastError();
+    }
     divergence_kernel<<<cell_grid(g, block, rows), block, 0, st>>>(u, v, p, div, g, scale, write_p);
     return cudaGetLastError();
 }
@@ -329,6 +503,11 @@ cudaError_t launch_last_project(const Geom &g, float *u, float *v, const float *
     if (rows == 0) return cudaSuccess;
     const dim3 block(64, 4);
     const float h = 1.0f / (float)g.N;
+    if (row4_ok(g, {u, v, p})) {
+        const dim3 b4(32, 8);
+        last_project4_kernel<<<row4_grid(g, b4, rows), b4, 0, st>>>(u, v, p, g, h);
+        return cudaGetLastError();
+    }
     last_project_kernel<<<cell_grid(g, block, rows), block, 0, st>>>(u, v, p, g, h);
     return cudaGetLastError();
 }

@@ -20,7 +20,7 @@ import os
 from typing import Optional
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libstablefluids_b200.so")
+LIB_PATH = os.environ.get("SF_LIBRARY") or os.path.join(PKG, "libstablefluids_b200.so")   # SF_LIBRARY: experimental builds
 
 SF_OPT_ARITHMETIC = 1
 SF_OPT_SWEEPS_PER_LAUNCH = 2

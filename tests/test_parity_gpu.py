@@ -113,6 +113,21 @@ def test_diffuse_subnormal_and_zero_fields(SF, oracle):
     assert_same(host(dx), want, "subnormal diffuse")
 
 
+def test_diffuse_huge_values_take_the_guarded_path(SF, oracle):
+    """Magnitudes beyond the fast division's validated range (|a| > 1e30) must still be exact: the
+    streaming kernel detects them when a row is fetched and switches to the fully guarded tick."""
+    N = 254; G = N + 2
+    rng = np.random.default_rng(9)
+    s = SF.StableFluids(N)
+    for spot in ((100, 100), (3, 250), (200, 7)):
+        x, x0 = rnd(rng, G), rnd(rng, G)
+        x[spot] = 3.0e31; x0[spot[1], spot[0]] = -2.5e32; x[spot[0] + 20, spot[1] - 2] = 1.0e33
+        want = x.copy(); oracle.diffuse(N, 1, want, x0, 2683.2, 10733.8, 14)
+        dx = dev(x); s.diffuse(1, dx, dev(x0), 2683.2, 10733.8, 14)
+        assert np.isfinite(want).all()
+        assert_same(host(dx), want, f"huge values at {spot}")
+
+
 # ---- steps ----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,K", [(30, 4), (62, 20), (126, 40), (254, 20), (130, 6)])
 def test_vel_and_dens_step(SF, oracle, N, K):
