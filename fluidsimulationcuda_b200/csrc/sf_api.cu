@@ -420,6 +420,19 @@ int sf_synchronize(sf_context *c)
     return SF_OK;
 }
 
+int sf_set_stream(sf_context *c, void *cuda_stream)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, !c->capturing, "set_stream during capture");
+    DeviceGuard guard(c->device);
+    for (auto &e : c->graphs) if (e.exec) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
+    c->graphs.clear();
+    if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = (cudaStream_t)cuda_stream;
+    c->work = c->stream;
+    return SF_OK;
+}
+
 int sf_launch_count(const sf_context *c, unsigned long long *count)
 {
     if (!c || !count) return SF_ERR_INVALID;
@@ -663,10 +676,20 @@ int sf_reduce_max_abs(sf_context *c, const float *x, float *host_out)
     DeviceGuard guard(c->device);
     int rc = ensure_scratch(c);
     if (rc) return rc;
-    SF_CUDA(c, launch_max_abs(c->g, x, c->red_f, c->stream));
+    SF_CUDA(c, launch_max_abs(c->g, x, c->red_f, true, c->stream));
     ++c->launches;
     SF_CUDA(c, cudaMemcpyAsync(host_out, c->red_f, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+int sf_reduce_max_abs_async(sf_context *c, const float *x, float *dev_out)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, x && dev_out, "reduce_max_abs_async: null argument");
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, launch_max_abs(c->g, x, dev_out, false, c->work));
+    ++c->launches;
     return SF_OK;
 }
 

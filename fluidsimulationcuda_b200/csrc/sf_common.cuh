@@ -152,7 +152,7 @@ cudaError_t launch_divergence(const Geom &g, const float *u, const float *v, flo
 cudaError_t launch_last_project(const Geom &g, float *u, float *v, const float *p, cudaStream_t st);
 cudaError_t launch_init(const Geom &g, uint64_t seed, float *dens, float *dens_prev, float *u, float *u_prev, float *v,
                         float *v_prev, cudaStream_t st);
-cudaError_t launch_max_abs(const Geom &g, const float *x, float *dev_out, cudaStream_t st);
+cudaError_t launch_max_abs(const Geom &g, const float *x, float *dev_out, bool zero_first, cudaStream_t st);
 cudaError_t launch_residual(const Geom &g, const float *x, const float *x0, float alpha, float beta, double *dev_out,
                             cudaStream_t st);
 

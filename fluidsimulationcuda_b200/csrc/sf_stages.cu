@@ -521,10 +521,12 @@ cudaError_t launch_init(const Geom &g, uint64_t seed, float *dens, float *dens_p
     return cudaGetLastError();
 }
 
-cudaError_t launch_max_abs(const Geom &g, const float *x, float *dev_out, cudaStream_t st)
+cudaError_t launch_max_abs(const Geom &g, const float *x, float *dev_out, bool zero_first, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(dev_out, 0, sizeof(float), st);
-    if (e != cudaSuccess) return e;
+    if (zero_first) {
+        cudaError_t e = cudaMemsetAsync(dev_out, 0, sizeof(float), st);
+        if (e != cudaSuccess) return e;
+    }
     const size_t first = (size_t)(g.own_lo - g.row_base) * g.G, count = (size_t)(g.own_hi - g.own_lo) * g.G;
     size_t blocks = (count + 1023) / 1024;
     if (blocks > 148 * 8) blocks = 148 * 8;

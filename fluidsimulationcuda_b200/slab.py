@@ -106,7 +106,8 @@ class SlabSolver(SlabLayout):
     """One rank's slab.  Fields are local tensors of (own_rows + 2*halo, G)."""
 
     def __init__(self, N: int, rank: int, world: int, *, iters: int = 40, halo: int = 0, arithmetic: int = SF.STRICT,
-                 sweeps_per_launch: int = 8, device: Optional[int] = None, comm=None, allocate: bool = True):
+                 sweeps_per_launch: int = 8, device: Optional[int] = None, comm=None, allocate: bool = True,
+                 overlap: bool = True, deferred_reach: bool = True):
         SlabLayout.__init__(self, N + 2, rank, world, 0)
         self.N = N
         self.iters = iters
@@ -129,11 +130,27 @@ class SlabSolver(SlabLayout):
         if allocate:
             self.f = {k: self.ctx.new_field() for k in self.names}
             self.scratch = self.ctx.new_field()
-        self._max = None
+        # Boundary strips run on a high-priority side stream (through a second context bound to
+        # it) so that they overlap the interior launch; `overlap=False` keeps everything on one
+        # stream (lock-step emulation of several ranks in one process).
+        self.overlap = bool(overlap) and world > 1
+        self.side = self.ctx_hi = None
+        if self.overlap:
+            torch = self.ctx.torch
+            self.main = torch.cuda.current_stream(self.ctx.device)
+            self.side = torch.cuda.Stream(device=self.ctx.device, priority=-1)
+            with torch.cuda.stream(self.side):
+                self.ctx_hi = SF.StableFluids(N, device, row_lo=self.row_lo, row_hi=self.row_hi, halo=halo,
+                                              arithmetic=arithmetic, sweeps_per_launch=sweeps_per_launch, use_graph=False)
+        # Advection reach: checked one step late so that no host synchronisation sits inside a step
+        # (deferred=True); the exchange then always carries the full ghost depth.
+        self.deferred_reach = bool(deferred_reach) and world > 1
+        self._pending_reach = []     # [(device scalar max|vel| over all ranks, dt)] of the current step
+        self._older_reach = []       # the same, per earlier step (oldest first)
 
     @property
     def launch_count(self) -> int:
-        return self.ctx.launch_count
+        return self.ctx.launch_count + (self.ctx_hi.launch_count if self.ctx_hi is not None else 0)
 
     # ---- the step as a generator of communication requests ---------------------------------------
     # yields ("exchange", [HaloSpec...])            blocking neighbour exchange
@@ -147,21 +164,38 @@ class SlabSolver(SlabLayout):
         if self.world == 1:
             c.diffuse(b, x, x0, alpha, beta, self.iters)
             return
-        yield ("exchange", [HaloSpec(x, plan[0]), HaloSpec(x0, T)])
+        yield ("exchange", [HaloSpec(x, plan[0]), HaloSpec(x0, T)], None)
         cur, nxt = x, self.scratch
+        torch = c.torch
         for k, sweeps in enumerate(plan):
             need_next = plan[k + 1] if k + 1 < len(plan) else 1   # after the solve: 1 row for the stencils that follow
             strip = max(need_next, 1)
-            # boundary strips first (only the sides that have a neighbour), then the interior while they travel
+            # boundary strips (only the sides that have a neighbour) and their exchange, while the interior runs
             top_hi = lo + strip if self.rank > 0 else lo
             bot_lo = hi - strip if self.rank < self.world - 1 else hi
-            if top_hi > lo:
-                c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, lo, top_hi)
-            if bot_lo < hi:
-                c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, bot_lo, hi)
-            yield ("exchange_begin", [HaloSpec(nxt, strip)])
-            c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, top_hi, bot_lo)
-            yield ("exchange_end", None)
+            if self.overlap:
+                ev = torch.cuda.Event()
+                ev.record(self.main)                 # everything this launch reads is complete on main
+                self.side.wait_event(ev)
+                with torch.cuda.stream(self.side):
+                    if top_hi > lo:
+                        self.ctx_hi.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, lo, top_hi)
+                    if bot_lo < hi:
+                        self.ctx_hi.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, bot_lo, hi)
+                yield ("exchange_begin", [HaloSpec(nxt, strip)], self.side)
+                c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, top_hi, bot_lo)   # main stream, concurrently
+                yield ("exchange_end", None, self.side)
+                ev2 = torch.cuda.Event()
+                ev2.record(self.side)                # strips written and ghost rows received
+                self.main.wait_event(ev2)
+            else:
+                if top_hi > lo:
+                    c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, lo, top_hi)
+                if bot_lo < hi:
+                    c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, bot_lo, hi)
+                yield ("exchange_begin", [HaloSpec(nxt, strip)], None)
+                c.jacobi_launch(b, nxt, cur, x0, alpha, beta, sweeps, top_hi, bot_lo)
+                yield ("exchange_end", None, None)
             cur, nxt = nxt, cur
         if cur is not x:
             x.copy_(cur)
@@ -176,13 +210,31 @@ class SlabSolver(SlabLayout):
         yield from self._lin_solve(0, p, div, 1.0, 4.0)
         c.lastProject(u, v, p, div)                 # p ghost row valid after the solve's last exchange
 
-    def _advect_reach(self, *vel):
-        """Ghost rows the gather can touch: |dt*N*v| rounded up, +2 for the bilinear footprint."""
+    def _advect_reach(self, dt, *vel):
+        """Ghost rows the gather can touch: |dt*N*v| rounded up, +2 for the bilinear footprint.
+        deferred: exchange the whole ghost depth now, verify the reach one step later (no host
+        synchronisation inside the step); otherwise a scalar MAX all-reduce read back on the host."""
+        if self.deferred_reach:
+            m = self.ctx.torch.zeros(1, dtype=self.ctx.torch.float32, device=vel[0].device)
+            for t in vel:
+                self.ctx.reduce_max_abs_async(t, m)
+            yield ("allreduce_max_device", m, None)
+            self._pending_reach.append((m, dt))
+            return self.halo
         m = 0.0
         for t in vel:
             m = max(m, self.ctx.reduce_max_abs(t))
-        m = yield ("allreduce_max", m)
-        return m
+        m = yield ("allreduce_max", m, None)
+        return self._reach_rows(m, dt)
+
+    def check_reach(self):
+        """Resolve the deferred advection-reach checks (synchronises); raises if a back-trace could
+        have left the ghost rows."""
+        steps = self._older_reach + [self._pending_reach]
+        self._older_reach, self._pending_reach = [], []
+        for pending in steps:
+            for m, dt in pending:
+                self._reach_rows(float(m.item()), dt)
 
     def step_gen(self, visc: float, diff: float, dt: float):
         c, f = self.ctx, self.f
@@ -196,22 +248,20 @@ class SlabSolver(SlabLayout):
         yield from self._lin_solve(2, v0, v, alpha, beta)
         yield from self._project(u0, v0, u, v)
         if multi:
-            m = yield from self._advect_reach(u0, v0)
-            W = self._reach_rows(m, dt)
-            yield ("exchange", [HaloSpec(u0, W), HaloSpec(v0, W)])
+            W = yield from self._advect_reach(dt, u0, v0)
+            yield ("exchange", [HaloSpec(u0, W), HaloSpec(v0, W)], None)
         c.advect(1, u, u0, u0, v0, dt)
         c.advect(2, v, v0, u0, v0, dt)
         if multi:
-            yield ("exchange", [HaloSpec(u, 1), HaloSpec(v, 1)])
+            yield ("exchange", [HaloSpec(u, 1), HaloSpec(v, 1)], None)
         yield from self._project(u, v, u0, v0)
         # ---- dens_step (:176-186) ----
         c.add_source(d, d0, dt)
         alpha, beta = f32_coeffs(dt, diff, self.N)
         yield from self._lin_solve(0, d0, d, alpha, beta)
         if multi:
-            m = yield from self._advect_reach(u, v)
-            W = self._reach_rows(m, dt)
-            yield ("exchange", [HaloSpec(d0, W)])
+            W = yield from self._advect_reach(dt, u, v)
+            yield ("exchange", [HaloSpec(d0, W)], None)
         c.advect(0, d, d0, u, v, dt)
 
     def _reach_rows(self, max_vel: float, dt: float) -> int:
@@ -235,14 +285,20 @@ class SlabSolver(SlabLayout):
             for _ in self.step_gen(visc, diff, dt):
                 raise AssertionError("single-slab steps do not communicate")
             return
+        if self._pending_reach:
+            self._older_reach.append(self._pending_reach)
+            self._pending_reach = []
+        while len(self._older_reach) > 1:      # two steps old: that work finished long ago, no stall
+            for m, dt_old in self._older_reach.pop(0):
+                self._reach_rows(float(m.item()), dt_old)
         gen = self.step_gen(visc, diff, dt)
         reply = None
         while True:
             try:
-                kind, arg = gen.send(reply)
+                kind, arg, stream = gen.send(reply)
             except StopIteration:
                 break
-            reply = self.comm.serve(self, kind, arg)
+            reply = self.comm.serve(self, kind, arg, stream)
 
 
 class TorchDistComm:
@@ -269,7 +325,12 @@ class TorchDistComm:
                 ops.append(dist.P2POp(dist.irecv, s.recv_down(sp.field, h), s.rank + 1, self.group))
         return dist.batch_isend_irecv(ops) if ops else []
 
-    def serve(self, s: SlabLayout, kind: str, arg):
+    def serve(self, s: SlabLayout, kind: str, arg, stream=None):
+        """`stream`: the CUDA stream the request is ordered on (None = the current stream)."""
+        if stream is not None:
+            import torch
+            with torch.cuda.stream(stream):
+                return self.serve(s, kind, arg, None)
         if kind == "exchange":
             for r in self._post(s, arg):
                 r.wait()
@@ -279,6 +340,8 @@ class TorchDistComm:
             for r in self.pending or []:
                 r.wait()
             self.pending = None
+        elif kind == "allreduce_max_device":
+            self.dist.all_reduce(arg, op=self.dist.ReduceOp.MAX, group=self.group)
         elif kind == "allreduce_max":
             import torch
             t = torch.tensor([arg], dtype=torch.float32, device=s.f["u"].device if hasattr(s, "f") else "cpu")
@@ -322,6 +385,7 @@ def run_lockstep(solvers: Sequence[SlabSolver], visc: float, diff: float, dt: fl
         if all(r is None for r in reqs):
             return
         assert all(r is not None for r in reqs), "ranks left the step at different points"
+        assert all(r[2] is None for r in reqs), "lock-step emulation runs on one stream (overlap=False)"
         kinds = {r[0] for r in reqs}
         assert len(kinds) == 1, f"ranks diverged: {kinds}"
         kind = kinds.pop()
@@ -337,5 +401,9 @@ def run_lockstep(solvers: Sequence[SlabSolver], visc: float, diff: float, dt: fl
         elif kind == "allreduce_max":
             m = max(r[1] for r in reqs)
             replies = [m] * len(gens)
+        elif kind == "allreduce_max_device":
+            m = max(float(r[1].item()) for r in reqs)
+            for r in reqs:
+                r[1].fill_(m)
         else:
             raise ValueError(kind)

@@ -32,11 +32,11 @@ STRICT, FAST = 0, 1
 # every symbol include/stablefluids.h declares (tests/test_abi.py checks the library exports them)
 ABI_SYMBOLS = [
     "sf_create", "sf_create_on_stream", "sf_create_slab", "sf_destroy", "sf_last_error_string",
-    "sf_set_option", "sf_get_option", "sf_synchronize", "sf_launch_count", "sf_field_bytes",
+    "sf_set_option", "sf_get_option", "sf_synchronize", "sf_set_stream", "sf_launch_count", "sf_field_bytes",
     "sf_alloc_field", "sf_free_field", "sf_upload", "sf_download",
     "sf_set_bnd", "sf_add_source", "sf_diffuse", "sf_advect", "sf_compute_divergence_and_pressure",
     "sf_last_project", "sf_project", "sf_dens_step", "sf_vel_step", "sf_step", "sf_step_host",
-    "sf_init_synthetic", "sf_init_sources", "sf_reduce_max_abs", "sf_residual_l2",
+    "sf_init_synthetic", "sf_init_sources", "sf_reduce_max_abs", "sf_reduce_max_abs_async", "sf_residual_l2",
     "sf_division_check", "sf_halo_rows_needed", "sf_jacobi_launch",
 ]
 
@@ -67,6 +67,7 @@ def load_library() -> C.CDLL:
     L.sf_set_option.argtypes = [vp, i, i]
     L.sf_get_option.argtypes = [vp, i, C.POINTER(i)]
     L.sf_synchronize.argtypes = [vp]
+    L.sf_set_stream.argtypes = [vp, vp]
     L.sf_launch_count.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     L.sf_field_bytes.argtypes = [vp]
     L.sf_field_bytes.restype = C.c_size_t
@@ -88,6 +89,7 @@ def load_library() -> C.CDLL:
     L.sf_init_synthetic.argtypes = [vp, u64] + [vp] * 6
     L.sf_init_sources.argtypes = [vp, u64] + [vp] * 3
     L.sf_reduce_max_abs.argtypes = [vp, vp, C.POINTER(f)]
+    L.sf_reduce_max_abs_async.argtypes = [vp, vp, vp]
     L.sf_residual_l2.argtypes = [vp, vp, vp, f, f, C.POINTER(C.c_double)]
     L.sf_division_check.argtypes = [vp, f, C.POINTER(i)]
     L.sf_halo_rows_needed.argtypes = [vp, C.POINTER(i)]
@@ -225,6 +227,15 @@ class StableFluids:
         out = C.c_float(0)
         self._check(self.L.sf_reduce_max_abs(self.h, self._p(x), C.byref(out)))
         return float(out.value)
+
+    def reduce_max_abs_async(self, x, dev_scalar):
+        """dev_scalar (1-element float32 CUDA tensor) = max(dev_scalar, max|x|); no synchronisation."""
+        self._check(self.L.sf_reduce_max_abs_async(self.h, self._p(x), C.c_void_p(dev_scalar.data_ptr())))
+
+    def set_stream(self, stream):
+        """Order all later calls on `stream` (a torch.cuda.Stream)."""
+        self._stream = stream
+        self._check(self.L.sf_set_stream(self.h, C.c_void_p(stream.cuda_stream)))
 
     def residual_sumsq(self, x, x0, alpha, beta) -> float:
         out = C.c_double(0)

@@ -86,6 +86,9 @@ const char *sf_last_error_string(const sf_context *ctx);
 int sf_set_option(sf_context *ctx, int option, int value);
 int sf_get_option(const sf_context *ctx, int option, int *value);
 int sf_synchronize(sf_context *ctx);
+/* Re-target the context to another CUDA stream (all later calls are ordered on it).  Captured
+ * graphs are dropped, since a graph launch is bound to the stream it is replayed on only. */
+int sf_set_stream(sf_context *ctx, void *cuda_stream);
 /* Number of kernels this context has launched (graph replays count their kernel nodes). */
 int sf_launch_count(const sf_context *ctx, unsigned long long *count);
 size_t sf_field_bytes(const sf_context *ctx);      /* bytes of one (local) field */
@@ -138,6 +141,9 @@ int sf_init_sources(sf_context *ctx, uint64_t seed, float *dens_prev, float *u_p
 /* ---- diagnostics (warp-shuffle reductions) ------------------------------------------------- */
 /* max |x| over the owned cells; result written to *host_out after an internal synchronize. */
 int sf_reduce_max_abs(sf_context *ctx, const float *x, float *host_out);
+/* Asynchronous form for pipelines that must not stall: *dev_out = max(*dev_out, max |x|) with
+ * dev_out a DEVICE float the caller has initialised (e.g. to 0); no synchronisation. */
+int sf_reduce_max_abs_async(sf_context *ctx, const float *x, float *dev_out);
 /* || x0 - (beta*x - alpha*sum_nb(x)) ||_2 over the interior: the lin_solve residual. */
 int sf_residual_l2(sf_context *ctx, const float *x, const float *x0, float alpha, float beta, double *host_out);
 

@@ -15,13 +15,15 @@ def gather(solvers, name):
     return torch.cat([s.owned(s.f[name]) for s in solvers], dim=0).cpu().numpy()
 
 
+@pytest.mark.parametrize("deferred", [False, True])
 @pytest.mark.parametrize("world", [2, 3, 4])
 @pytest.mark.parametrize("N,K", [(254, 20), (126, 40)])
-def test_slabs_bit_identical_to_oracle(oracle, world, N, K):
+def test_slabs_bit_identical_to_oracle(oracle, world, N, K, deferred):
     from fluidsimulationcuda_b200.slab import SlabSolver, run_lockstep
     if (N + 2) // world < 16:
         pytest.skip("slab thinner than two boundary strips")
-    solvers = [SlabSolver(N, r, world, iters=K, halo=16 if N < 200 else 24) for r in range(world)]
+    solvers = [SlabSolver(N, r, world, iters=K, halo=16 if N < 200 else 24, overlap=False, deferred_reach=deferred)
+               for r in range(world)]
     for s in solvers:
         s.init_synthetic(5)
     w = oracle.init_synthetic(N, 5)
@@ -38,6 +40,8 @@ def test_slabs_bit_identical_to_oracle(oracle, world, N, K):
         for k in w:
             got = gather(solvers, k)
             assert bits_equal(got, w[k]), mismatch_report(got, w[k], f"world={world} step={step} {k}")
+    for s in solvers:
+        s.check_reach()
 
 
 def test_single_slab_solver_equals_plain_solver(oracle):
@@ -56,10 +60,13 @@ def test_advection_reach_larger_than_halo_is_an_error():
     from fluidsimulationcuda_b200.slab import SlabSolver, run_lockstep
     from fluidsimulationcuda_b200.solver import StableFluidsError
     N = 254
-    solvers = [SlabSolver(N, r, 2, iters=4, halo=8) for r in range(2)]
-    for s in solvers:
-        s.init_synthetic(1)
-        s.f["u_prev"].fill_(400.0)      # dt*N*v ~ 26 rows per step after add_source
-        s.f["v_prev"].fill_(400.0)
-    with pytest.raises(StableFluidsError):
-        run_lockstep(solvers, VIS, DIFF, DT)
+    for deferred in (False, True):
+        solvers = [SlabSolver(N, r, 2, iters=4, halo=8, overlap=False, deferred_reach=deferred) for r in range(2)]
+        for s in solvers:
+            s.init_synthetic(1)
+            s.f["u_prev"].fill_(400.0)      # dt*N*v ~ 26 rows per step after add_source
+            s.f["v_prev"].fill_(400.0)
+        with pytest.raises(StableFluidsError):
+            run_lockstep(solvers, VIS, DIFF, DT)
+            for s in solvers:               # deferred mode reports at the check, not inside the step
+                s.check_reach()

@@ -17,6 +17,7 @@ for st in range(steps):
     if st > 0:
         for k in ("dens_prev", "u_prev", "v_prev"): s.f[k].zero_()
     s.step(None, 0.0025, 0.1, 0.016)
+s.check_reach()
 torch.cuda.synchronize()
 ok = True
 for k in s.names:
