@@ -447,15 +447,16 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     if (rows <= 0) return cudaSuccess;
     int chunk = L.chunk_rows;
     if (chunk <= 0) {
-        // One work item (band x chunk) per resident warp: 16 warps per SM (4 CTAs of 4 warps).  All
-        // items cost about the same, so a single full wave has no tail; chunks are kept >= 16 T rows so
-        // that the 2T redundant halo rows stay a small share.
+        // One work item (band x chunk) per resident warp (12 or 16 warps per SM).  All items cost about
+        // the same, so a single full wave has no tail.  Large grids get chunks of hundreds of rows (2T
+        // redundant halo rows each: a few percent); small grids cannot fill the wave with such chunks and
+        // are latency-bound, so there the chunks shrink (down to 2T rows) to put every SM to work.
         const bool heavy = (L.mode == MODE_STRICT || L.mode == MODE_IEEE) && L.sweeps >= 6;   // min_ctas<T, MODE>()
         const int slots = sm_count * (heavy ? 3 : 4) * WPC;
         int want_chunks = slots / A.nbands;
         if (want_chunks < 1) want_chunks = 1;
         chunk = (rows + want_chunks - 1) / want_chunks;
-        const int min_chunk = 16 * L.sweeps;
+        const int min_chunk = 2 * L.sweeps > 8 ? 2 * L.sweeps : 8;
         if (chunk < min_chunk) chunk = min_chunk;
     }
     if (chunk > rows) chunk = rows;
