@@ -120,7 +120,9 @@ def run_reference(args):
         "impl": "reference", "metric": "jacobi_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"stable-fluids step G={G} (N={N}), {K} Jacobi iterations", "grid": G, "iters": K},
+        "config": {"workload": f"stable-fluids step (vel_step + dens_step) G={G} (N={N}), {K} Jacobi iterations per lin_solve, "
+                               f"the reference's sequential CPU path, sampled as one dens_step per step",
+                   "grid": G, "iters": K, "parallelism": "1 host thread (the reference has no threading)"},
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -49,6 +49,7 @@ struct sf_context {
     int use_graph = 1;
     int force_generic = 0;
     int chunk_rows = 0;
+    int staging = 0;
     float *scratch = nullptr;        // lin_solve ping-pong partner
     float *red_f = nullptr;          // reduction outputs
     double *red_d = nullptr;
@@ -143,6 +144,7 @@ int one_jacobi_launch(sf_context *c, int b, float *xout, const float *xin, const
     L.out_lo = out_lo; L.out_hi = out_hi;
     L.chunk_rows = c->chunk_rows;
     L.zero_guess = zero_guess;
+    L.staging = c->staging;
     const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
     if (stream_ok) {
         SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, c->work));
@@ -314,6 +316,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.f[0] = f0; k.f[1] = f1; k.f[2] = f2;
     k.iters = iters;
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
+    k.opts[4] = c->staging;
     return k;
 }
 
@@ -393,6 +396,7 @@ int sf_set_option(sf_context *c, int option, int value)
         case SF_OPT_USE_GRAPH: c->use_graph = value ? 1 : 0; break;
         case SF_OPT_FORCE_GENERIC: c->force_generic = value ? 1 : 0; break;
         case SF_OPT_CHUNK_ROWS: SF_REQUIRE(c, value >= 0, "chunk rows >= 0"); c->chunk_rows = value; break;
+        case SF_OPT_STAGING: SF_REQUIRE(c, value == 0 || value == 1, "staging: 0 cp.async / 1 bulk copy"); c->staging = value; break;
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }
     return SF_OK;
@@ -407,6 +411,7 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_USE_GRAPH: *value = c->use_graph; break;
         case SF_OPT_FORCE_GENERIC: *value = c->force_generic; break;
         case SF_OPT_CHUNK_ROWS: *value = c->chunk_rows; break;
+        case SF_OPT_STAGING: *value = c->staging; break;
         default: return SF_ERR_INVALID;
     }
     return SF_OK;

@@ -76,6 +76,35 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory"); }
 
+// ---- TMA-style staging: 1-D bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ float4 scale4(float4 v, float s)
 {
     return make_float4(__fmul_rn(v.x, s), __fmul_rn(v.y, s), __fmul_rn(v.z, s), __fmul_rn(v.w, s));
@@ -162,7 +191,10 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
     return ok;
 }
 
-template <int T, int MODE>
+// TMA = false: rows are staged with per-lane cp.async (LDGSTS.128).  TMA = true: one elected lane
+// issues a 1-D bulk copy (cp.async.bulk -> UBLKCP) of the warp's whole 512-byte row piece per field,
+// completing on a per-slot mbarrier that all lanes wait on (SF_OPT_STAGING; measured in DESIGN.md).
+template <int T, int MODE, bool TMA>
 __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
 {
     extern __shared__ float4 ring[];
@@ -184,6 +216,22 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
 
     float4 *xring = ring + (size_t)warp * (RING_X + RING_R) * 32 + lane;
     float4 *rring = xring + RING_X * 32;
+    // TMA staging: per-warp mbarriers behind the rings, one per x-ring slot (row r uses slot r & 7)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)WPC * (RING_X + RING_R) * 32) + warp * RING_X;
+    const int col0 = band * VALID_W - HALO_X;                 // band's first column (may be < 0)
+    const int tma_lo = max(col0, 0), tma_hi = min(col0 + BAND_W, A.G);
+    const unsigned tma_bytes = (unsigned)(tma_hi - tma_lo) * 4u;
+    if (TMA) {
+        if (!indom) {   // lanes outside the grid are never written by the bulk copies: zero them once
+            for (int k = 0; k < RING_X; ++k) xring[k * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < RING_R; ++k) rring[k * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (lane == 0) {
+            for (int k = 0; k < RING_X; ++k) mbar_init(bars + k, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     const int s_lo = max(a_lo - T, 0);
     const int s_hi = a_hi - 1 + T;                 // inclusive
@@ -194,6 +242,18 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     const bool zero_guess = A.zero_guess != 0;
 
     auto issue = [&](int row) {
+        if (TMA) {
+            if (row <= load_hi && lane == 0) {
+                const size_t off = (size_t)(row - A.row_base) * pitch + tma_lo;
+                uint64_t *bar = bars + (row & (RING_X - 1));
+                float4 *xw = xring - lane, *rw = rring - lane;     // warp-level ring bases
+                mbar_expect_tx(bar, zero_guess ? tma_bytes : 2u * tma_bytes);
+                if (!zero_guess)
+                    bulk_copy_g2s(reinterpret_cast<float *>(xw + (row & (RING_X - 1)) * 32) + (tma_lo - col0), A.xin + off, tma_bytes, bar);
+                bulk_copy_g2s(reinterpret_cast<float *>(rw + (row & (RING_R - 1)) * 32) + (tma_lo - col0), A.rhs + off, tma_bytes, bar);
+            }
+            return;
+        }
         if (row <= load_hi) {
             const size_t off = (size_t)(row - A.row_base) * pitch;
             if (!zero_guess) cp_async16(xring + (row & (RING_X - 1)) * 32, xsrc + off, nbytes);
@@ -201,9 +261,20 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
         }
         cp_async_commit();
     };
-    auto fetch = [&](int row) -> float4 {   // level-0 row `row` (after its cp.async group landed)
+    // rows [first, first + n) have been issued; block until they have landed
+    auto landed = [&](int first, int n) {
+        if (TMA) {
+            for (int k = 0; k < n; ++k) {
+                const int row = first + k;
+                if (row <= load_hi) mbar_wait(bars + (row & (RING_X - 1)), (unsigned)((row - s_lo) >> 3) & 1u);
+            }
+        } else {
+            cp_async_wait<PREFETCH>();
+        }
+    };
+    auto fetch = [&](int row) -> float4 {   // level-0 row `row` (after it landed)
         issue(row + PREFETCH);
-        cp_async_wait<PREFETCH>();
+        landed(row, 1);
         float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!zero_guess && row <= load_hi) in = xring[(row & (RING_X - 1)) * 32];
         return in;
@@ -273,7 +344,7 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     while (s <= s_hi) {
         if (!slow && s >= fast_lo && s + 2 <= fast_hi) {
             issue(s + PREFETCH); issue(s + PREFETCH + 1); issue(s + PREFETCH + 2);
-            cp_async_wait<PREFETCH>();       // rows <= s+2 have landed
+            landed(s, 3);                    // rows <= s+2 have landed
             if (MODE == MODE_STRICT) slow = __any_sync(0xffffffffu, row_is_big(s) | row_is_big(s + 1) | row_is_big(s + 2));
             if (!slow) {
                 float4 o;
@@ -319,7 +390,12 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
         general_tick(s, fetch(s));
         ++s;
     }
-    cp_async_wait<0>();
+    if (TMA) {   // drain: rows issued beyond the last one consumed must land before the CTA's smem is released
+        for (int row = s_hi + 1; row <= min(s_hi + PREFETCH + 2, load_hi); ++row)
+            mbar_wait(bars + (row & (RING_X - 1)), (unsigned)((row - s_lo) >> 3) & 1u);
+    } else {
+        cp_async_wait<0>();
+    }
 }
 
 // ---- generic fallback: one sweep, one thread per interior cell, any G -----------------------
@@ -364,26 +440,40 @@ __global__ void validate_division_kernel(DivConst d, unsigned long long *mismatc
 }
 
 template <int T, int MODE>
-cudaError_t launch_stream_T(const StreamArgs &A, dim3 grid, size_t smem, cudaStream_t st)
+cudaError_t launch_stream_T(const StreamArgs &A, dim3 grid, size_t smem, bool tma, cudaStream_t st)
 {
     static_assert((size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4) <= 48 * 1024,
                   "ring fits the default 48 KB dynamic shared memory limit (no attribute call needed)");
-    jacobi_stream_kernel<T, MODE><<<grid, WPC * 32, smem, st>>>(A);
+    // the bulk-copy variant is built for the depths the default launch plans use (5, 6, 7)
+    if (tma && (T == 5 || T == 6 || T == 7) && (MODE == MODE_STRICT || MODE == MODE_PRESSURE)) {
+        constexpr int TT = (T == 5 || T == 6 || T == 7) ? T : 7;
+        constexpr int MM = (MODE == MODE_STRICT || MODE == MODE_PRESSURE) ? MODE : MODE_PRESSURE;
+        const size_t smem_tma = smem + (size_t)WPC * RING_X * sizeof(uint64_t);
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(jacobi_stream_kernel<TT, MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        jacobi_stream_kernel<TT, MM, true><<<grid, WPC * 32, smem_tma, st>>>(A);
+        return cudaGetLastError();
+    }
+    jacobi_stream_kernel<T, MODE, false><<<grid, WPC * 32, smem, st>>>(A);
     return cudaGetLastError();
 }
 
 template <int MODE>
-cudaError_t launch_stream_mode(int T, const StreamArgs &A, dim3 grid, size_t smem, cudaStream_t st)
+cudaError_t launch_stream_mode(int T, const StreamArgs &A, dim3 grid, size_t smem, bool tma, cudaStream_t st)
 {
     switch (T) {
-        case 1: return launch_stream_T<1, MODE>(A, grid, smem, st);
-        case 2: return launch_stream_T<2, MODE>(A, grid, smem, st);
-        case 3: return launch_stream_T<3, MODE>(A, grid, smem, st);
-        case 4: return launch_stream_T<4, MODE>(A, grid, smem, st);
-        case 5: return launch_stream_T<5, MODE>(A, grid, smem, st);
-        case 6: return launch_stream_T<6, MODE>(A, grid, smem, st);
-        case 7: return launch_stream_T<7, MODE>(A, grid, smem, st);
-        case 8: return launch_stream_T<8, MODE>(A, grid, smem, st);
+        case 1: return launch_stream_T<1, MODE>(A, grid, smem, tma, st);
+        case 2: return launch_stream_T<2, MODE>(A, grid, smem, tma, st);
+        case 3: return launch_stream_T<3, MODE>(A, grid, smem, tma, st);
+        case 4: return launch_stream_T<4, MODE>(A, grid, smem, tma, st);
+        case 5: return launch_stream_T<5, MODE>(A, grid, smem, tma, st);
+        case 6: return launch_stream_T<6, MODE>(A, grid, smem, tma, st);
+        case 7: return launch_stream_T<7, MODE>(A, grid, smem, tma, st);
+        case 8: return launch_stream_T<8, MODE>(A, grid, smem, tma, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -466,10 +556,10 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     dim3 grid((items + WPC - 1) / WPC);
     const size_t smem = (size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4);
     switch (L.mode) {
-        case MODE_PRESSURE: return launch_stream_mode<MODE_PRESSURE>(L.sweeps, A, grid, smem, st);
-        case MODE_FAST: return launch_stream_mode<MODE_FAST>(L.sweeps, A, grid, smem, st);
-        case MODE_STRICT: return launch_stream_mode<MODE_STRICT>(L.sweeps, A, grid, smem, st);
-        default: return launch_stream_mode<MODE_IEEE>(L.sweeps, A, grid, smem, st);
+        case MODE_PRESSURE: return launch_stream_mode<MODE_PRESSURE>(L.sweeps, A, grid, smem, L.staging == 1, st);
+        case MODE_FAST: return launch_stream_mode<MODE_FAST>(L.sweeps, A, grid, smem, L.staging == 1, st);
+        case MODE_STRICT: return launch_stream_mode<MODE_STRICT>(L.sweeps, A, grid, smem, L.staging == 1, st);
+        default: return launch_stream_mode<MODE_IEEE>(L.sweeps, A, grid, smem, L.staging == 1, st);
     }
 }
 

@@ -217,6 +217,33 @@ __global__ void init_kernel(float *dens, float *dens_prev, float *u, float *u_pr
     if (u) u[i] = 0.0f;
     if (v) v[i] = 0.0f;
 }
+// float4 variant (G % 4 == 0): one thread writes four consecutive cells of each field
+__global__ void __launch_bounds__(256) init4_kernel(float *dens, float *dens_prev, float *u, float *u_prev, float *v,
+                                                    float *v_prev, Geom g, uint64_t seed)
+{
+    const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y + g.own_lo;
+    if (col >= g.G || row >= g.own_hi) return;
+    const size_t cell = (size_t)row * g.G + col;
+    const size_t i = (size_t)(row - g.row_base) * g.G + col;
+    const int mid = g.G / 2, half = g.G / 8;
+    const bool rin = (row < mid + half) && (row >= mid - half);
+    float d[4], a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool inside = rin && (col + k < mid + half) && (col + k >= mid - half);
+        d[k] = inside ? __fdiv_rn((float)hash100(seed, 0, cell + k), 1000.0f) : 0.0f;
+        a[k] = __fdiv_rn((float)hash100(seed, 1, cell + k), 100.0f);
+        b[k] = __fdiv_rn((float)hash100(seed, 2, cell + k), 100.0f);
+    }
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dens_prev) *reinterpret_cast<float4 *>(dens_prev + i) = make_float4(d[0], d[1], d[2], d[3]);
+    if (u_prev) *reinterpret_cast<float4 *>(u_prev + i) = make_float4(a[0], a[1], a[2], a[3]);
+    if (v_prev) *reinterpret_cast<float4 *>(v_prev + i) = make_float4(b[0], b[1], b[2], b[3]);
+    if (dens) *reinterpret_cast<float4 *>(dens + i) = z;
+    if (u) *reinterpret_cast<float4 *>(u + i) = z;
+    if (v) *reinterpret_cast<float4 *>(v + i) = z;
+}
 
 // ---- reductions (warp shuffle, then one atomic per block) ------------------------------------
 __global__ void max_abs_kernel(const float *__restrict__ x, size_t first, size_t count, float *out)
@@ -516,6 +543,13 @@ cudaError_t launch_init(const Geom &g, uint64_t seed, float *dens, float *dens_p
                         float *v_prev, cudaStream_t st)
 {
     const dim3 block(64, 4);
+    bool vec = (g.G % 4 == 0);
+    for (const float *p : {dens, dens_prev, u, u_prev, v, v_prev}) vec = vec && ((uintptr_t)p % 16 == 0);
+    if (vec) {
+        const dim3 grid4((g.G / 4 + 63) / 64, (g.own_hi - g.own_lo + 3) / 4);
+        init4_kernel<<<grid4, block, 0, st>>>(dens, dens_prev, u, u_prev, v, v_prev, g, seed);
+        return cudaGetLastError();
+    }
     const dim3 grid((g.G + 63) / 64, (g.own_hi - g.own_lo + 3) / 4);
     init_kernel<<<grid, block, 0, st>>>(dens, dens_prev, u, u_prev, v, v_prev, g, seed);
     return cudaGetLastError();

@@ -27,6 +27,7 @@ SF_OPT_SWEEPS_PER_LAUNCH = 2
 SF_OPT_USE_GRAPH = 3
 SF_OPT_FORCE_GENERIC = 4
 SF_OPT_CHUNK_ROWS = 5
+SF_OPT_STAGING = 6
 STRICT, FAST = 0, 1
 
 # every symbol include/stablefluids.h declares (tests/test_abi.py checks the library exports them)

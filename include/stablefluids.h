@@ -63,7 +63,10 @@ enum {
      * streaming kernels (testing aid). */
     SF_OPT_FORCE_GENERIC = 4,
     /* interior rows per streaming chunk (0 = automatic). */
-    SF_OPT_CHUNK_ROWS = 5
+    SF_OPT_CHUNK_ROWS = 5,
+    /* how the Jacobi kernel stages rows global -> shared: 0 (default) = cp.async per lane
+     * (LDGSTS.128), 1 = one bulk copy per warp row through the TMA unit (cp.async.bulk + mbarrier). */
+    SF_OPT_STAGING = 6
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 

@@ -223,14 +223,15 @@ void so_init_reference_rand(int N, float *dens, float *dens_prev, float *u, floa
 
 /* Counter-based synthetic initial condition with the reference's value distributions
  * (SURVEY.md section 8(d)): same formula as the device-side generator sf_init_synthetic, so big
- * grids never cross PCIe.  splitmix64 finaliser over (seed, field, cell). */
+ * grids never cross PCIe.  32-bit avalanche mixer over (seed, field, cell), reduced to 0..99. */
 static inline uint32_t so_hash100(uint64_t seed, uint64_t field, uint64_t cell)
 {
-    uint64_t z = seed * 0x9E3779B97F4A7C15ull + field * 0xD1B54A32D192ED03ull + cell;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z % 100ull);
+    uint32_t h = (uint32_t)cell ^ (uint32_t)(cell >> 32) * 0x9E3779B1u;
+    h ^= (uint32_t)seed * 0x85EBCA6Bu + (uint32_t)field * 0xC2B2AE35u + 0x27D4EB2Fu;
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return (uint32_t)(((uint64_t)h * 100ull) >> 32);
 }
 
 void so_init_synthetic(int N, uint64_t seed, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev)

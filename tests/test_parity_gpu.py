@@ -113,6 +113,20 @@ def test_diffuse_subnormal_and_zero_fields(SF, oracle):
     assert_same(host(dx), want, "subnormal diffuse")
 
 
+@pytest.mark.parametrize("N,K", [(126, 40), (254, 20), (510, 40), (222, 21)])
+def test_diffuse_bulk_copy_staging(SF, oracle, N, K):
+    """SF_OPT_STAGING=1: rows staged by cp.async.bulk (TMA unit) + mbarrier instead of per-lane cp.async."""
+    G = N + 2
+    rng = np.random.default_rng(N * K)
+    s = SF.StableFluids(N)
+    s.set_option(SF.SF_OPT_STAGING, 1)
+    for b, (alpha, beta) in ((0, (1.0, 4.0)), (1, (2683.2, 10733.8)), (2, (0.635, 3.54))):
+        x, x0 = rnd(rng, G), rnd(rng, G)
+        want = x.copy(); oracle.diffuse(N, b, want, x0, alpha, beta, K)
+        dx = dev(x); s.diffuse(b, dx, dev(x0), alpha, beta, K)
+        assert_same(host(dx), want, f"bulk staging N={N} K={K} b={b}")
+
+
 def test_diffuse_huge_values_take_the_guarded_path(SF, oracle):
     """Magnitudes beyond the fast division's validated range (|a| > 1e30) must still be exact: the
     streaming kernel detects them when a row is fetched and switches to the fully guarded tick."""
@@ -287,3 +301,48 @@ def test_c_example_with_reference_names(oracle, tmp_path):
         oracle.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=0)
     want = float(w["dens"].astype(np.float64).sum())
     assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (got, want)
+
+
+@pytest.mark.parametrize("G,K", [(4096, 40)] + ([(8192, 40)] if os.environ.get("SF_TEST_FULL_SIZE") else []))
+def test_full_size_step_against_threaded_oracle(SF, oracle_mt, G, K):
+    """One whole step at a BASELINE-sized grid, bit for bit against the (threaded, identical) oracle.
+    G=8192 (the headline configuration, ~1 min of CPU) runs when SF_TEST_FULL_SIZE=1."""
+    N = G - 2
+    s = SF.StableFluids(N)
+    names = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
+    f = {k: s.new_field() for k in names}
+    s.init_synthetic(2, *[f[k] for k in names])
+    w = oracle_mt.init_synthetic(N, 2)
+    s.step(*[f[k] for k in names], VIS, DIFF, DT, K)
+    oracle_mt.run_steps(N, 1, w, VIS, DIFF, DT, K)
+    for k in names:
+        assert_same(host(f[k]), w[k], f"G={G} {k}")
+
+
+def test_full_size_properties_8192(SF):
+    """Size-independent properties at the headline size (G=8192, K=40), no oracle needed:
+    (1) determinism / graph replay: the same step from the same state twice gives identical bits;
+    (2) the temporal-blocking depth does not change a single bit (T = 1 launch-per-sweep vs T = 8);
+    (3) set_bnd is idempotent on the solver's outputs and the walls obey the mirror rule."""
+    import torch
+    N, K = 8190, 40
+    names = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
+    outs = []
+    for T in (8, 8, 3):
+        s = SF.StableFluids(N, sweeps_per_launch=T)
+        f = {k: s.new_field() for k in names}
+        s.init_synthetic(4, *[f[k] for k in names])
+        for rep in range(2):          # second call replays the captured graph
+            s.init_sources(4 + rep, f["dens_prev"], f["u_prev"], f["v_prev"])
+            s.step(*[f[k] for k in names], VIS, DIFF, DT, K)
+        torch.cuda.synchronize()
+        outs.append({k: f[k].clone() for k in ("dens", "u", "v")})
+        if T == 3:
+            u = f["u"]
+            assert torch.equal(u[1:-1, 0], -u[1:-1, 1]) and torch.equal(u[1:-1, -1], -u[1:-1, -2])   # b = 1
+            assert torch.equal(u[0, 1:-1], u[1, 1:-1])
+            before = u.clone(); s.set_bnd(1, u); assert torch.equal(before.view(torch.int32), u.view(torch.int32))
+        s.close(); del f
+    for k in ("dens", "u", "v"):
+        assert torch.equal(outs[0][k].view(torch.int32), outs[1][k].view(torch.int32)), f"non-deterministic {k}"
+        assert torch.equal(outs[0][k].view(torch.int32), outs[2][k].view(torch.int32)), f"blocking depth changed {k}"

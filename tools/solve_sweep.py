@@ -3,9 +3,13 @@ import torch, os
 from fluidsimulationcuda_b200 import solver as SF
 print("lib", os.environ.get("SF_LIBRARY", "default"))
 G = 8192; K = 40
-for T in (5, 6, 7, 8):
+import sys
+staging = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+print("staging", staging)
+for T in (5, 7):
     for mode, (al, be) in (("pressure", (1.0, 4.0)), ("strict", (2683.2, 10733.8))):
         s = SF.StableFluids(G - 2, sweeps_per_launch=T, use_graph=False)
+        s.set_option(SF.SF_OPT_STAGING, staging)
         x, x0 = s.new_field(), s.new_field(); x.uniform_(0, 1); x0.uniform_(0, 1)
         for _ in range(2): s.diffuse(0, x, x0, al, be, K)
         torch.cuda.synchronize()
