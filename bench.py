@@ -191,8 +191,14 @@ def run_ours(args):
 
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        from fluidsimulationcuda_b200.slab import SlabSolver, TorchDistComm
-        sim = SlabSolver(N, rank, world, iters=K, arithmetic=SF.STRICT, comm=TorchDistComm())
+        from fluidsimulationcuda_b200.slab import SlabSolver, TorchDistComm, PeerSlabSolver
+        if args.slab_comm == "peer":
+            # product path: neighbours' slabs mapped over NVLink (CUDA IPC), halo pushes fused into the
+            # Jacobi strips, device-side neighbour barriers, one CUDA-graph replay per step per GPU
+            sim = PeerSlabSolver(N, rank, world, iters=K, arithmetic=SF.STRICT)
+            sim.connect_dist()
+        else:
+            sim = SlabSolver(N, rank, world, iters=K, arithmetic=SF.STRICT, comm=TorchDistComm())
         sim.init_synthetic(1)
         step = lambda seed: sim.step(seed, VIS, DIFF, DT)
         sync = lambda: (torch.cuda.synchronize(), dist.barrier())
@@ -215,14 +221,16 @@ def run_ours(args):
     if sampler:
         sampler.start(); time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # events go on the stream the kernels are launched on (a peer slab owns its stream)
+    tstream = sim.stream if (world > 1 and args.slab_comm == "peer") else torch.cuda.current_stream()
     n0 = launches()
     sync()
-    ev0.record()
+    ev0.record(tstream)
     for i in range(args.steps):
         step(1000 + i)
     if world > 1:
         sim.check_reach()      # deferred advection-reach verification of the last steps (synchronises)
-    ev1.record()
+    ev1.record(tstream)
     sync()
     ms = ev0.elapsed_time(ev1)
     n_launch = launches() - n0
@@ -248,6 +256,10 @@ def run_ours(args):
                    "grid": G, "iters": K, "parallelism": f"row slabs x{world}" if world > 1 else "single GPU",
                    "l2": "every field (G^2*4 B = %.0f MiB) is larger than the 126 MB L2; 9 fields live" % (cells * 4 / 2**20),
                    "per_step": ("device-side source refresh + vel_step + dens_step, replayed from a CUDA graph" if world == 1 else
+                                "device-side source refresh + vel_step + dens_step per slab, one CUDA-graph replay per GPU; halo rows "
+                                "stored into the neighbour's ghost rows over NVLink by the Jacobi boundary-strip kernels (peer memory) "
+                                "while the interior launch runs; advect gathers through the peer mapping; device-side neighbour barriers"
+                                if args.slab_comm == "peer" else
                                 "device-side source refresh + vel_step + dens_step per slab; NCCL neighbour halo exchange "
                                 "overlapped with the interior Jacobi launch; MAX all-reduce for the advection reach")},
         "full_step_cells_per_s": cells / (ms_step * 1e-3),
@@ -332,6 +344,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=0, help="full grid width G = N+2 (default 8192 at 1 GPU, 32768 at >1)")
     ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--slab-comm", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU halo traffic: peer = fused peer-memory pushes + device barriers (default), nccl = NCCL send/recv")
     ap.add_argument("--skip-extras", action="store_true",
                     help="only the timed region (no roofline / e2e / cpu_baseline passes): for ncu launch lists")
     args = ap.parse_args()

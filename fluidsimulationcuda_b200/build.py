@@ -11,8 +11,8 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libstablefluids_b200.so")
-SOURCES = ["sf_api.cu", "sf_jacobi.cu", "sf_stages.cu"]
-HEADERS = ["sf_common.cuh", os.path.join("..", "..", "include", "stablefluids.h")]
+SOURCES = ["sf_api.cu", "sf_jacobi.cu", "sf_stages.cu", "sf_slab.cu"]
+HEADERS = ["sf_common.cuh", "sf_internal.h", os.path.join("..", "..", "include", "stablefluids.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

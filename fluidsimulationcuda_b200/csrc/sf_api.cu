@@ -11,87 +11,11 @@
 #include <string>
 #include <vector>
 
-#include "../../include/stablefluids.h"
-#include "sf_common.cuh"
+#include "sf_internal.h"
 
 using namespace sf;
 
-namespace {
-
-struct GraphKey {   // laid out without padding so memcmp is a valid equality
-    uint64_t kind;
-    const void *p[6];
-    float f[4];
-    int iters;
-    int opts[5];
-    bool operator==(const GraphKey &o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
-};
-struct GraphEntry {
-    GraphKey key;
-    cudaGraphExec_t exec;
-    cudaGraph_t graph;
-    unsigned long long kernels;
-    unsigned long long last_use;
-};
-
-}  // namespace
-
-struct sf_context {
-    Geom g;
-    int device = 0;
-    cudaStream_t stream = nullptr;   // the stream results are ordered on (own or caller's)
-    cudaStream_t work = nullptr;     // where launches go: == stream, or cap_stream while capturing
-    cudaStream_t cap_stream = nullptr;
-    bool own_stream = false;
-    int sm_count = 148;
-    int arith = SF_ARITH_STRICT;
-    int sweeps_opt = 0;
-    int use_graph = 1;
-    int force_generic = 0;
-    int chunk_rows = 0;
-    int staging = 0;
-    float *scratch = nullptr;        // lin_solve ping-pong partner
-    float *red_f = nullptr;          // reduction outputs
-    double *red_d = nullptr;
-    unsigned long long launches = 0;
-    unsigned long long tick = 0;
-    bool capturing = false;
-    std::string err;
-    std::vector<GraphEntry> graphs;
-    // sf_step_host resources
-    float *stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t h2d = nullptr, d2h = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-};
-
-namespace {
-
-int fail(sf_context *c, int code, const char *what, cudaError_t e = cudaSuccess)
-{
-    if (c) {
-        c->err = what;
-        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
-    }
-    return code;
-}
-#define SF_CUDA(ctx, call)                                                       \
-    do {                                                                         \
-        cudaError_t e_ = (call);                                                 \
-        if (e_ != cudaSuccess) return fail(ctx, SF_ERR_CUDA, #call, e_);         \
-    } while (0)
-#define SF_REQUIRE(ctx, cond, msg)                                               \
-    do {                                                                         \
-        if (!(cond)) return fail(ctx, SF_ERR_INVALID, msg);                      \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-size_t field_cells(const sf_context *c) { return (size_t)c->g.rows * (size_t)c->g.G; }
-bool is_full_grid(const sf_context *c) { return c->g.own_lo == 0 && c->g.own_hi == c->g.G; }
+namespace sf {
 
 int ensure_scratch(sf_context *c)
 {
@@ -134,8 +58,8 @@ std::vector<int> plan_launches(int iters, int T)
     return plan;
 }
 
-int one_jacobi_launch(sf_context *c, int b, float *xout, const float *xin, const float *x0, float alpha, float beta,
-                      int sweeps, int out_lo, int out_hi, int zero_guess)
+int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const float *xin, const float *x0, float alpha,
+                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, const PushSpec &push)
 {
     JacobiLaunch L;
     L.xin = xin; L.rhs = x0; L.xout = xout;
@@ -145,16 +69,17 @@ int one_jacobi_launch(sf_context *c, int b, float *xout, const float *xin, const
     L.chunk_rows = c->chunk_rows;
     L.zero_guess = zero_guess;
     L.staging = c->staging;
-    const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
-    if (stream_ok) {
-        SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, c->work));
+    L.xpeer = push.xpeer; L.peer_row_base = push.peer_row_base; L.push_lo = push.push_lo; L.push_hi = push.push_hi;
+    if (stream_kernels_ok(c)) {
+        SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, st));
     } else {
         SF_REQUIRE(c, sweeps == 1, "generic Jacobi kernel does one sweep per launch");
+        SF_REQUIRE(c, push.xpeer == nullptr, "generic Jacobi kernel cannot push rows to a neighbour");
         if (zero_guess) {
             // generic kernel always reads xin
-            SF_CUDA(c, cudaMemsetAsync(const_cast<float *>(xin), 0, field_cells(c) * sizeof(float), c->work));
+            SF_CUDA(c, cudaMemsetAsync(const_cast<float *>(xin), 0, field_cells(c) * sizeof(float), st));
         }
-        SF_CUDA(c, launch_jacobi_generic(c->g, L, c->work));
+        SF_CUDA(c, launch_jacobi_generic(c->g, L, st));
     }
     ++c->launches;
     return SF_OK;
@@ -163,13 +88,14 @@ int one_jacobi_launch(sf_context *c, int b, float *xout, const float *xin, const
 // lin_solve: result always ends in x.
 int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess)
 {
+    if (is_linked_slab(c)) return slab_lin_solve(c, b, x, x0, alpha, beta, iters, zero_guess);
     int rc = ensure_scratch(c);
     if (rc) return rc;
     const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
     const std::vector<int> plan = plan_launches(iters, stream_ok ? default_sweeps(c) : 1);
     float *cur = x, *nxt = c->scratch;
     for (size_t k = 0; k < plan.size(); ++k) {
-        rc = one_jacobi_launch(c, b, nxt, cur, x0, alpha, beta, plan[k], c->g.own_lo, c->g.own_hi, zero_guess && k == 0);
+        rc = one_jacobi_launch(c, c->work, b, nxt, cur, x0, alpha, beta, plan[k], c->g.own_lo, c->g.own_hi, zero_guess && k == 0);
         if (rc) return rc;
         float *t = cur; cur = nxt; nxt = t;
     }
@@ -179,7 +105,7 @@ int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, floa
 
 int check_multi_launch_ok(sf_context *c, int iters)
 {
-    if (is_full_grid(c)) return SF_OK;
+    if (is_full_grid(c) || is_linked_slab(c)) return SF_OK;
     const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
     const int L = (int)plan_launches(iters, stream_ok ? default_sweeps(c) : 1).size();
     if (L > 1)
@@ -192,6 +118,7 @@ int check_multi_launch_ok(sf_context *c, int iters)
 // ---- step bodies (enqueue only) --------------------------------------------------------------
 int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters)
 {
+    if (is_linked_slab(c)) return slab_dens_step(c, x, x0, u, v, diff, dt, iters);
     float *xs[1] = {x};
     const float *ss[1] = {x0};
     SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->work));
@@ -211,6 +138,7 @@ int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const 
 
 int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters)
 {
+    if (is_linked_slab(c)) return slab_project(c, u, v, p, div, iters);
     // the streaming lin_solve can start from an implicit zero guess, so p need not be written here
     const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
     SF_CUDA(c, launch_divergence(c->g, u, v, p, div, stream_ok ? 0 : 1, c->work));
@@ -224,6 +152,7 @@ int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int
 
 int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
 {
+    if (is_linked_slab(c)) return slab_vel_step(c, u, v, u0, v0, visc, dt, iters);
     float *xs[2] = {u, v};
     const float *ss[2] = {u0, v0};
     SF_CUDA(c, launch_add_source(c->g, 2, xs, ss, dt, c->work));
@@ -245,67 +174,6 @@ int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, fl
     return enqueue_project(c, u, v, u0, v0, iters);                    // :238-240 (p in u0, div in v0)
 }
 
-// ---- CUDA graph cache ------------------------------------------------------------------------
-template <class Body>
-int run_graphed(sf_context *c, const GraphKey &key, Body body)
-{
-    if (!c->use_graph || c->capturing) return body();
-    ++c->tick;
-    GraphEntry *seen = nullptr;
-    for (auto &e : c->graphs)
-        if (e.key == key) {
-            e.last_use = c->tick;
-            if (e.exec) {
-                SF_CUDA(c, cudaGraphLaunch(e.exec, c->stream));
-                c->launches += e.kernels;
-                return SF_OK;
-            }
-            seen = &e;
-        }
-    int rc = ensure_scratch(c);
-    if (rc) return rc;
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(c->stream, &st);
-    if (st != cudaStreamCaptureStatusNone) return body();   // caller is capturing already
-    if (!seen) {
-        // First sighting of these arguments: launch directly (this also loads the kernels' modules
-        // outside of any capture); the second call with the same arguments captures the graph.
-        if (c->graphs.size() >= 16) {   // evict least recently used
-            size_t victim = 0;
-            for (size_t k = 1; k < c->graphs.size(); ++k)
-                if (c->graphs[k].last_use < c->graphs[victim].last_use) victim = k;
-            if (c->graphs[victim].exec) { cudaGraphExecDestroy(c->graphs[victim].exec); cudaGraphDestroy(c->graphs[victim].graph); }
-            c->graphs.erase(c->graphs.begin() + victim);
-        }
-        c->graphs.push_back(GraphEntry{key, nullptr, nullptr, 0, c->tick});
-        return body();
-    }
-    // Capture on a private stream: the caller's stream may be the legacy default stream, which
-    // cannot be captured.  The instantiated graph is then launched on the caller's stream.
-    if (!c->cap_stream) SF_CUDA(c, cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
-    const unsigned long long before = c->launches;
-    c->capturing = true;
-    cudaError_t e = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) { c->capturing = false; return fail(c, SF_ERR_CUDA, "cudaStreamBeginCapture", e); }
-    c->work = c->cap_stream;
-    rc = body();
-    c->work = c->stream;
-    cudaGraph_t graph = nullptr;
-    e = cudaStreamEndCapture(c->cap_stream, &graph);
-    c->capturing = false;
-    const unsigned long long kernels = c->launches - before;
-    c->launches = before;
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) return fail(c, SF_ERR_CUDA, "cudaStreamEndCapture", e);
-    cudaGraphExec_t exec = nullptr;
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail(c, SF_ERR_CUDA, "cudaGraphInstantiate", e); }
-    seen->exec = exec; seen->graph = graph; seen->kernels = kernels;
-    SF_CUDA(c, cudaGraphLaunch(exec, c->stream));
-    c->launches += kernels;
-    return SF_OK;
-}
-
 GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const void *> ptrs, float f0, float f1, float f2, int iters)
 {
     GraphKey k;
@@ -319,6 +187,10 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.opts[4] = c->staging;
     return k;
 }
+
+}  // namespace sf
+
+namespace {
 
 int create_common(sf_context **out, int N, int device, void *stream, bool own_stream, int row_lo, int row_hi, int halo)
 {
@@ -335,6 +207,7 @@ int create_common(sf_context **out, int N, int device, void *stream, bool own_st
     c->g.own_lo = row_lo; c->g.own_hi = row_hi;
     c->g.row_base = row_lo - halo;
     c->g.rows = row_hi - row_lo + 2 * halo;
+    c->halo = halo;
     c->device = device;
     DeviceGuard guard(device);
     cudaDeviceProp prop;
@@ -366,13 +239,19 @@ int sf_create_slab(sf_context **out, int N, int device, void *cuda_stream, int r
     return create_common(out, N, device, cuda_stream, false, row_lo, row_hi, halo);
 }
 
+int sf_create_slab_own_stream(sf_context **out, int N, int device, int row_lo, int row_hi, int halo)
+{
+    return create_common(out, N, device, nullptr, true, row_lo, row_hi, halo);
+}
+
 int sf_destroy(sf_context *c)
 {
     if (!c) return SF_ERR_INVALID;
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto &e : c->graphs) if (e.exec) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
-    if (c->scratch) cudaFree(c->scratch);
+    if (c->scratch && !c->scratch_in_arena) cudaFree(c->scratch);
+    slab_release(c);
     if (c->red_f) cudaFree(c->red_f);
     if (c->red_d) cudaFree(c->red_d);
     for (auto &s : c->stage) if (s) cudaFree(s);
@@ -435,6 +314,13 @@ int sf_set_stream(sf_context *c, void *cuda_stream)
     if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
     c->stream = (cudaStream_t)cuda_stream;
     c->work = c->stream;
+    return SF_OK;
+}
+
+int sf_get_stream(const sf_context *c, void **cuda_stream)
+{
+    if (!c || !cuda_stream) return SF_ERR_INVALID;
+    *cuda_stream = (void *)c->stream;
     return SF_OK;
 }
 
@@ -513,6 +399,7 @@ int sf_diffuse(sf_context *c, int b, float *x, const float *x0, float alpha, flo
     DeviceGuard guard(c->device);
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
+    if (is_linked_slab(c)) (void)arith_mode(c, alpha, beta);   // the divisor check synchronises: before anything is enqueued
     return lin_solve(c, b, x, x0, alpha, beta, iters, 0);
 }
 
@@ -522,6 +409,7 @@ int sf_advect(sf_context *c, int b, float *d, const float *d0, const float *u, c
     SF_REQUIRE(c, d && d0 && u && v && d != d0 && d != u && d != v, "advect: null fields or output aliases an input");
     SF_REQUIRE(c, b >= 0 && b <= 2, "advect: b not in 0..2");
     DeviceGuard guard(c->device);
+    if (is_linked_slab(c)) return slab_advect(c, b, d, d0, u, v, dt, true);
     SF_CUDA(c, launch_advect(c->g, b, d, d0, u, v, dt, c->stream));
     ++c->launches;
     return SF_OK;
@@ -566,6 +454,7 @@ int sf_dens_step(sf_context *c, float *x, float *x0, const float *u, const float
     DeviceGuard guard(c->device);
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
+    if (is_linked_slab(c) && (rc = slab_prevalidate(c, diff, dt))) return rc;
     const GraphKey key = make_key(c, 1, {x, x0, u, v}, diff, dt, 0.f, iters);
     return run_graphed(c, key, [&] { return enqueue_dens_step(c, x, x0, u, v, diff, dt, iters); });
 }
@@ -578,6 +467,7 @@ int sf_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float v
     DeviceGuard guard(c->device);
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
+    if (is_linked_slab(c) && (rc = slab_prevalidate(c, visc, dt))) return rc;
     const GraphKey key = make_key(c, 2, {u, v, u0, v0}, visc, dt, 0.f, iters);
     return run_graphed(c, key, [&] { return enqueue_vel_step(c, u, v, u0, v0, visc, dt, iters); });
 }
@@ -591,6 +481,7 @@ int sf_step(sf_context *c, float *dens, float *dens_prev, float *u, float *u_pre
     DeviceGuard guard(c->device);
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
+    if (is_linked_slab(c) && ((rc = slab_prevalidate(c, visc, dt)) || (rc = slab_prevalidate(c, diff, dt)))) return rc;
     const GraphKey key = make_key(c, 3, {dens, dens_prev, u, u_prev, v, v_prev}, visc, diff, dt, iters);
     return run_graphed(c, key, [&] {
         int r = enqueue_vel_step(c, u, v, u_prev, v_prev, visc, dt, iters);   // FluidSequential.c:305
@@ -746,7 +637,7 @@ int sf_jacobi_launch(sf_context *c, int b, float *xout, const float *xin, const 
         SF_REQUIRE(c, rd_lo >= c->g.row_base && rd_hi < c->g.row_base + c->g.rows, "jacobi_launch: halo rows too few for this many sweeps");
     }
     DeviceGuard guard(c->device);
-    return one_jacobi_launch(c, b, xout, xin, x0, alpha, beta, sweeps, out_lo, out_hi, 0);
+    return one_jacobi_launch(c, c->stream, b, xout, xin, x0, alpha, beta, sweeps, out_lo, out_hi, 0);
 }
 
 }  // extern "C"

@@ -133,6 +133,11 @@ struct JacobiLaunch {
     int chunk_rows;      // 0 = auto
     int zero_guess;      // xin is known to be all zeros: do not read it
     int staging;         // 0 = cp.async per lane (LDGSTS), 1 = bulk copies per warp row (cp.async.bulk / TMA unit)
+    // fused halo push (peer-memory slabs): output rows [push_lo, push_hi) are ALSO stored into xpeer, a
+    // neighbour GPU's copy of the field (peer-mapped memory) whose first stored row is global row
+    // peer_row_base -- the neighbour's ghost rows are written by the kernel that computes them
+    float *xpeer = nullptr;
+    int peer_row_base = 0, push_lo = 0, push_hi = 0;
 };
 cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_count, cudaStream_t st);
 cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStream_t st);
@@ -141,6 +146,43 @@ bool jacobi_stream_supported(const Geom &g);
 // Returns true when MODE_STRICT may be used.  Synchronises `st`; must not be called while `st`
 // is being captured (pass allow_run = false to only consult the cache).
 bool division_validated(float beta, bool allow_run, cudaStream_t st);
+
+// ---- peer-memory slabs (sf_slab.cu) ------------------------------------------------------------
+// Synchronisation words of one slab, in its own device memory; the neighbours write `inbox` through
+// peer mappings.  A neighbour barrier on channel ch: bump epoch[ch], store it into both neighbours'
+// inbox[ch][side], then spin until both of this slab's inbox[ch][*] have reached the same value.
+struct SlabFlags {
+    unsigned long long inbox[2][2];   // [channel][0 = written by the up neighbour, 1 = by the down neighbour]
+    unsigned long long epoch[2];      // barriers executed per channel (touched by this slab's barrier kernels only)
+    unsigned int error;               // sticky SF_SLAB_ERR_* bits
+    unsigned int pad;
+};
+// the two neighbours' copies of one field plus their geometry: row r of the up neighbour's array is
+// up + (r - up_row_base) * G, valid for r in [up_lo, own_lo); down likewise for r in [own_hi, dn_hi)
+struct PeerSrc {
+    const float *up = nullptr, *dn = nullptr;
+};
+struct PeerGeom {
+    int up_row_base = 0, up_lo = 0, dn_row_base = 0, dn_hi = 0;
+    unsigned int *error = nullptr;    // device word that receives SF_SLAB_ERR_REACH
+};
+cudaError_t launch_nbr_barrier(SlabFlags *me, SlabFlags *up, SlabFlags *dn, int channel, unsigned long long timeout_ns,
+                               cudaStream_t st);
+struct PushSegment {
+    const float *src;
+    float *dst;
+    size_t count;   // floats, multiple of 4, both pointers 16-byte aligned
+};
+cudaError_t launch_push_rows(const PushSegment *segs, int nsegs, cudaStream_t st);
+// advect whose gather may leave the slab: rows outside [own_lo, own_hi) are read from the neighbours
+cudaError_t launch_advect_peer(const Geom &g, int b, float *d, const float *d0, const float *u, const float *v, float dt,
+                               PeerSrc d0p, PeerGeom pg, cudaStream_t st);
+cudaError_t launch_advect_uv_peer(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt,
+                                  PeerSrc u0p, PeerSrc v0p, PeerGeom pg, cudaStream_t st);
+
+// force-load every kernel of the library (see preload_jacobi_kernels)
+void preload_jacobi_kernels();
+void preload_stage_kernels();
 
 cudaError_t launch_set_bnd(const Geom &g, int b, float *x, cudaStream_t st);
 cudaError_t launch_add_source(const Geom &g, int nfields, float *const *x, const float *const *s, float dt,

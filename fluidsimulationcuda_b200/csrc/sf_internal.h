@@ -1,0 +1,209 @@
+// Host-side internals shared by the C ABI (sf_api.cu) and the peer-memory slab driver (sf_slab.cu):
+// the context, error plumbing, launch planning and the CUDA-graph cache.  Not installed.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <initializer_list>
+#include <string>
+#include <vector>
+
+#include "../../include/stablefluids.h"
+#include "sf_common.cuh"
+
+namespace sf {
+
+struct GraphKey {   // laid out without padding so memcmp is a valid equality
+    uint64_t kind;
+    const void *p[6];
+    float f[4];
+    int iters;
+    int opts[5];
+    bool operator==(const GraphKey &o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    cudaGraph_t graph;
+    unsigned long long kernels;
+    unsigned long long last_use;
+};
+
+// Peer-memory view of a slab and its two neighbours (sf_slab.cu).  All fields of a slab live in ONE
+// device allocation (the arena: nfields caller fields, the lin_solve scratch field, then the
+// synchronisation flags), so that one pointer -- or one CUDA IPC handle -- makes a neighbour's whole
+// slab addressable: field k of a neighbour is nbr.base + k * nbr.field_bytes.
+struct SlabLink {
+    int nfields = 0;              // caller fields; index nfields is the scratch field
+    char *base = nullptr;         // local arena (nullptr: no arena, context is not peer-capable)
+    size_t field_bytes = 0;
+    SlabFlags *flags = nullptr;   // inside the arena, after the fields
+    struct Nbr {
+        bool present = false;
+        bool ipc = false;         // base came from cudaIpcOpenMemHandle (closed in sf_destroy)
+        char *base = nullptr;
+        size_t field_bytes = 0;
+        SlabFlags *flags = nullptr;
+        int row_lo = 0, row_hi = 0, row_base = 0;
+    } nbr[2];                     // 0 = up (smaller rows), 1 = down
+    cudaStream_t side = nullptr;  // high-priority stream for the boundary strips and their exchange
+    cudaEvent_t fork = nullptr, join = nullptr;
+    unsigned long long timeout_ns = 20000000000ull;   // barrier spin limit before the error bit is set
+    int world_links() const { return (nbr[0].present ? 1 : 0) + (nbr[1].present ? 1 : 0); }
+};
+
+}  // namespace sf
+
+struct sf_context {
+    sf::Geom g;
+    int device = 0;
+    int halo = 0;
+    cudaStream_t stream = nullptr;   // the stream results are ordered on (own or caller's)
+    cudaStream_t work = nullptr;     // where launches go: == stream, or cap_stream while capturing
+    cudaStream_t cap_stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int arith = SF_ARITH_STRICT;
+    int sweeps_opt = 0;
+    int use_graph = 1;
+    int force_generic = 0;
+    int chunk_rows = 0;
+    int staging = 0;
+    float *scratch = nullptr;        // lin_solve ping-pong partner (inside the arena for peer slabs)
+    bool scratch_in_arena = false;
+    float *red_f = nullptr;          // reduction outputs
+    double *red_d = nullptr;
+    unsigned long long launches = 0;
+    unsigned long long tick = 0;
+    bool capturing = false;
+    std::string err;
+    std::vector<sf::GraphEntry> graphs;
+    // sf_step_host resources
+    float *stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    sf::SlabLink link;
+};
+
+namespace sf {
+
+inline int fail(sf_context *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+#define SF_CUDA(ctx, call)                                                       \
+    do {                                                                         \
+        cudaError_t e_ = (call);                                                 \
+        if (e_ != cudaSuccess) return sf::fail(ctx, SF_ERR_CUDA, #call, e_);     \
+    } while (0)
+#define SF_REQUIRE(ctx, cond, msg)                                               \
+    do {                                                                         \
+        if (!(cond)) return sf::fail(ctx, SF_ERR_INVALID, msg);                  \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline size_t field_cells(const sf_context *c) { return (size_t)c->g.rows * (size_t)c->g.G; }
+inline bool is_full_grid(const sf_context *c) { return c->g.own_lo == 0 && c->g.own_hi == c->g.G; }
+// a slab whose neighbours are reachable through peer memory: the step drivers exchange halos themselves
+inline bool is_linked_slab(const sf_context *c) { return !is_full_grid(c) && c->link.base && c->link.world_links() > 0; }
+inline bool stream_kernels_ok(const sf_context *c) { return jacobi_stream_supported(c->g) && !c->force_generic; }
+
+// ---- implemented in sf_api.cu ----
+int ensure_scratch(sf_context *c);
+int arith_mode(const sf_context *c, float alpha, float beta);
+int default_sweeps(const sf_context *c);
+std::vector<int> plan_launches(int iters, int T);
+// rows [push_lo, push_hi) of the output are also stored into `xpeer` (a neighbour's copy of the field
+// whose first stored row is global row peer_row_base); xpeer == nullptr: no push
+struct PushSpec {
+    float *xpeer = nullptr;
+    int peer_row_base = 0, push_lo = 0, push_hi = 0;
+};
+int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const float *xin, const float *x0, float alpha,
+                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, const PushSpec &push = PushSpec());
+int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess);
+int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters);
+int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters);
+int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters);
+GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const void *> ptrs, float f0, float f1, float f2, int iters);
+
+// ---- implemented in sf_slab.cu (peer-memory slabs; every rank must issue the same call sequence) ----
+int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess);
+int slab_project(sf_context *c, float *u, float *v, float *p, float *div, int iters);
+int slab_advect(sf_context *c, int b, float *d, const float *d0, const float *u, const float *v, float dt, bool trailing_barrier);
+int slab_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters);
+int slab_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters);
+int slab_prevalidate(sf_context *c, float coef, float dt);
+void slab_release(sf_context *c);
+
+// ---- CUDA graph cache ------------------------------------------------------------------------
+template <class Body>
+int run_graphed(sf_context *c, const GraphKey &key, Body body)
+{
+    if (!c->use_graph || c->capturing) return body();
+    ++c->tick;
+    GraphEntry *seen = nullptr;
+    for (auto &e : c->graphs)
+        if (e.key == key) {
+            e.last_use = c->tick;
+            if (e.exec) {
+                SF_CUDA(c, cudaGraphLaunch(e.exec, c->stream));
+                c->launches += e.kernels;
+                return SF_OK;
+            }
+            seen = &e;
+        }
+    int rc = ensure_scratch(c);
+    if (rc) return rc;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(c->stream, &st);
+    if (st != cudaStreamCaptureStatusNone) return body();   // caller is capturing already
+    if (!seen) {
+        // First sighting of these arguments: launch directly (this also loads the kernels' modules
+        // outside of any capture); the second call with the same arguments captures the graph.
+        if (c->graphs.size() >= 16) {   // evict least recently used
+            size_t victim = 0;
+            for (size_t k = 1; k < c->graphs.size(); ++k)
+                if (c->graphs[k].last_use < c->graphs[victim].last_use) victim = k;
+            if (c->graphs[victim].exec) { cudaGraphExecDestroy(c->graphs[victim].exec); cudaGraphDestroy(c->graphs[victim].graph); }
+            c->graphs.erase(c->graphs.begin() + victim);
+        }
+        c->graphs.push_back(GraphEntry{key, nullptr, nullptr, 0, c->tick});
+        return body();
+    }
+    // Capture on a private stream: the caller's stream may be the legacy default stream, which
+    // cannot be captured.  The instantiated graph is then launched on the caller's stream.
+    if (!c->cap_stream) SF_CUDA(c, cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+    const unsigned long long before = c->launches;
+    c->capturing = true;
+    cudaError_t e = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { c->capturing = false; return fail(c, SF_ERR_CUDA, "cudaStreamBeginCapture", e); }
+    c->work = c->cap_stream;
+    rc = body();
+    c->work = c->stream;
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(c->cap_stream, &graph);
+    c->capturing = false;
+    const unsigned long long kernels = c->launches - before;
+    c->launches = before;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(c, SF_ERR_CUDA, "cudaStreamEndCapture", e);
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail(c, SF_ERR_CUDA, "cudaGraphInstantiate", e); }
+    seen->exec = exec; seen->graph = graph; seen->kernels = kernels;
+    SF_CUDA(c, cudaGraphLaunch(exec, c->stream));
+    c->launches += kernels;
+    return SF_OK;
+}
+
+}  // namespace sf

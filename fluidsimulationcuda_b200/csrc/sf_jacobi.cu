@@ -65,6 +65,8 @@ struct StreamArgs {
     float alpha, sx, sy;
     float hi_in;         // level-0 magnitudes up to this keep every numerator of the launch <= SF_DIV_HI
     DivConst div;        // beta and its reciprocals
+    float *xpeer;        // fused halo push: rows [push_lo, push_hi) also go to a neighbour GPU's array
+    int peer_row_base, push_lo, push_hi;
 };
 
 __device__ __forceinline__ void cp_async16(float4 *smem_dst, const float *gmem_src, int src_bytes)
@@ -305,12 +307,24 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     for (int k = 0; k < PREFETCH; ++k) issue(s_lo + k);
 
     float *orow = A.xout + cc;
+    // peer-memory slabs: a boundary strip stores the rows its neighbour needs straight into the
+    // neighbour's ghost rows over NVLink (plain peer stores; the exchange is part of the compute kernel)
+    auto push = [&](int a, const float4 &o) {
+        if (A.xpeer != nullptr && a >= A.push_lo && a < A.push_hi)
+            *reinterpret_cast<float4 *>(A.xpeer + cc + (size_t)(a - A.peer_row_base) * pitch) = o;
+    };
     auto emit_plain = [&](int a, const float4 &o) {
-        if (a >= a_lo && a < a_hi && st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
+        if (a >= a_lo && a < a_hi && st_ok) {
+            *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
+            push(a, o);
+        }
     };
     auto emit_walls = [&](int a, const float4 &o) {
         if (a < a_lo || a >= a_hi) return;
-        if (st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
+        if (st_ok) {
+            *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
+            push(a, o);
+        }
         if (a == 1 && A.write_top) {
             float4 w = scale4(o, A.sy);
             if (ownsL) w.x = __fmul_rn(0.5f, __fadd_rn(w.y, o.x));   // x[0][0] = .5*(x[0][1] + x[1][0])
@@ -483,6 +497,35 @@ std::map<uint32_t, bool> g_div_ok;   // beta bits -> div_const verified bit-iden
 
 }  // namespace
 
+// CUDA loads kernels lazily, and loading one while other kernels run synchronises the context.  A peer
+// slab must never hit that inside a step (its neighbour barrier kernels may be spinning on the device
+// at that moment), so every kernel a step can launch is loaded up front.
+namespace {
+template <int T, int MODE>
+void preload_T(cudaFuncAttributes &a)
+{
+    cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE, false>);
+}
+template <int MODE>
+void preload_mode()
+{
+    cudaFuncAttributes a;
+    preload_T<1, MODE>(a); preload_T<2, MODE>(a); preload_T<3, MODE>(a); preload_T<4, MODE>(a);
+    preload_T<5, MODE>(a); preload_T<6, MODE>(a); preload_T<7, MODE>(a); preload_T<8, MODE>(a);
+    cudaFuncGetAttributes(&a, jacobi_generic_kernel<MODE>);
+}
+}  // namespace
+void preload_jacobi_kernels()
+{
+    preload_mode<MODE_STRICT>(); preload_mode<MODE_PRESSURE>(); preload_mode<MODE_FAST>(); preload_mode<MODE_IEEE>();
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, jacobi_stream_kernel<5, MODE_STRICT, true>); cudaFuncGetAttributes(&a, jacobi_stream_kernel<6, MODE_STRICT, true>);
+    cudaFuncGetAttributes(&a, jacobi_stream_kernel<7, MODE_STRICT, true>); cudaFuncGetAttributes(&a, jacobi_stream_kernel<5, MODE_PRESSURE, true>);
+    cudaFuncGetAttributes(&a, jacobi_stream_kernel<6, MODE_PRESSURE, true>); cudaFuncGetAttributes(&a, jacobi_stream_kernel<7, MODE_PRESSURE, true>);
+    cudaFuncGetAttributes(&a, validate_division_kernel);
+    (void)cudaGetLastError();
+}
+
 bool jacobi_stream_supported(const Geom &g) { return (g.G % 4) == 0 && g.G >= 4; }
 
 bool division_validated(float beta, bool allow_run, cudaStream_t st)
@@ -521,6 +564,7 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     A.write_top = (L.out_lo == 0);
     A.write_bot = (L.out_hi == g.G);
     A.nbands = (g.G + VALID_W - 1) / VALID_W;
+    A.xpeer = L.xpeer; A.peer_row_base = L.peer_row_base; A.push_lo = L.push_lo; A.push_hi = L.push_hi;
     A.zero_guess = L.zero_guess;
     A.alpha = L.alpha; A.div = make_div_const(L.beta);
     {   // see row_is_big: bound on level-0 magnitudes that keeps all numerators of T sweeps in range

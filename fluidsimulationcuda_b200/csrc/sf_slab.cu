@@ -1,0 +1,497 @@
+// Peer-memory slab driver: the stable-fluids step on a row slab whose neighbours live on other GPUs
+// of the same NVLink/NVSwitch box (the reference has no multi-GPU path).
+//
+// B200-first design, not NCCL send/recv around single-GPU kernels:
+//   * every slab keeps its fields in ONE device allocation (the arena) that its two neighbours map
+//     (CUDA IPC between processes, plain peer access inside one process);
+//   * lin_solve: the two boundary strips of each temporally blocked launch run first on a
+//     high-priority side stream and store the rows the neighbour needs STRAIGHT INTO THE NEIGHBOUR'S
+//     GHOST ROWS (fused compute + halo push, jacobi_stream_kernel's `xpeer`), while the interior
+//     launch runs on the main stream;
+//   * advect: no halo exchange at all -- a back-trace that leaves the slab reads the neighbour's rows
+//     through the peer mapping (advect4_peer_kernel);
+//   * ordering between GPUs: a NEIGHBOUR BARRIER kernel (one warp): bump a local epoch, store it
+//     into both neighbours' inboxes (release, system scope), spin until both neighbours' epochs have
+//     arrived (acquire).  Epochs live in device memory, so a captured CUDA graph of the whole step
+//     replays correctly; no host thread, no NCCL call and no stream synchronisation sits inside a step.
+//   Results do not depend on the partition: every p gives the single-GPU bits (tests/test_peer_slab_gpu.py).
+//
+// Protocol (every slab issues the same sequence; channel 0 = main stream, channel 1 = side stream):
+//   exchange(fields) on main :  barrier  (all my earlier readers of my ghost rows are done, everywhere)
+//                               push kernel (my boundary rows -> neighbours' ghost rows)
+//                               barrier  (both neighbours' pushes into my ghost rows have landed)
+//   blocked launch k         :  fork side from main;
+//                               side: barrier, top strip (+push up), bottom strip (+push down), barrier
+//                               main: interior rows;   join side into main
+//   advect                   :  barrier (sources final everywhere), gather with peer loads, barrier
+//                               (nobody overwrites a source a neighbour may still be reading)
+// A barrier that waits longer than link.timeout_ns sets SF_SLAB_ERR_TIMEOUT in the slab's error word
+// and stops waiting (sticky), so a lost neighbour is an error report, never a hung GPU.
+#include <algorithm>
+
+#include "sf_internal.h"
+
+namespace sf {
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+
+// One warp; lane 0 posts to both neighbours, lanes 0 / 1 wait for the up / down neighbour.
+__global__ void nbr_barrier_kernel(SlabFlags *me, SlabFlags *up, SlabFlags *dn, int ch, unsigned long long timeout_ns)
+{
+    unsigned long long e = 0;
+    if (threadIdx.x == 0) {
+        e = me->epoch[ch] + 1;
+        me->epoch[ch] = e;
+        __threadfence_system();     // everything this stream did before the barrier is visible before the post
+        if (up) st_release_sys(&up->inbox[ch][1], e);   // I am the DOWN neighbour of `up`
+        if (dn) st_release_sys(&dn->inbox[ch][0], e);   // I am the UP neighbour of `dn`
+    }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    const bool waits = (threadIdx.x == 0 && up != nullptr) || (threadIdx.x == 1 && dn != nullptr);
+    if (waits) {
+        const unsigned long long *box = &me->inbox[ch][threadIdx.x];
+        const unsigned long long t0 = global_timer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys(box) < e) {
+            if ((++spins & 1023u) == 0) {
+                if (*(volatile unsigned int *)&me->error & 1u) break;      // a barrier already timed out: do not wait again
+                if (global_timer_ns() - t0 > timeout_ns) { atomicOr(&me->error, 1u); break; }   // SF_SLAB_ERR_TIMEOUT
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+}
+
+struct PushArgs {
+    PushSegment s[6];
+};
+__global__ void __launch_bounds__(256) push_rows_kernel(PushArgs A)
+{
+    const PushSegment seg = A.s[blockIdx.y];
+    const float4 *src = reinterpret_cast<const float4 *>(seg.src);
+    float4 *dst = reinterpret_cast<float4 *>(seg.dst);
+    const size_t n4 = seg.count / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+size_t arena_flags_offset(int nfields, size_t field_bytes) { return (((size_t)(nfields + 1) * field_bytes) + 255) / 256 * 256; }
+
+// index of a local arena field, or -1
+int field_index(const sf_context *c, const void *p)
+{
+    const SlabLink &L = c->link;
+    if (!L.base) return -1;
+    const char *q = (const char *)p;
+    if (q < L.base || q >= L.base + (size_t)(L.nfields + 1) * L.field_bytes) return -1;
+    const size_t off = (size_t)(q - L.base);
+    if (off % L.field_bytes != 0) return -1;
+    return (int)(off / L.field_bytes);
+}
+float *nbr_field(const sf_context *c, int dir, int k)
+{
+    const SlabLink::Nbr &n = c->link.nbr[dir];
+    return n.present ? reinterpret_cast<float *>(n.base + (size_t)k * n.field_bytes) : nullptr;
+}
+
+int slab_barrier(sf_context *c, cudaStream_t st, int ch)
+{
+    SlabLink &L = c->link;
+    SF_CUDA(c, launch_nbr_barrier(L.flags, L.nbr[0].present ? L.nbr[0].flags : nullptr,
+                                  L.nbr[1].present ? L.nbr[1].flags : nullptr, ch, L.timeout_ns, st));
+    ++c->launches;
+    return SF_OK;
+}
+
+struct HaloSpec {
+    const float *field;
+    int rows;
+};
+// push my first / last `rows` owned rows of every listed field into the neighbours' ghost rows
+int slab_push(sf_context *c, cudaStream_t st, std::initializer_list<HaloSpec> specs)
+{
+    PushSegment segs[6];
+    int n = 0;
+    const size_t G = (size_t)c->g.G;
+    for (const HaloSpec &h : specs) {
+        if (h.rows <= 0) continue;
+        const int k = field_index(c, h.field);
+        SF_REQUIRE(c, k >= 0, "peer slab: field is not part of this context's arena (sf_slab_field)");
+        SF_REQUIRE(c, h.rows <= c->halo && h.rows <= c->g.own_hi - c->g.own_lo, "peer slab: more halo rows requested than allocated");
+        for (int dir = 0; dir < 2; ++dir) {
+            const SlabLink::Nbr &nb = c->link.nbr[dir];
+            if (!nb.present) continue;
+            const int r0 = (dir == 0) ? c->g.own_lo : c->g.own_hi - h.rows;     // first global row that travels
+            SF_REQUIRE(c, n < 6, "peer slab: too many fields in one exchange");
+            segs[n].src = h.field + (size_t)(r0 - c->g.row_base) * G;
+            segs[n].dst = nbr_field(c, dir, k) + (size_t)(r0 - nb.row_base) * G;
+            segs[n].count = (size_t)h.rows * G;
+            ++n;
+        }
+    }
+    if (n == 0) return SF_OK;
+    SF_CUDA(c, launch_push_rows(segs, n, st));
+    ++c->launches;
+    return SF_OK;
+}
+
+int slab_exchange(sf_context *c, std::initializer_list<HaloSpec> specs)
+{
+    int rc = slab_barrier(c, c->work, 0);
+    if (rc) return rc;
+    rc = slab_push(c, c->work, specs);
+    if (rc) return rc;
+    return slab_barrier(c, c->work, 0);
+}
+
+PeerGeom peer_geom(const sf_context *c)
+{
+    PeerGeom pg;
+    const SlabLink &L = c->link;
+    pg.up_row_base = L.nbr[0].row_base; pg.up_lo = L.nbr[0].present ? L.nbr[0].row_lo : c->g.own_lo;
+    pg.dn_row_base = L.nbr[1].row_base; pg.dn_hi = L.nbr[1].present ? L.nbr[1].row_hi : c->g.own_hi;
+    pg.error = &L.flags->error;
+    return pg;
+}
+int peer_src(sf_context *c, const float *field, PeerSrc &out)
+{
+    const int k = field_index(c, field);
+    SF_REQUIRE(c, k >= 0, "peer slab: advected field is not part of this context's arena (sf_slab_field)");
+    out.up = nbr_field(c, 0, k);
+    out.dn = nbr_field(c, 1, k);
+    return SF_OK;
+}
+
+}  // namespace
+
+cudaError_t launch_nbr_barrier(SlabFlags *me, SlabFlags *up, SlabFlags *dn, int channel, unsigned long long timeout_ns,
+                               cudaStream_t st)
+{
+    nbr_barrier_kernel<<<1, 32, 0, st>>>(me, up, dn, channel, timeout_ns);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_push_rows(const PushSegment *segs, int nsegs, cudaStream_t st)
+{
+    if (nsegs < 1 || nsegs > 6) return cudaErrorInvalidValue;
+    PushArgs A;
+    size_t most = 0;
+    for (int k = 0; k < 6; ++k) {
+        A.s[k] = segs[k < nsegs ? k : 0];
+        if (k < nsegs) {
+            if (segs[k].count % 4 != 0 || (uintptr_t)segs[k].src % 16 != 0 || (uintptr_t)segs[k].dst % 16 != 0) return cudaErrorInvalidValue;
+            most = std::max(most, segs[k].count / 4);
+        }
+    }
+    unsigned blocks = (unsigned)std::min<size_t>((most + 255) / 256, 148 * 2);
+    if (blocks < 1) blocks = 1;
+    push_rows_kernel<<<dim3(blocks, nsegs), 256, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+// ---- lin_solve with fused strip pushes (replaces diffuse(), FluidSequential.c:85-104, on a slab) ----
+int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess)
+{
+    SlabLink &L = c->link;
+    SF_REQUIRE(c, stream_kernels_ok(c), "peer slab: grid width must be a multiple of 4 (streaming kernels)");
+    SF_REQUIRE(c, field_index(c, x) >= 0 && field_index(c, x0) >= 0, "peer slab: lin_solve fields must be arena fields (sf_slab_field)");
+    const int T = default_sweeps(c);
+    const std::vector<int> plan = plan_launches(iters, T);
+    const int maxT = *std::max_element(plan.begin(), plan.end());
+    const int lo = c->g.own_lo, hi = c->g.own_hi;
+    SF_REQUIRE(c, c->halo >= maxT, "peer slab: halo rows < sweeps per launch");
+    SF_REQUIRE(c, hi - lo >= 2 * maxT, "peer slab: slab thinner than two boundary strips");
+    const bool has_up = L.nbr[0].present, has_dn = L.nbr[1].present;
+
+    // ghost rows the launches read: plan[0] rows of the initial guess, maxT rows of the right-hand side
+    int rc = slab_exchange(c, {HaloSpec{x, zero_guess ? 0 : plan[0]}, HaloSpec{x0, maxT}});
+    if (rc) return rc;
+
+    float *cur = x, *nxt = c->scratch;
+    for (size_t k = 0; k < plan.size(); ++k) {
+        const int sweeps = plan[k];
+        const int strip = (k + 1 < plan.size()) ? plan[k + 1] : 1;   // after the solve: 1 row for the stencils that follow
+        const int top_hi = has_up ? lo + strip : lo;
+        const int bot_lo = has_dn ? hi - strip : hi;
+        const int zg = (zero_guess && k == 0) ? 1 : 0;
+        const int kn = field_index(c, nxt);
+        // fork: the side stream starts where the main stream is (everything this launch reads is complete)
+        SF_CUDA(c, cudaEventRecord(L.fork, c->work));
+        SF_CUDA(c, cudaStreamWaitEvent(L.side, L.fork, 0));
+        if ((rc = slab_barrier(c, L.side, 1))) return rc;            // neighbours are done reading the ghost rows of `nxt`
+        if (has_up) {
+            PushSpec ps;
+            ps.xpeer = nbr_field(c, 0, kn); ps.peer_row_base = L.nbr[0].row_base; ps.push_lo = lo; ps.push_hi = top_hi;
+            if ((rc = one_jacobi_launch(c, L.side, b, nxt, cur, x0, alpha, beta, sweeps, lo, top_hi, zg, ps))) return rc;
+        }
+        if (has_dn) {
+            PushSpec ps;
+            ps.xpeer = nbr_field(c, 1, kn); ps.peer_row_base = L.nbr[1].row_base; ps.push_lo = bot_lo; ps.push_hi = hi;
+            if ((rc = one_jacobi_launch(c, L.side, b, nxt, cur, x0, alpha, beta, sweeps, bot_lo, hi, zg, ps))) return rc;
+        }
+        if ((rc = slab_barrier(c, L.side, 1))) return rc;            // the neighbours' strips have landed in my ghost rows
+        // interior rows on the main stream, concurrently with the strips and their exchange
+        if ((rc = one_jacobi_launch(c, c->work, b, nxt, cur, x0, alpha, beta, sweeps, top_hi, bot_lo, zg))) return rc;
+        SF_CUDA(c, cudaEventRecord(L.join, L.side));
+        SF_CUDA(c, cudaStreamWaitEvent(c->work, L.join, 0));
+        std::swap(cur, nxt);
+    }
+    if (cur != x) SF_CUDA(c, cudaMemcpyAsync(x, cur, field_cells(c) * sizeof(float), cudaMemcpyDeviceToDevice, c->work));
+    return SF_OK;
+}
+
+// projection triple (FluidSequential.c:213-223): u, v must hold 1 valid ghost row on entry
+int slab_project(sf_context *c, float *u, float *v, float *p, float *div, int iters)
+{
+    SF_CUDA(c, launch_divergence(c->g, u, v, p, div, 0, c->work));   // zero guess is implicit: p is not written
+    ++c->launches;
+    int rc = slab_lin_solve(c, 0, p, div, 1.0f, 4.0f, iters, 1);
+    if (rc) return rc;
+    SF_CUDA(c, launch_last_project(c->g, u, v, p, c->work));           // p holds 1 valid ghost row after the solve
+    ++c->launches;
+    return SF_OK;
+}
+
+// advect(b, d, d0, u, v) with peer-memory gathers; d0 must be an arena field.  NF = 2 form below.
+int slab_advect(sf_context *c, int b, float *d, const float *d0, const float *u, const float *v, float dt, bool trailing_barrier)
+{
+    PeerSrc s;
+    int rc = peer_src(c, d0, s);
+    if (rc) return rc;
+    if ((rc = slab_barrier(c, c->work, 0))) return rc;     // d0 is final on both neighbours
+    SF_CUDA(c, launch_advect_peer(c->g, b, d, d0, u, v, dt, s, peer_geom(c), c->work));
+    ++c->launches;
+    if (trailing_barrier) rc = slab_barrier(c, c->work, 0);   // neighbours are done reading my d0
+    return rc;
+}
+
+int slab_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
+{
+    float *xs[2] = {u, v};
+    const float *ss[2] = {u0, v0};
+    SF_CUDA(c, launch_add_source(c->g, 2, xs, ss, dt, c->work));      // FluidSequential.c:193,197
+    ++c->launches;
+    const float fN = (float)c->g.N;
+    float alpha = dt * visc;      // :199, left to right in binary32
+    alpha = alpha * fN;
+    alpha = alpha * fN;
+    float beta = 4.0f * alpha;    // :200
+    beta = 1.0f + beta;
+    int rc = slab_lin_solve(c, 1, u0, u, alpha, beta, iters, 0);      // :201-204
+    if (rc) return rc;
+    if ((rc = slab_lin_solve(c, 2, v0, v, alpha, beta, iters, 0))) return rc;   // :209-210
+    if ((rc = slab_project(c, u0, v0, u, v, iters))) return rc;       // :213-223 (p in u, div in v)
+    // :228-237  advect(1,u,u0,u0,v0); advect(2,v,v0,u0,v0) in one pass, sources pulled from the neighbours
+    PeerSrc su, sv;
+    if ((rc = peer_src(c, u0, su)) || (rc = peer_src(c, v0, sv))) return rc;
+    if ((rc = slab_barrier(c, c->work, 0))) return rc;                 // u0, v0 final everywhere
+    SF_CUDA(c, launch_advect_uv_peer(c->g, u, v, u0, v0, dt, su, sv, peer_geom(c), c->work));
+    ++c->launches;
+    // the exchange's first barrier also tells the neighbours that this slab is done reading their u0, v0
+    if ((rc = slab_exchange(c, {HaloSpec{u, 1}, HaloSpec{v, 1}}))) return rc;
+    return slab_project(c, u, v, u0, v0, iters);                       // :238-240 (p in u0, div in v0)
+}
+
+int slab_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters)
+{
+    float *xs[1] = {x};
+    const float *ss[1] = {x0};
+    SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->work));      // :177
+    ++c->launches;
+    const float fN = (float)c->g.N;
+    float alpha = dt * diff;      // :179
+    alpha = alpha * fN;
+    alpha = alpha * fN;
+    float beta = 4.0f * alpha;    // :180
+    beta = 1.0f + beta;
+    int rc = slab_lin_solve(c, 0, x0, x, alpha, beta, iters, 0);      // :182
+    if (rc) return rc;
+    return slab_advect(c, 0, x, x0, u, v, dt, true);                   // :185
+}
+
+// The exact-division check synchronises the stream, which must not happen between two barriers of a
+// step (the neighbour may be waiting for this slab): run it before anything is enqueued.
+int slab_prevalidate(sf_context *c, float coef, float dt)
+{
+    if (c->capturing) return SF_OK;
+    const float fN = (float)c->g.N;
+    float alpha = dt * coef;
+    alpha = alpha * fN;
+    alpha = alpha * fN;
+    float beta = 4.0f * alpha;
+    beta = 1.0f + beta;
+    (void)arith_mode(c, alpha, beta);
+    return SF_OK;
+}
+
+void slab_release(sf_context *c)
+{
+    SlabLink &L = c->link;
+    for (auto &n : L.nbr) {
+        if (n.present && n.ipc && n.base) cudaIpcCloseMemHandle(n.base);
+        n = SlabLink::Nbr();
+    }
+    if (L.side) cudaStreamDestroy(L.side);
+    if (L.fork) cudaEventDestroy(L.fork);
+    if (L.join) cudaEventDestroy(L.join);
+    if (L.base) cudaFree(L.base);
+    L = SlabLink();
+}
+
+}  // namespace sf
+
+using namespace sf;
+
+// =================================================================================================
+extern "C" {
+
+int sf_slab_arena_create(sf_context *c, int nfields)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, nfields >= 1 && nfields <= 64, "slab arena: 1..64 fields");
+    SF_REQUIRE(c, !c->link.base, "slab arena: already created");
+    SF_REQUIRE(c, !c->scratch, "slab arena: create it before the first solve");
+    SF_REQUIRE(c, c->g.G % 4 == 0, "slab arena: grid width must be a multiple of 4");
+    DeviceGuard guard(c->device);
+    SlabLink &L = c->link;
+    L.nfields = nfields;
+    L.field_bytes = field_cells(c) * sizeof(float);
+    const size_t off = arena_flags_offset(nfields, L.field_bytes);
+    SF_CUDA(c, cudaMalloc(&L.base, off + 256));
+    SF_CUDA(c, cudaMemset(L.base, 0, off + 256));
+    L.flags = reinterpret_cast<SlabFlags *>(L.base + off);
+    c->scratch = reinterpret_cast<float *>(L.base + (size_t)nfields * L.field_bytes);
+    c->scratch_in_arena = true;
+    int lo_pri = 0, hi_pri = 0;
+    SF_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    SF_CUDA(c, cudaStreamCreateWithPriority(&L.side, cudaStreamNonBlocking, hi_pri));
+    SF_CUDA(c, cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
+    SF_CUDA(c, cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming));
+    {   // nothing may be loaded or allocated inside a step (see preload_jacobi_kernels)
+        cudaFuncAttributes a;
+        cudaFuncGetAttributes(&a, nbr_barrier_kernel);
+        cudaFuncGetAttributes(&a, push_rows_kernel);
+        (void)cudaGetLastError();
+        preload_jacobi_kernels();
+        preload_stage_kernels();
+    }
+    return ensure_scratch(c);
+}
+
+int sf_slab_field(sf_context *c, int k, float **dev_field)
+{
+    if (!c || !dev_field) return SF_ERR_INVALID;
+    SF_REQUIRE(c, c->link.base && k >= 0 && k < c->link.nfields, "slab field: no arena or index out of range");
+    *dev_field = reinterpret_cast<float *>(c->link.base + (size_t)k * c->link.field_bytes);
+    return SF_OK;
+}
+
+int sf_slab_ipc_handle(sf_context *c, void *handle64)
+{
+    if (!c || !handle64) return SF_ERR_INVALID;
+    SF_REQUIRE(c, c->link.base, "slab ipc handle: no arena");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    DeviceGuard guard(c->device);
+    cudaIpcMemHandle_t h;
+    SF_CUDA(c, cudaIpcGetMemHandle(&h, c->link.base));
+    std::memcpy(handle64, &h, sizeof(h));
+    return SF_OK;
+}
+
+static int connect_common(sf_context *c, int dir, char *base, bool ipc, int nbr_row_lo, int nbr_row_hi)
+{
+    SlabLink &L = c->link;
+    SlabLink::Nbr &n = L.nbr[dir];
+    n.present = true; n.ipc = ipc; n.base = base;
+    n.row_lo = nbr_row_lo; n.row_hi = nbr_row_hi; n.row_base = nbr_row_lo - c->halo;
+    n.field_bytes = (size_t)(nbr_row_hi - nbr_row_lo + 2 * c->halo) * (size_t)c->g.G * sizeof(float);
+    n.flags = reinterpret_cast<SlabFlags *>(base + arena_flags_offset(L.nfields, n.field_bytes));
+    // graphs captured before the link existed do not contain the exchanges
+    for (auto &e : c->graphs) if (e.exec) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
+    c->graphs.clear();
+    return SF_OK;
+}
+
+static int check_connect_args(sf_context *c, int dir, int nbr_row_lo, int nbr_row_hi)
+{
+    SF_REQUIRE(c, c->link.base, "slab connect: create the arena first");
+    SF_REQUIRE(c, dir == 0 || dir == 1, "slab connect: dir is 0 (up) or 1 (down)");
+    SF_REQUIRE(c, !c->link.nbr[dir].present, "slab connect: neighbour already connected");
+    if (dir == 0) SF_REQUIRE(c, nbr_row_hi == c->g.own_lo && nbr_row_lo >= 0 && nbr_row_lo < nbr_row_hi, "slab connect: up neighbour must end where this slab begins");
+    if (dir == 1) SF_REQUIRE(c, nbr_row_lo == c->g.own_hi && nbr_row_hi <= c->g.G && nbr_row_lo < nbr_row_hi, "slab connect: down neighbour must begin where this slab ends");
+    return SF_OK;
+}
+
+int sf_slab_connect_ipc(sf_context *c, int dir, const void *handle64, int nbr_row_lo, int nbr_row_hi)
+{
+    if (!c || !handle64) return SF_ERR_INVALID;
+    int rc = check_connect_args(c, dir, nbr_row_lo, nbr_row_hi);
+    if (rc) return rc;
+    DeviceGuard guard(c->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    void *p = nullptr;
+    SF_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return connect_common(c, dir, (char *)p, true, nbr_row_lo, nbr_row_hi);
+}
+
+int sf_slab_connect_local(sf_context *c, int dir, sf_context *nb)
+{
+    if (!c || !nb) return SF_ERR_INVALID;
+    SF_REQUIRE(c, nb->link.base && nb->link.nfields == c->link.nfields && nb->halo == c->halo && nb->g.G == c->g.G,
+               "slab connect: neighbour has no arena or a different layout");
+    int rc = check_connect_args(c, dir, nb->g.own_lo, nb->g.own_hi);
+    if (rc) return rc;
+    DeviceGuard guard(c->device);
+    if (nb->device != c->device) {
+        int can = 0;
+        SF_CUDA(c, cudaDeviceCanAccessPeer(&can, c->device, nb->device));
+        SF_REQUIRE(c, can, "slab connect: no peer access between the two devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+        SF_CUDA(c, e);
+    }
+    return connect_common(c, dir, nb->link.base, false, nb->g.own_lo, nb->g.own_hi);
+}
+
+int sf_slab_set_timeout_ms(sf_context *c, int ms)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, ms >= 1, "slab timeout: >= 1 ms");
+    c->link.timeout_ns = (unsigned long long)ms * 1000000ull;
+    for (auto &e : c->graphs) if (e.exec) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
+    c->graphs.clear();
+    return SF_OK;
+}
+
+int sf_slab_status(sf_context *c, unsigned int *error_bits)
+{
+    if (!c || !error_bits) return SF_ERR_INVALID;
+    SF_REQUIRE(c, c->link.base, "slab status: no arena");
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, cudaMemcpyAsync(error_bits, &c->link.flags->error, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (*error_bits & SF_SLAB_ERR_TIMEOUT) c->err = "peer slab: a neighbour barrier timed out (neighbour missing or call sequences differ)";
+    else if (*error_bits & SF_SLAB_ERR_REACH) c->err = "peer slab: an advection back-trace reached beyond the neighbouring slab";
+    return SF_OK;
+}
+
+}  // extern "C"

@@ -431,6 +431,74 @@ __global__ void __launch_bounds__(256) advect4_kernel(float *__restrict__ dA, fl
     if (NF == 2) store_row4_walls(dB, g, row, c, oB, 1.0f, -1.0f);   // b = 2
 }
 
+// ---- advect on a peer-memory slab ---------------------------------------------------------------
+// Same arithmetic; the gather's two source rows are resolved per cell: a row outside this slab's
+// owned range is read straight from the neighbour GPU that owns it (peer loads over NVLink), so the
+// advection needs no halo exchange and no bound on the back-trace other than "not beyond the
+// neighbour's slab" (which sets an error bit instead of reading out of bounds).
+struct PeerView {
+    const float *loc, *up, *dn;
+};
+__device__ __forceinline__ const float *peer_row(const PeerView &f, const Geom &g, const PeerGeom &pg, int r)
+{
+    const size_t G = (size_t)g.G;
+    if (r < g.own_lo) {
+        if (r < pg.up_lo) { atomicOr(pg.error, 2u); r = pg.up_lo; }          // SF_SLAB_ERR_REACH
+        return f.up + (size_t)(r - pg.up_row_base) * G;
+    }
+    if (r >= g.own_hi) {
+        if (r >= pg.dn_hi) { atomicOr(pg.error, 2u); r = pg.dn_hi - 1; }
+        return f.dn + (size_t)(r - pg.dn_row_base) * G;
+    }
+    return f.loc + (size_t)(r - g.row_base) * G;
+}
+template <int NF>
+__device__ __forceinline__ void advect_cell_peer(const PeerView &sA, const PeerView &sB, const Geom &g, const PeerGeom &pg,
+                                                 int row, int col, float uu, float vv, float dt0, float hiC, float &oA, float &oB)
+{
+    float px = __fsub_rn((float)col, __fmul_rn(dt0, uu));
+    float py = __fsub_rn((float)row, __fmul_rn(dt0, vv));
+    if (px < 0.5f) px = 0.5f;
+    if (px > hiC) px = hiC;
+    if (py < 0.5f) py = 0.5f;
+    if (py > hiC) py = hiC;
+    const int c0 = (int)px, r0 = (int)py;
+    const float wx1 = __fsub_rn(px, (float)c0), wx0 = __fsub_rn(1.0f, wx1);
+    const float wy1 = __fsub_rn(py, (float)r0), wy0 = __fsub_rn(1.0f, wy1);
+    {
+        const float *p0 = peer_row(sA, g, pg, r0) + c0, *p1 = peer_row(sA, g, pg, r0 + 1) + c0;
+        const float a00 = __ldg(p0), a10 = __ldg(p1), a01 = __ldg(p0 + 1), a11 = __ldg(p1 + 1);
+        oA = __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
+                       __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
+    }
+    if (NF == 2) {
+        const float *p0 = peer_row(sB, g, pg, r0) + c0, *p1 = peer_row(sB, g, pg, r0 + 1) + c0;
+        const float a00 = __ldg(p0), a10 = __ldg(p1), a01 = __ldg(p0 + 1), a11 = __ldg(p1 + 1);
+        oB = __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
+                       __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
+    }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256) advect4_peer_kernel(float *__restrict__ dA, float *__restrict__ dB, PeerView sA,
+                                                           PeerView sB, const float *__restrict__ u,
+                                                           const float *__restrict__ v, Geom g, PeerGeom pg, float dt0, int bA)
+{
+    SF_ROW4_PROLOGUE
+    (void)lane; (void)cs;
+    if (!active) return;
+    const float4 uu = __ldg(reinterpret_cast<const float4 *>(u + rowoff + c));
+    const float4 vv = __ldg(reinterpret_cast<const float4 *>(v + rowoff + c));
+    const float hiC = (float)g.N + 0.5f;
+    float4 oA = make_float4(0.f, 0.f, 0.f, 0.f), oB = oA;
+    advect_cell_peer<NF>(sA, sB, g, pg, row, c + 0, uu.x, vv.x, dt0, hiC, oA.x, oB.x);
+    advect_cell_peer<NF>(sA, sB, g, pg, row, c + 1, uu.y, vv.y, dt0, hiC, oA.y, oB.y);
+    advect_cell_peer<NF>(sA, sB, g, pg, row, c + 2, uu.z, vv.z, dt0, hiC, oA.z, oB.z);
+    advect_cell_peer<NF>(sA, sB, g, pg, row, c + 3, uu.w, vv.w, dt0, hiC, oA.w, oB.w);
+    store_row4_walls(dA, g, row, c, oA, bA == 1 ? -1.0f : 1.0f, bA == 2 ? -1.0f : 1.0f);
+    if (NF == 2) store_row4_walls(dB, g, row, c, oB, 1.0f, -1.0f);   // b = 2
+}
+
 inline bool row4_ok(const Geom &g, std::initializer_list<const void *> ptrs)
 {
     if (g.G % 4 != 0) return false;
@@ -452,6 +520,20 @@ inline int interior_row_count(const Geom &g)
 }
 
 }  // namespace
+
+void preload_stage_kernels()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, set_bnd_kernel); cudaFuncGetAttributes(&a, add_source_kernel);
+    cudaFuncGetAttributes(&a, advect_kernel<1>); cudaFuncGetAttributes(&a, advect_kernel<2>);
+    cudaFuncGetAttributes(&a, advect4_kernel<1>); cudaFuncGetAttributes(&a, advect4_kernel<2>);
+    cudaFuncGetAttributes(&a, advect4_peer_kernel<1>); cudaFuncGetAttributes(&a, advect4_peer_kernel<2>);
+    cudaFuncGetAttributes(&a, divergence_kernel); cudaFuncGetAttributes(&a, divergence4_kernel);
+    cudaFuncGetAttributes(&a, last_project_kernel); cudaFuncGetAttributes(&a, last_project4_kernel);
+    cudaFuncGetAttributes(&a, init_kernel); cudaFuncGetAttributes(&a, init4_kernel);
+    cudaFuncGetAttributes(&a, max_abs_kernel); cudaFuncGetAttributes(&a, residual_kernel);
+    (void)cudaGetLastError();
+}
 
 cudaError_t launch_set_bnd(const Geom &g, int b, float *x, cudaStream_t st)
 {
@@ -505,6 +587,32 @@ cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u
         return cudaGetLastError();
     }
     advect_kernel<2><<<cell_grid(g, block, rows), block, 0, st>>>(du, dv, u0, v0, u0, v0, g, dt0, 1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_advect_peer(const Geom &g, int b, float *d, const float *d0, const float *u, const float *v, float dt,
+                               PeerSrc d0p, PeerGeom pg, cudaStream_t st)
+{
+    const int rows = interior_row_count(g);
+    if (rows == 0) return cudaSuccess;
+    if (!row4_ok(g, {d, d0, u, v, d0p.up, d0p.dn})) return cudaErrorInvalidValue;
+    const float dt0 = dt * (float)g.N;   // FluidSequential.c:111
+    const dim3 b4(32, 8);
+    const PeerView sA{d0, d0p.up, d0p.dn};
+    advect4_peer_kernel<1><<<row4_grid(g, b4, rows), b4, 0, st>>>(d, nullptr, sA, sA, u, v, g, pg, dt0, b);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_advect_uv_peer(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt,
+                                  PeerSrc u0p, PeerSrc v0p, PeerGeom pg, cudaStream_t st)
+{
+    const int rows = interior_row_count(g);
+    if (rows == 0) return cudaSuccess;
+    if (!row4_ok(g, {du, dv, u0, v0, u0p.up, u0p.dn, v0p.up, v0p.dn})) return cudaErrorInvalidValue;
+    const float dt0 = dt * (float)g.N;
+    const dim3 b4(32, 8);
+    const PeerView sA{u0, u0p.up, u0p.dn}, sB{v0, v0p.up, v0p.dn};
+    advect4_peer_kernel<2><<<row4_grid(g, b4, rows), b4, 0, st>>>(du, dv, sA, sB, u0, v0, g, pg, dt0, 1);
     return cudaGetLastError();
 }
 

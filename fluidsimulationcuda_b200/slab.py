@@ -407,3 +407,113 @@ def run_lockstep(solvers: Sequence[SlabSolver], visc: float, diff: float, dt: fl
                 r[1].fill_(m)
         else:
             raise ValueError(kind)
+
+
+# =================================================================================================
+# Peer-memory slabs: the product path on an NVLink / NVSwitch box
+# =================================================================================================
+class PeerSlabSolver(SlabLayout):
+    """One rank's slab with its neighbours' memory mapped (CUDA IPC between processes, peer access
+    inside one process).  The whole step -- halo pushes fused into the boundary strips of every
+    temporally blocked Jacobi launch, peer-memory gathers in advect, one-warp neighbour barriers --
+    runs inside libstablefluids_b200.so and is replayed from one CUDA graph per GPU
+    (csrc/sf_slab.cu).  This class only allocates, wires the neighbours up and calls ``sf_step``;
+    torch.distributed is used once, to pass the 64-byte IPC handles around.
+
+    ``step`` is collective: every rank must call it the same number of times."""
+
+    NAMES = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
+
+    def __init__(self, N: int, rank: int, world: int, *, iters: int = 40, halo: int = 8, arithmetic: int = SF.STRICT,
+                 sweeps_per_launch: int = 8, device: Optional[int] = None, stream=None, use_graph: bool = True,
+                 timeout_ms: Optional[int] = None):
+        if world == 1:
+            halo = 0
+        SlabLayout.__init__(self, N + 2, rank, world, halo)
+        self.N, self.iters, self.names = N, iters, self.NAMES
+        if world > 1 and halo < sweeps_per_launch:
+            raise ValueError("halo must cover the temporal-blocking depth")
+        if world > 1 and self.own_rows < 2 * sweeps_per_launch:
+            raise ValueError("slab thinner than two boundary strips")
+        import torch
+        self.torch = torch
+        dev = torch.cuda.current_device() if device is None else int(device)
+        if stream is None:
+            # the context's own non-blocking stream: never the legacy default stream, and (several slabs in
+            # one process) one hardware queue per slab, so a waiting barrier kernel never sits in front of
+            # the kernel it waits for
+            self.ctx = SF.StableFluids(N, dev, row_lo=self.row_lo, row_hi=self.row_hi, halo=halo, arithmetic=arithmetic,
+                                       sweeps_per_launch=sweeps_per_launch, use_graph=use_graph, own_stream=True)
+            self.stream = self.ctx._stream
+        else:
+            self.stream = stream
+            with torch.cuda.stream(self.stream):
+                self.ctx = SF.StableFluids(N, dev, row_lo=self.row_lo, row_hi=self.row_hi, halo=halo, arithmetic=arithmetic,
+                                           sweeps_per_launch=sweeps_per_launch, use_graph=use_graph)
+        self.f = dict(zip(self.NAMES, self.ctx.arena_create(len(self.NAMES))))
+        if timeout_ms is not None:
+            self.ctx.set_slab_timeout_ms(timeout_ms)
+
+    @property
+    def launch_count(self) -> int:
+        return self.ctx.launch_count
+
+    # ---- wiring ------------------------------------------------------------------------------
+    def connect_local(self, solvers: Sequence["PeerSlabSolver"]):
+        """All ranks live in this process (`solvers[r]` is rank r)."""
+        if self.rank > 0:
+            self.ctx.connect_local(SF.SF_SLAB_UP, solvers[self.rank - 1].ctx)
+        if self.rank < self.world - 1:
+            self.ctx.connect_local(SF.SF_SLAB_DOWN, solvers[self.rank + 1].ctx)
+
+    def connect_dist(self, group=None):
+        """One process per GPU: all-gather the arenas' CUDA IPC handles and map ranks r-1 / r+1."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.ctx.ipc_handle(), group=group)
+        parts = partition_rows(self.G, self.world)
+        if self.rank > 0:
+            self.ctx.connect_ipc(SF.SF_SLAB_UP, handles[self.rank - 1], *parts[self.rank - 1])
+        if self.rank < self.world - 1:
+            self.ctx.connect_ipc(SF.SF_SLAB_DOWN, handles[self.rank + 1], *parts[self.rank + 1])
+        dist.barrier(group=group)       # every arena is mapped before anyone enqueues a push
+
+    # ---- drivers -----------------------------------------------------------------------------
+    def init_synthetic(self, seed: int):
+        with self.torch.cuda.stream(self.stream):
+            self.ctx.init_synthetic(seed, *[self.f[k] for k in self.NAMES])
+
+    def zero_sources(self):
+        """The reference loop's rule for steps >= 1 (FluidSequential.c:298-302)."""
+        with self.torch.cuda.stream(self.stream):
+            for k in ("dens_prev", "u_prev", "v_prev"):
+                self.f[k].zero_()
+
+    def step(self, seed: Optional[int], visc: float, diff: float, dt: float):
+        """One loop-body iteration (optional device-side source refresh, vel_step, dens_step)."""
+        f = self.f
+        with self.torch.cuda.stream(self.stream):
+            if seed is not None:
+                self.ctx.init_sources(seed, f["dens_prev"], f["u_prev"], f["v_prev"])
+            self.ctx.step(f["dens"], f["dens_prev"], f["u"], f["u_prev"], f["v"], f["v_prev"], visc, diff, dt, self.iters)
+
+    def status(self) -> int:
+        """Synchronise; raise if a neighbour barrier timed out or a back-trace left the neighbour's slab."""
+        bits = self.ctx.slab_status() if self.world > 1 else 0
+        if bits:
+            what = []
+            if bits & SF.SF_SLAB_ERR_TIMEOUT:
+                what.append("a neighbour barrier timed out")
+            if bits & SF.SF_SLAB_ERR_REACH:
+                what.append("an advection back-trace reached beyond the neighbouring slab")
+            raise SF.StableFluidsError("peer slab: " + "; ".join(what))
+        return bits
+
+    def check_reach(self):
+        self.status()
+
+    def close(self):
+        self.f = {}
+        self.ctx.close()

@@ -32,14 +32,18 @@ STRICT, FAST = 0, 1
 
 # every symbol include/stablefluids.h declares (tests/test_abi.py checks the library exports them)
 ABI_SYMBOLS = [
-    "sf_create", "sf_create_on_stream", "sf_create_slab", "sf_destroy", "sf_last_error_string",
-    "sf_set_option", "sf_get_option", "sf_synchronize", "sf_set_stream", "sf_launch_count", "sf_field_bytes",
+    "sf_create", "sf_create_on_stream", "sf_create_slab", "sf_create_slab_own_stream", "sf_destroy", "sf_last_error_string",
+    "sf_set_option", "sf_get_option", "sf_synchronize", "sf_set_stream", "sf_get_stream", "sf_launch_count", "sf_field_bytes",
     "sf_alloc_field", "sf_free_field", "sf_upload", "sf_download",
     "sf_set_bnd", "sf_add_source", "sf_diffuse", "sf_advect", "sf_compute_divergence_and_pressure",
     "sf_last_project", "sf_project", "sf_dens_step", "sf_vel_step", "sf_step", "sf_step_host",
     "sf_init_synthetic", "sf_init_sources", "sf_reduce_max_abs", "sf_reduce_max_abs_async", "sf_residual_l2",
     "sf_division_check", "sf_halo_rows_needed", "sf_jacobi_launch",
+    "sf_slab_arena_create", "sf_slab_field", "sf_slab_ipc_handle", "sf_slab_connect_ipc", "sf_slab_connect_local",
+    "sf_slab_set_timeout_ms", "sf_slab_status",
 ]
+SF_SLAB_UP, SF_SLAB_DOWN = 0, 1
+SF_SLAB_ERR_TIMEOUT, SF_SLAB_ERR_REACH = 1, 2
 
 _lib = None
 
@@ -62,6 +66,7 @@ def load_library() -> C.CDLL:
     L.sf_create.argtypes = [C.POINTER(vp), i, i]
     L.sf_create_on_stream.argtypes = [C.POINTER(vp), i, i, vp]
     L.sf_create_slab.argtypes = [C.POINTER(vp), i, i, vp, i, i, i]
+    L.sf_create_slab_own_stream.argtypes = [C.POINTER(vp), i, i, i, i, i]
     L.sf_destroy.argtypes = [vp]
     L.sf_last_error_string.argtypes = [vp]
     L.sf_last_error_string.restype = C.c_char_p
@@ -69,6 +74,7 @@ def load_library() -> C.CDLL:
     L.sf_get_option.argtypes = [vp, i, C.POINTER(i)]
     L.sf_synchronize.argtypes = [vp]
     L.sf_set_stream.argtypes = [vp, vp]
+    L.sf_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.sf_launch_count.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     L.sf_field_bytes.argtypes = [vp]
     L.sf_field_bytes.restype = C.c_size_t
@@ -95,11 +101,31 @@ def load_library() -> C.CDLL:
     L.sf_division_check.argtypes = [vp, f, C.POINTER(i)]
     L.sf_halo_rows_needed.argtypes = [vp, C.POINTER(i)]
     L.sf_jacobi_launch.argtypes = [vp, i, vp, vp, vp, f, f, i, i, i]
+    L.sf_slab_arena_create.argtypes = [vp, i]
+    L.sf_slab_field.argtypes = [vp, i, C.POINTER(vp)]
+    L.sf_slab_ipc_handle.argtypes = [vp, C.c_char_p]
+    L.sf_slab_connect_ipc.argtypes = [vp, i, C.c_char_p, i, i]
+    L.sf_slab_connect_local.argtypes = [vp, i, vp]
+    L.sf_slab_set_timeout_ms.argtypes = [vp, i]
+    L.sf_slab_status.argtypes = [vp, C.POINTER(C.c_uint)]
     for name in ABI_SYMBOLS:
         if name not in ("sf_last_error_string", "sf_field_bytes"):
             getattr(L, name).restype = i
     _lib = L
     return L
+
+
+class _DevicePointer:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+def _tensor_view(torch, ptr, shape, device):
+    with torch.cuda.device(device):
+        return torch.as_tensor(_DevicePointer(ptr, shape), device=f"cuda:{device}")
 
 
 class StableFluids:
@@ -109,7 +135,8 @@ class StableFluids:
     fluidsimulationcuda_b200.slab); the defaults are the whole grid."""
 
     def __init__(self, N: int, device: Optional[int] = None, *, row_lo: int = 0, row_hi: Optional[int] = None,
-                 halo: int = 0, arithmetic: int = STRICT, sweeps_per_launch: int = 0, use_graph: bool = True):
+                 halo: int = 0, arithmetic: int = STRICT, sweeps_per_launch: int = 0, use_graph: bool = True,
+                 own_stream: bool = False):
         import torch
         if not torch.cuda.is_available():
             raise StableFluidsError("no CUDA device: the stable-fluids path has no CPU fallback")
@@ -121,12 +148,21 @@ class StableFluids:
         self.row_hi = self.G if row_hi is None else int(row_hi)
         self.halo = int(halo)
         self.local_rows = self.row_hi - self.row_lo + 2 * self.halo
-        self._stream = torch.cuda.current_stream(self.device)
         h = C.c_void_p()
-        rc = self.L.sf_create_slab(C.byref(h), self.N, self.device, C.c_void_p(self._stream.cuda_stream),
-                                   self.row_lo, self.row_hi, self.halo)
-        if rc != 0:
-            raise StableFluidsError(f"sf_create_slab failed with status {rc}")
+        if own_stream:
+            # the context creates (and owns) a non-blocking stream; torch sees it as an ExternalStream
+            rc = self.L.sf_create_slab_own_stream(C.byref(h), self.N, self.device, self.row_lo, self.row_hi, self.halo)
+            if rc != 0:
+                raise StableFluidsError(f"sf_create_slab_own_stream failed with status {rc}")
+            sp = C.c_void_p()
+            self.L.sf_get_stream(h, C.byref(sp))
+            self._stream = torch.cuda.ExternalStream(sp.value, device=f"cuda:{self.device}")
+        else:
+            self._stream = torch.cuda.current_stream(self.device)
+            rc = self.L.sf_create_slab(C.byref(h), self.N, self.device, C.c_void_p(self._stream.cuda_stream),
+                                       self.row_lo, self.row_hi, self.halo)
+            if rc != 0:
+                raise StableFluidsError(f"sf_create_slab failed with status {rc}")
         self.h = h
         self.set_option(SF_OPT_ARITHMETIC, arithmetic)
         self.set_option(SF_OPT_SWEEPS_PER_LAUNCH, sweeps_per_launch)
@@ -247,6 +283,39 @@ class StableFluids:
         out = C.c_int(0)
         self._check(self.L.sf_division_check(self.h, beta, C.byref(out)))
         return bool(out.value)
+
+    # -- peer-memory slabs (include/stablefluids.h, "peer-memory slabs") -------------------------
+    def arena_create(self, nfields: int):
+        """Allocate this slab's fields in one peer-mappable device allocation; returns the fields as
+        torch tensors (views of library-owned memory, valid until close())."""
+        self._check(self.L.sf_slab_arena_create(self.h, int(nfields)))
+        out = []
+        for k in range(nfields):
+            p = C.c_void_p()
+            self._check(self.L.sf_slab_field(self.h, k, C.byref(p)))
+            out.append(_tensor_view(self.torch, p.value, (self.local_rows, self.G), self.device))
+        return out
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.L.sf_slab_ipc_handle(self.h, buf))
+        return bytes(buf.raw)
+
+    def connect_ipc(self, direction: int, handle: bytes, nbr_row_lo: int, nbr_row_hi: int):
+        assert len(handle) == 64
+        self._check(self.L.sf_slab_connect_ipc(self.h, direction, handle, nbr_row_lo, nbr_row_hi))
+
+    def connect_local(self, direction: int, neighbour: "StableFluids"):
+        self._check(self.L.sf_slab_connect_local(self.h, direction, neighbour.h))
+
+    def set_slab_timeout_ms(self, ms: int):
+        self._check(self.L.sf_slab_set_timeout_ms(self.h, int(ms)))
+
+    def slab_status(self) -> int:
+        """Synchronise and return the sticky device-side error bits (0 = fine)."""
+        bits = C.c_uint(0)
+        self._check(self.L.sf_slab_status(self.h, C.byref(bits)))
+        return int(bits.value)
 
     def jacobi_launch(self, b, xout, xin, x0, alpha, beta, sweeps, out_lo=-1, out_hi=-1):
         self._check(self.L.sf_jacobi_launch(self.h, b, self._p(xout), self._p(xin), self._p(x0), alpha, beta,

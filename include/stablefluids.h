@@ -84,6 +84,8 @@ int sf_create_on_stream(sf_context **out, int N, int device, void *cuda_stream);
  * The caller fills the halo rows (neighbour exchange) before each call that reads them; see
  * sf_halo_rows_needed.  row_lo = 0, row_hi = N+2, halo = 0 is the single-GPU layout. */
 int sf_create_slab(sf_context **out, int N, int device, void *cuda_stream, int row_lo, int row_hi, int halo);
+/* Same, on a non-blocking stream the context creates and owns (see sf_get_stream). */
+int sf_create_slab_own_stream(sf_context **out, int N, int device, int row_lo, int row_hi, int halo);
 int sf_destroy(sf_context *ctx);
 const char *sf_last_error_string(const sf_context *ctx);
 int sf_set_option(sf_context *ctx, int option, int value);
@@ -92,6 +94,8 @@ int sf_synchronize(sf_context *ctx);
 /* Re-target the context to another CUDA stream (all later calls are ordered on it).  Captured
  * graphs are dropped, since a graph launch is bound to the stream it is replayed on only. */
 int sf_set_stream(sf_context *ctx, void *cuda_stream);
+/* The CUDA stream (cudaStream_t as void*) the context orders its work on. */
+int sf_get_stream(const sf_context *ctx, void **cuda_stream);
 /* Number of kernels this context has launched (graph replays count their kernel nodes). */
 int sf_launch_count(const sf_context *ctx, unsigned long long *count);
 size_t sf_field_bytes(const sf_context *ctx);      /* bytes of one (local) field */
@@ -167,6 +171,40 @@ int sf_halo_rows_needed(const sf_context *ctx, int *rows);
  * Building block for halo-exchange overlap: boundary strips first, interior while halos fly. */
 int sf_jacobi_launch(sf_context *ctx, int b, float *xout, const float *xin, const float *x0, float alpha, float beta,
                      int sweeps, int out_lo, int out_hi);
+
+/* ---- peer-memory slabs: the multi-GPU path (the reference is single-GPU) -------
+ * A slab context whose neighbours' memory is mapped (NVLink / NVSwitch peer access) runs the SAME entry
+ * points -- sf_step, sf_vel_step, sf_dens_step, sf_diffuse, sf_project, sf_advect -- and performs the
+ * halo traffic itself, on the device: boundary strips of every temporally blocked Jacobi launch store
+ * their rows straight into the neighbour's ghost rows, advect reads out-of-slab rows through the peer
+ * mapping, and GPUs order themselves with one-warp neighbour-barrier kernels (no host thread, no NCCL
+ * call and no stream synchronisation inside a step; a whole step is one CUDA-graph replay per GPU).
+ * These calls are COLLECTIVE over the connected slabs: every slab must issue the same sequence.
+ * Results are bit-identical to the single-GPU path for any partition.
+ *
+ * Set-up, per slab context (created with sf_create_slab, halo >= sweeps per launch, (N+2) % 4 == 0):
+ *   sf_slab_arena_create(ctx, nfields)      one device allocation holding nfields fields (zeroed), the
+ *                                           lin_solve scratch and the synchronisation words;
+ *   sf_slab_field(ctx, k, &ptr)             field k of the arena (pass these to the entry points);
+ *   sf_slab_ipc_handle / sf_slab_connect_ipc    one process per GPU: exchange the 64-byte CUDA IPC
+ *                                           handle of the arena with ranks r-1 / r+1 (any transport)
+ *   sf_slab_connect_local                   several slabs in one process (peer access is enabled). */
+enum { SF_SLAB_UP = 0, SF_SLAB_DOWN = 1 };
+enum { SF_SLAB_ERR_TIMEOUT = 1, SF_SLAB_ERR_REACH = 2 };
+int sf_slab_arena_create(sf_context *ctx, int nfields);
+int sf_slab_field(sf_context *ctx, int k, float **dev_field);
+int sf_slab_ipc_handle(sf_context *ctx, void *handle64);
+/* dir = SF_SLAB_UP: the slab owning the rows just above (smaller row numbers); the neighbour owns
+ * global rows [nbr_row_lo, nbr_row_hi) and was created with the same N, halo and nfields. */
+int sf_slab_connect_ipc(sf_context *ctx, int dir, const void *handle64, int nbr_row_lo, int nbr_row_hi);
+int sf_slab_connect_local(sf_context *ctx, int dir, sf_context *neighbour);
+/* A neighbour barrier that waits longer than this sets SF_SLAB_ERR_TIMEOUT and stops waiting
+ * (default 20 s): a missing neighbour is an error report, never a hung GPU. */
+int sf_slab_set_timeout_ms(sf_context *ctx, int milliseconds);
+/* Synchronises the context and returns the sticky device-side error bits: SF_SLAB_ERR_TIMEOUT, or
+ * SF_SLAB_ERR_REACH when an advection back-trace left the neighbouring slab (|dt*N*v| larger than a
+ * whole slab: results of that step are invalid). */
+int sf_slab_status(sf_context *ctx, unsigned int *error_bits);
 
 #ifdef __cplusplus
 }

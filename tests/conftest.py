@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# Several emulated slabs in one process wait for each other ON THE DEVICE (tests/test_peer_slab_gpu.py):
+# give every stream its own hardware queue so that no waiting kernel sits in front of the kernel it waits for.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

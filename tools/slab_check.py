@@ -3,7 +3,8 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
-from fluidsimulationcuda_b200.slab import SlabSolver, TorchDistComm
+from fluidsimulationcuda_b200.slab import SlabSolver, TorchDistComm, PeerSlabSolver
+MODE = os.environ.get("SF_SLAB_COMM", "peer")     # peer = device-side peer-memory driver, nccl = NCCL send/recv driver
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
@@ -11,7 +12,11 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 N = G - 2
-s = SlabSolver(N, rank, world, iters=K, comm=TorchDistComm())
+if MODE == "peer":
+    s = PeerSlabSolver(N, rank, world, iters=K)
+    s.connect_dist()
+else:
+    s = SlabSolver(N, rank, world, iters=K, comm=TorchDistComm())
 s.init_synthetic(3)
 for st in range(steps):
     if st > 0:
@@ -32,7 +37,7 @@ for k in s.names:
             o = Oracle(threads=True); w = o.init_synthetic(N, 3); o.run_steps(N, steps, w, 0.0025, 0.1, 0.016, K)
         same = np.array_equal(got.view(np.uint32), w[k].view(np.uint32))
         ok &= same
-        print(f"world={world} G={G} K={K} steps={steps} field {k}: {'bit-identical' if same else 'MISMATCH'}", flush=True)
+        print(f"[{MODE}] world={world} G={G} K={K} steps={steps} field {k}: {'bit-identical' if same else 'MISMATCH'}", flush=True)
 if rank == 0:
     print("SLAB CHECK", "PASSED" if ok else "FAILED", flush=True)
 dist.barrier(); dist.destroy_process_group()
