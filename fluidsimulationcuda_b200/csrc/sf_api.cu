@@ -59,7 +59,7 @@ std::vector<int> plan_launches(int iters, int T)
 }
 
 int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const float *xin, const float *x0, float alpha,
-                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, const PushSpec &push)
+                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, int strip_rows)
 {
     JacobiLaunch L;
     L.xin = xin; L.rhs = x0; L.xout = xout;
@@ -69,12 +69,17 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
     L.chunk_rows = c->chunk_rows;
     L.zero_guess = zero_guess;
     L.staging = c->staging;
-    L.xpeer = push.xpeer; L.peer_row_base = push.peer_row_base; L.push_lo = push.push_lo; L.push_hi = push.push_hi;
+    if (strip_rows > 0) {
+        L.strips = slab_strip_args(c, xout, strip_rows);
+        SF_REQUIRE(c, L.strips != nullptr, "peer slab: output field is not an arena field or strip too high");
+        L.strip_rows[0] = c->link.nbr[0].present ? strip_rows : 0;
+        L.strip_rows[1] = c->link.nbr[1].present ? strip_rows : 0;
+    }
     if (stream_kernels_ok(c)) {
         SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, st));
     } else {
         SF_REQUIRE(c, sweeps == 1, "generic Jacobi kernel does one sweep per launch");
-        SF_REQUIRE(c, push.xpeer == nullptr, "generic Jacobi kernel cannot push rows to a neighbour");
+        SF_REQUIRE(c, strip_rows == 0, "generic Jacobi kernel has no fused strip exchange");
         if (zero_guess) {
             // generic kernel always reads xin
             SF_CUDA(c, cudaMemsetAsync(const_cast<float *>(xin), 0, field_cells(c) * sizeof(float), st));

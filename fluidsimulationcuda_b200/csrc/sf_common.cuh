@@ -121,6 +121,45 @@ __host__ __device__ __forceinline__ uint32_t hash100(uint64_t seed, uint64_t fie
     return (uint32_t)(((uint64_t)h * 100ull) >> 32);
 }
 
+// ---- peer-memory slabs (sf_slab.cu) ------------------------------------------------------------
+// Synchronisation words of one slab, in its own device memory; the neighbours write the inboxes
+// through peer mappings.
+//  * neighbour barrier on channel ch (nbr_barrier_kernel): bump epoch[ch], store it into both
+//    neighbours' inbox[ch][side], spin until both of this slab's inbox[ch][*] have reached it;
+//  * fused strip exchange (jacobi_stream_kernel): the boundary-strip warps of launch number k on side d
+//    first wait until strip_inbox[d] >= k (the neighbour's k-th strip launch has stored its rows into
+//    my ghost rows and is done reading its own), store their output rows into the neighbour's ghost
+//    rows as they produce them, and the last strip warp to finish posts k+1 to the neighbour.
+struct SlabFlags {
+    unsigned long long inbox[2][2];       // [channel][0 = written by the up neighbour, 1 = by the down neighbour]
+    unsigned long long epoch[2];          // barriers executed per channel (touched by this slab's barrier kernels only)
+    unsigned long long strip_inbox[2];    // [side] strip launches the neighbour on that side has completed
+    unsigned long long strip_seq[2];      // [side] strip launches this slab has completed
+    unsigned long long strip_arrive[2];   // [side] strip warps finished, over all launches
+    unsigned int error;                   // sticky SF_SLAB_ERR_* bits
+    unsigned int pad;
+};
+// One side of a blocked Jacobi launch on a peer-memory slab: the `rows` owned rows next to the
+// neighbour are produced by dedicated warps of the same kernel (scheduled first) that exchange them.
+struct StripPort {
+    int rows = 0;                              // strip height; 0 = no neighbour on this side
+    float *xpeer = nullptr;                    // the neighbour's copy of the output field (peer-mapped)
+    int peer_row_base = 0;                     // global row of the first row stored in xpeer
+    unsigned long long *inbox = nullptr;       // local strip_inbox[side]
+    unsigned long long *seq = nullptr;         // local strip_seq[side]
+    unsigned long long *arrive = nullptr;      // local strip_arrive[side]
+    unsigned long long *nbr_inbox = nullptr;   // neighbour's strip_inbox[other side] (peer-mapped)
+};
+// Everything the strip warps of one launch need, resident in DEVICE memory (one entry per output field
+// and strip height, written when the neighbours are connected): the kernel receives a pointer, so the
+// kernel parameter block of the single-GPU launches keeps its size.
+struct StripArgs {
+    int o_lo = 0, o_hi = 0;                    // all output rows of the launch (the slab's owned rows)
+    StripPort port[2];                         // [0] side facing the up neighbour, [1] the down neighbour
+    unsigned int *error = nullptr;             // device word for SF_SLAB_ERR_TIMEOUT
+    unsigned long long timeout_ns = 0;
+};
+
 // ---- launch wrappers implemented in the .cu files (all enqueue on `st`, return cudaError_t) ----
 struct JacobiLaunch {
     const float *xin, *rhs;
@@ -133,11 +172,10 @@ struct JacobiLaunch {
     int chunk_rows;      // 0 = auto
     int zero_guess;      // xin is known to be all zeros: do not read it
     int staging;         // 0 = cp.async per lane (LDGSTS), 1 = bulk copies per warp row (cp.async.bulk / TMA unit)
-    // fused halo push (peer-memory slabs): output rows [push_lo, push_hi) are ALSO stored into xpeer, a
-    // neighbour GPU's copy of the field (peer-mapped memory) whose first stored row is global row
-    // peer_row_base -- the neighbour's ghost rows are written by the kernel that computes them
-    float *xpeer = nullptr;
-    int peer_row_base = 0, push_lo = 0, push_hi = 0;
+    // Fused halo exchange (peer-memory slabs, sf_slab.cu): device-resident StripArgs of this launch and,
+    // for the host-side launch geometry, the strip heights it holds (0 = no strip on that side)
+    const StripArgs *strips = nullptr;
+    int strip_rows[2] = {0, 0};
 };
 cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_count, cudaStream_t st);
 cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStream_t st);
@@ -147,16 +185,6 @@ bool jacobi_stream_supported(const Geom &g);
 // is being captured (pass allow_run = false to only consult the cache).
 bool division_validated(float beta, bool allow_run, cudaStream_t st);
 
-// ---- peer-memory slabs (sf_slab.cu) ------------------------------------------------------------
-// Synchronisation words of one slab, in its own device memory; the neighbours write `inbox` through
-// peer mappings.  A neighbour barrier on channel ch: bump epoch[ch], store it into both neighbours'
-// inbox[ch][side], then spin until both of this slab's inbox[ch][*] have reached the same value.
-struct SlabFlags {
-    unsigned long long inbox[2][2];   // [channel][0 = written by the up neighbour, 1 = by the down neighbour]
-    unsigned long long epoch[2];      // barriers executed per channel (touched by this slab's barrier kernels only)
-    unsigned int error;               // sticky SF_SLAB_ERR_* bits
-    unsigned int pad;
-};
 // the two neighbours' copies of one field plus their geometry: row r of the up neighbour's array is
 // up + (r - up_row_base) * G, valid for r in [up_lo, own_lo); down likewise for r in [own_hi, dn_hi)
 struct PeerSrc {

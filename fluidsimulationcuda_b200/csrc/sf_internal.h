@@ -46,9 +46,8 @@ struct SlabLink {
         SlabFlags *flags = nullptr;
         int row_lo = 0, row_hi = 0, row_base = 0;
     } nbr[2];                     // 0 = up (smaller rows), 1 = down
-    cudaStream_t side = nullptr;  // high-priority stream for the boundary strips and their exchange
-    cudaEvent_t fork = nullptr, join = nullptr;
     unsigned long long timeout_ns = 20000000000ull;   // barrier spin limit before the error bit is set
+    StripArgs *strip_table = nullptr;   // device: entry [field * 9 + rows] = StripArgs of a launch writing `field`
     int world_links() const { return (nbr[0].present ? 1 : 0) + (nbr[1].present ? 1 : 0); }
 };
 
@@ -122,14 +121,10 @@ int ensure_scratch(sf_context *c);
 int arith_mode(const sf_context *c, float alpha, float beta);
 int default_sweeps(const sf_context *c);
 std::vector<int> plan_launches(int iters, int T);
-// rows [push_lo, push_hi) of the output are also stored into `xpeer` (a neighbour's copy of the field
-// whose first stored row is global row peer_row_base); xpeer == nullptr: no push
-struct PushSpec {
-    float *xpeer = nullptr;
-    int peer_row_base = 0, push_lo = 0, push_hi = 0;
-};
+// strip_rows > 0 (peer-memory slabs): the launch exchanges boundary strips of that height with the
+// neighbours (fused into the kernel; see StripArgs in sf_common.cuh); xout must be an arena field
 int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const float *xin, const float *x0, float alpha,
-                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, const PushSpec &push = PushSpec());
+                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, int strip_rows = 0);
 int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess);
 int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters);
 int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters);
@@ -144,6 +139,7 @@ int slab_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float
 int slab_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters);
 int slab_prevalidate(sf_context *c, float coef, float dt);
 void slab_release(sf_context *c);
+const StripArgs *slab_strip_args(const sf_context *c, const float *xout, int rows);   // device pointer, or nullptr
 
 // ---- CUDA graph cache ------------------------------------------------------------------------
 template <class Body>

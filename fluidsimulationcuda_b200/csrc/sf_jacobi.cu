@@ -65,9 +65,61 @@ struct StreamArgs {
     float alpha, sx, sy;
     float hi_in;         // level-0 magnitudes up to this keep every numerator of the launch <= SF_DIV_HI
     DivConst div;        // beta and its reciprocals
-    float *xpeer;        // fused halo push: rows [push_lo, push_hi) also go to a neighbour GPU's array
-    int peer_row_base, push_lo, push_hi;
+    const StripArgs *strips;   // peer-memory slabs: the fused exchange of the top / bottom strip (device memory)
 };
+
+// ---- fused strip exchange (peer-memory slabs) -----------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+// A strip warp of launch number k (= strip launches this side has completed) may read its ghost rows
+// and overwrite the neighbour's once the neighbour has completed k strip launches of its own.
+__device__ __forceinline__ void strip_wait(const unsigned long long *seq, const unsigned long long *inbox, unsigned int *error,
+                                        unsigned long long timeout_ns, int lane)
+{
+    if (lane == 0) {
+        const unsigned long long k = *(const volatile unsigned long long *)seq;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys_u64(inbox) < k) {
+            if ((++spins & 255u) == 0) {
+                if (*(volatile unsigned int *)error & 1u) break;
+                if (globaltimer_ns() - t0 > timeout_ns) { atomicOr(error, 1u); break; }   // SF_SLAB_ERR_TIMEOUT
+            }
+            __nanosleep(32);
+        }
+    }
+    __syncwarp();
+}
+// Every strip warp publishes its peer stores; the last one of the launch posts the new count to the neighbour.
+__device__ __forceinline__ void strip_post(unsigned long long *arrive, unsigned long long *seq, unsigned long long *nbr_inbox,
+                                        int warps_per_launch, int lane)
+{
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned long long n = atomicAdd(arrive, 1ull) + 1ull;
+        if (n % (unsigned long long)warps_per_launch == 0) {
+            const unsigned long long k1 = n / (unsigned long long)warps_per_launch;
+            *(volatile unsigned long long *)seq = k1;
+            __threadfence_system();
+            st_release_sys_u64(nbr_inbox, k1);
+        }
+    }
+}
 
 __device__ __forceinline__ void cp_async16(float4 *smem_dst, const float *gmem_src, int src_bytes)
 {
@@ -196,17 +248,47 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
 // TMA = false: rows are staged with per-lane cp.async (LDGSTS.128).  TMA = true: one elected lane
 // issues a 1-D bulk copy (cp.async.bulk -> UBLKCP) of the warp's whole 512-byte row piece per field,
 // completing on a per-slot mbarrier that all lanes wait on (SF_OPT_STAGING; measured in DESIGN.md).
-template <int T, int MODE, bool TMA>
+// VAR = 2: cp.async staging plus the fused strip exchange of peer-memory slabs (own instantiation, so
+// that the single-GPU kernels carry none of it).
+template <int T, int MODE, int VAR>
 __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
 {
+    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2);
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk
-    const int item = blockIdx.x * WPC + warp;
-    if (item >= A.nbands * A.nchunks) return;
-    const int band = item % A.nbands, chunk = item / A.nbands;
-    const int a_lo = A.a_lo + chunk * A.chunk_rows;
-    const int a_hi = min(a_lo + A.chunk_rows, A.a_hi);
+    // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.
+    // Peer-memory slabs: the first items are the boundary strips (one warp per band and side), so they
+    // are scheduled first and their rows travel while the interior items compute.
+    int band_, a_lo_, a_hi_;
+    bool is_strip_ = false, is_top_ = false;
+    if constexpr (STRIPS) {
+        const StripArgs *S = A.strips;
+        const int item0 = blockIdx.x * WPC + warp;
+        const int rows_top = S->port[0].rows, rows_bot = S->port[1].rows;
+        const int n_top = rows_top > 0 ? A.nbands : 0, n_bot = rows_bot > 0 ? A.nbands : 0;
+        is_strip_ = item0 < n_top + n_bot; is_top_ = item0 < n_top;
+        if (is_strip_) {
+            const StripPort *P = &S->port[is_top_ ? 0 : 1];
+            strip_wait(P->seq, P->inbox, S->error, S->timeout_ns, lane);
+            band_ = is_top_ ? item0 : item0 - n_top;
+            a_lo_ = is_top_ ? S->o_lo : S->o_hi - rows_bot;
+            a_hi_ = is_top_ ? S->o_lo + rows_top : S->o_hi;
+        } else {
+            const int item = item0 - (n_top + n_bot);
+            if (item >= A.nbands * A.nchunks) return;
+            band_ = item % A.nbands;
+            a_lo_ = A.a_lo + (item / A.nbands) * A.chunk_rows;
+            a_hi_ = min(a_lo_ + A.chunk_rows, A.a_hi);
+        }
+    } else {
+        const int item = blockIdx.x * WPC + warp;
+        if (item >= A.nbands * A.nchunks) return;
+        band_ = item % A.nbands;
+        a_lo_ = A.a_lo + (item / A.nbands) * A.chunk_rows;
+        a_hi_ = min(a_lo_ + A.chunk_rows, A.a_hi);
+    }
+    const int band = band_, a_lo = a_lo_, a_hi = a_hi_;
+    const bool is_strip = is_strip_, is_top = is_top_;
     if (a_lo >= a_hi) return;
 
     const int c = band * VALID_W - HALO_X + 4 * lane;     // first of this lane's 4 columns
@@ -310,8 +392,12 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     // peer-memory slabs: a boundary strip stores the rows its neighbour needs straight into the
     // neighbour's ghost rows over NVLink (plain peer stores; the exchange is part of the compute kernel)
     auto push = [&](int a, const float4 &o) {
-        if (A.xpeer != nullptr && a >= A.push_lo && a < A.push_hi)
-            *reinterpret_cast<float4 *>(A.xpeer + cc + (size_t)(a - A.peer_row_base) * pitch) = o;
+        if constexpr (STRIPS) {
+            if (is_strip) {   // the port is re-read per row (cached) rather than held in registers across the hot loop
+                const StripPort *P = &A.strips->port[is_top ? 0 : 1];
+                *reinterpret_cast<float4 *>(P->xpeer + cc + (ptrdiff_t)(a - P->peer_row_base) * (ptrdiff_t)pitch) = o;
+            }
+        }
     };
     auto emit_plain = [&](int a, const float4 &o) {
         if (a >= a_lo && a < a_hi && st_ok) {
@@ -404,6 +490,15 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
         general_tick(s, fetch(s));
         ++s;
     }
+    if constexpr (STRIPS) {   // strip warps: publish the rows stored into the neighbour's ghost rows
+        const StripArgs *S = A.strips;
+        const int it = blockIdx.x * WPC + warp;
+        const int n_top = S->port[0].rows > 0 ? A.nbands : 0, n_bot = S->port[1].rows > 0 ? A.nbands : 0;
+        if (it < n_top + n_bot) {
+            const StripPort *P = &S->port[it < n_top ? 0 : 1];
+            strip_post(P->arrive, P->seq, P->nbr_inbox, A.nbands, lane);
+        }
+    }
     if (TMA) {   // drain: rows issued beyond the last one consumed must land before the CTA's smem is released
         for (int row = s_hi + 1; row <= min(s_hi + PREFETCH + 2, load_hi); ++row)
             mbar_wait(bars + (row & (RING_X - 1)), (unsigned)((row - s_lo) >> 3) & 1u);
@@ -465,14 +560,25 @@ cudaError_t launch_stream_T(const StreamArgs &A, dim3 grid, size_t smem, bool tm
         const size_t smem_tma = smem + (size_t)WPC * RING_X * sizeof(uint64_t);
         static bool configured = false;
         if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(jacobi_stream_kernel<TT, MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+            cudaError_t e = cudaFuncSetAttribute(jacobi_stream_kernel<TT, MM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
             if (e != cudaSuccess) return e;
             configured = true;
         }
-        jacobi_stream_kernel<TT, MM, true><<<grid, WPC * 32, smem_tma, st>>>(A);
+        jacobi_stream_kernel<TT, MM, 1><<<grid, WPC * 32, smem_tma, st>>>(A);
         return cudaGetLastError();
     }
-    jacobi_stream_kernel<T, MODE, false><<<grid, WPC * 32, smem, st>>>(A);
+    if (A.strips != nullptr) {
+        // the peer-slab variant is built for the arithmetic modes a step uses
+        if (MODE == MODE_FAST || MODE == MODE_IEEE) {
+            constexpr int MM = (MODE == MODE_FAST || MODE == MODE_IEEE) ? MODE_IEEE : MODE;
+            if (MODE == MODE_FAST) return cudaErrorNotSupported;
+            jacobi_stream_kernel<T, MM, 2><<<grid, WPC * 32, smem, st>>>(A);
+        } else {
+            jacobi_stream_kernel<T, MODE, 2><<<grid, WPC * 32, smem, st>>>(A);
+        }
+        return cudaGetLastError();
+    }
+    jacobi_stream_kernel<T, MODE, 0><<<grid, WPC * 32, smem, st>>>(A);
     return cudaGetLastError();
 }
 
@@ -504,7 +610,8 @@ namespace {
 template <int T, int MODE>
 void preload_T(cudaFuncAttributes &a)
 {
-    cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE, false>);
+    cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE, 0>);
+    if (MODE != MODE_FAST) cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE == MODE_FAST ? MODE_IEEE : MODE, 2>);
 }
 template <int MODE>
 void preload_mode()
@@ -519,9 +626,9 @@ void preload_jacobi_kernels()
 {
     preload_mode<MODE_STRICT>(); preload_mode<MODE_PRESSURE>(); preload_mode<MODE_FAST>(); preload_mode<MODE_IEEE>();
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, jacobi_stream_kernel<5, MODE_STRICT, true>); cudaFuncGetAttributes(&a, jacobi_stream_kernel<6, MODE_STRICT, true>);
-    cudaFuncGetAttributes(&a, jacobi_stream_kernel<7, MODE_STRICT, true>); cudaFuncGetAttributes(&a, jacobi_stream_kernel<5, MODE_PRESSURE, true>);
-    cudaFuncGetAttributes(&a, jacobi_stream_kernel<6, MODE_PRESSURE, true>); cudaFuncGetAttributes(&a, jacobi_stream_kernel<7, MODE_PRESSURE, true>);
+    cudaFuncGetAttributes(&a, jacobi_stream_kernel<5, MODE_STRICT, 1>); cudaFuncGetAttributes(&a, jacobi_stream_kernel<6, MODE_STRICT, 1>);
+    cudaFuncGetAttributes(&a, jacobi_stream_kernel<7, MODE_STRICT, 1>); cudaFuncGetAttributes(&a, jacobi_stream_kernel<5, MODE_PRESSURE, 1>);
+    cudaFuncGetAttributes(&a, jacobi_stream_kernel<6, MODE_PRESSURE, 1>); cudaFuncGetAttributes(&a, jacobi_stream_kernel<7, MODE_PRESSURE, 1>);
     cudaFuncGetAttributes(&a, validate_division_kernel);
     (void)cudaGetLastError();
 }
@@ -559,12 +666,16 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     StreamArgs A;
     A.xin = L.xin; A.rhs = L.rhs; A.xout = L.xout;
     A.G = g.G; A.N = g.N; A.row_base = g.row_base;
-    A.a_lo = max(L.out_lo, 1);
-    A.a_hi = min(L.out_hi, g.N + 1);
+    const int st_top = L.strips ? L.strip_rows[0] : 0, st_bot = L.strips ? L.strip_rows[1] : 0;
+    A.strips = (st_top > 0 || st_bot > 0) ? L.strips : nullptr;
+    if (st_top < 0 || st_bot < 0 || st_top + st_bot > L.out_hi - L.out_lo) return cudaErrorInvalidValue;
+    if ((st_top > 0 && L.out_lo < 1) || (st_bot > 0 && L.out_hi > g.N + 1)) return cudaErrorInvalidValue;   // a strip faces a neighbour, never a wall
+    // interior segment: the output rows between the strips
+    A.a_lo = max(L.out_lo + st_top, 1);
+    A.a_hi = min(L.out_hi - st_bot, g.N + 1);
     A.write_top = (L.out_lo == 0);
     A.write_bot = (L.out_hi == g.G);
     A.nbands = (g.G + VALID_W - 1) / VALID_W;
-    A.xpeer = L.xpeer; A.peer_row_base = L.peer_row_base; A.push_lo = L.push_lo; A.push_hi = L.push_hi;
     A.zero_guess = L.zero_guess;
     A.alpha = L.alpha; A.div = make_div_const(L.beta);
     {   // see row_is_big: bound on level-0 magnitudes that keeps all numerators of T sweeps in range
@@ -577,8 +688,9 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     }
     A.sx = (L.b == 1) ? -1.0f : 1.0f;
     A.sy = (L.b == 2) ? -1.0f : 1.0f;
+    const int n_strip_items = (st_top > 0 ? A.nbands : 0) + (st_bot > 0 ? A.nbands : 0);
     const int rows = A.a_hi - A.a_lo;
-    if (rows <= 0) return cudaSuccess;
+    if (rows <= 0 && n_strip_items == 0) return cudaSuccess;
     int chunk = L.chunk_rows;
     if (chunk <= 0) {
         // One work item (band x chunk) per resident warp (12 or 16 warps per SM).  All items cost about
@@ -589,14 +701,14 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
         const int slots = sm_count * (heavy ? 3 : 4) * WPC;
         int want_chunks = slots / A.nbands;
         if (want_chunks < 1) want_chunks = 1;
-        chunk = (rows + want_chunks - 1) / want_chunks;
+        chunk = (max(rows, 1) + want_chunks - 1) / want_chunks;
         const int min_chunk = 2 * L.sweeps > 8 ? 2 * L.sweeps : 8;
         if (chunk < min_chunk) chunk = min_chunk;
     }
-    if (chunk > rows) chunk = rows;
+    if (chunk > rows) chunk = max(rows, 1);
     A.chunk_rows = chunk;
-    A.nchunks = (rows + chunk - 1) / chunk;
-    const int items = A.nbands * A.nchunks;
+    A.nchunks = rows > 0 ? (rows + chunk - 1) / chunk : 0;
+    const int items = n_strip_items + A.nbands * A.nchunks;
     dim3 grid((items + WPC - 1) / WPC);
     const size_t smem = (size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4);
     switch (L.mode) {

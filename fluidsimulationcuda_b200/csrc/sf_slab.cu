@@ -4,29 +4,28 @@
 // B200-first design, not NCCL send/recv around single-GPU kernels:
 //   * every slab keeps its fields in ONE device allocation (the arena) that its two neighbours map
 //     (CUDA IPC between processes, plain peer access inside one process);
-//   * lin_solve: the two boundary strips of each temporally blocked launch run first on a
-//     high-priority side stream and store the rows the neighbour needs STRAIGHT INTO THE NEIGHBOUR'S
-//     GHOST ROWS (fused compute + halo push, jacobi_stream_kernel's `xpeer`), while the interior
-//     launch runs on the main stream;
+//   * lin_solve: every temporally blocked launch is ONE kernel that computes AND exchanges.  Its first
+//     work items are the two boundary strips (one warp per 128-column band and side): they wait for
+//     the neighbour's previous strips (acquire on a word the neighbour posts to), store the rows they
+//     produce STRAIGHT INTO THE NEIGHBOUR'S GHOST ROWS over NVLink as well as locally, and the last
+//     strip warp to finish posts the new count to the neighbour (release, system scope).  All other
+//     warps are interior work items that never touch a ghost row and never wait;
 //   * advect: no halo exchange at all -- a back-trace that leaves the slab reads the neighbour's rows
 //     through the peer mapping (advect4_peer_kernel);
-//   * ordering between GPUs: a NEIGHBOUR BARRIER kernel (one warp): bump a local epoch, store it
-//     into both neighbours' inboxes (release, system scope), spin until both neighbours' epochs have
-//     arrived (acquire).  Epochs live in device memory, so a captured CUDA graph of the whole step
-//     replays correctly; no host thread, no NCCL call and no stream synchronisation sits inside a step.
+//   * the few remaining exchanges (right-hand sides, one row of u, v) are a push kernel between two
+//     NEIGHBOUR BARRIER kernels (one warp: bump a local epoch, store it into both neighbours' inboxes,
+//     spin until both neighbours' epochs have arrived).  All counters live in device memory and only
+//     ever grow, so a captured CUDA graph of the whole step replays correctly; no host thread, no NCCL
+//     call, no side stream and no stream synchronisation sits inside a step.
 //   Results do not depend on the partition: every p gives the single-GPU bits (tests/test_peer_slab_gpu.py).
 //
-// Protocol (every slab issues the same sequence; channel 0 = main stream, channel 1 = side stream):
-//   exchange(fields) on main :  barrier  (all my earlier readers of my ghost rows are done, everywhere)
-//                               push kernel (my boundary rows -> neighbours' ghost rows)
-//                               barrier  (both neighbours' pushes into my ghost rows have landed)
-//   blocked launch k         :  fork side from main;
-//                               side: barrier, top strip (+push up), bottom strip (+push down), barrier
-//                               main: interior rows;   join side into main
-//   advect                   :  barrier (sources final everywhere), gather with peer loads, barrier
-//                               (nobody overwrites a source a neighbour may still be reading)
-// A barrier that waits longer than link.timeout_ns sets SF_SLAB_ERR_TIMEOUT in the slab's error word
-// and stops waiting (sticky), so a lost neighbour is an error report, never a hung GPU.
+// Ordering argument.  Ghost rows of the lin_solve buffers are read by strip warps only (a strip is at
+// least `sweeps` rows high).  Strip warps of launch k wait for the neighbour's strip launch k-1, which (a)
+// delivered their ghost rows and (b) was the last reader of the ghost rows they are about to overwrite
+// on the neighbour (the buffers ping-pong).  Every solve starts with a barrier-protected exchange and
+// ends with a barrier, so stage kernels on either side never race with a push.
+// A wait longer than link.timeout_ns sets SF_SLAB_ERR_TIMEOUT in the slab's error word and stops
+// waiting (sticky), so a lost neighbour is an error report, never a hung GPU.
 #include <algorithm>
 
 #include "sf_internal.h"
@@ -210,7 +209,6 @@ cudaError_t launch_push_rows(const PushSegment *segs, int nsegs, cudaStream_t st
 // ---- lin_solve with fused strip pushes (replaces diffuse(), FluidSequential.c:85-104, on a slab) ----
 int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess)
 {
-    SlabLink &L = c->link;
     SF_REQUIRE(c, stream_kernels_ok(c), "peer slab: grid width must be a multiple of 4 (streaming kernels)");
     SF_REQUIRE(c, field_index(c, x) >= 0 && field_index(c, x0) >= 0, "peer slab: lin_solve fields must be arena fields (sf_slab_field)");
     const int T = default_sweeps(c);
@@ -219,7 +217,6 @@ int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha,
     const int lo = c->g.own_lo, hi = c->g.own_hi;
     SF_REQUIRE(c, c->halo >= maxT, "peer slab: halo rows < sweeps per launch");
     SF_REQUIRE(c, hi - lo >= 2 * maxT, "peer slab: slab thinner than two boundary strips");
-    const bool has_up = L.nbr[0].present, has_dn = L.nbr[1].present;
 
     // ghost rows the launches read: plan[0] rows of the initial guess, maxT rows of the right-hand side
     int rc = slab_exchange(c, {HaloSpec{x, zero_guess ? 0 : plan[0]}, HaloSpec{x0, maxT}});
@@ -228,32 +225,17 @@ int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha,
     float *cur = x, *nxt = c->scratch;
     for (size_t k = 0; k < plan.size(); ++k) {
         const int sweeps = plan[k];
-        const int strip = (k + 1 < plan.size()) ? plan[k + 1] : 1;   // after the solve: 1 row for the stencils that follow
-        const int top_hi = has_up ? lo + strip : lo;
-        const int bot_lo = has_dn ? hi - strip : hi;
-        const int zg = (zero_guess && k == 0) ? 1 : 0;
-        const int kn = field_index(c, nxt);
-        // fork: the side stream starts where the main stream is (everything this launch reads is complete)
-        SF_CUDA(c, cudaEventRecord(L.fork, c->work));
-        SF_CUDA(c, cudaStreamWaitEvent(L.side, L.fork, 0));
-        if ((rc = slab_barrier(c, L.side, 1))) return rc;            // neighbours are done reading the ghost rows of `nxt`
-        if (has_up) {
-            PushSpec ps;
-            ps.xpeer = nbr_field(c, 0, kn); ps.peer_row_base = L.nbr[0].row_base; ps.push_lo = lo; ps.push_hi = top_hi;
-            if ((rc = one_jacobi_launch(c, L.side, b, nxt, cur, x0, alpha, beta, sweeps, lo, top_hi, zg, ps))) return rc;
-        }
-        if (has_dn) {
-            PushSpec ps;
-            ps.xpeer = nbr_field(c, 1, kn); ps.peer_row_base = L.nbr[1].row_base; ps.push_lo = bot_lo; ps.push_hi = hi;
-            if ((rc = one_jacobi_launch(c, L.side, b, nxt, cur, x0, alpha, beta, sweeps, bot_lo, hi, zg, ps))) return rc;
-        }
-        if ((rc = slab_barrier(c, L.side, 1))) return rc;            // the neighbours' strips have landed in my ghost rows
-        // interior rows on the main stream, concurrently with the strips and their exchange
-        if ((rc = one_jacobi_launch(c, c->work, b, nxt, cur, x0, alpha, beta, sweeps, top_hi, bot_lo, zg))) return rc;
-        SF_CUDA(c, cudaEventRecord(L.join, L.side));
-        SF_CUDA(c, cudaStreamWaitEvent(c->work, L.join, 0));
+        // The strip must hold what the neighbour's next launch reads (plan[k+1] rows; after the solve: 1
+        // row for the stencils that follow) and be at least `sweeps` high, so that ONLY strip warps read
+        // ghost rows and the interior warps never have to wait for a neighbour.
+        const int need = (k + 1 < plan.size()) ? plan[k + 1] : 1;
+        const int strip = std::max(need, sweeps);
+        // ONE launch: strip warps (scheduled first) exchange their rows while the interior warps compute
+        if ((rc = one_jacobi_launch(c, c->work, b, nxt, cur, x0, alpha, beta, sweeps, lo, hi, (zero_guess && k == 0) ? 1 : 0, strip))) return rc;
         std::swap(cur, nxt);
     }
+    // the neighbours' last strips must have landed before the stencils that follow read the ghost row
+    if ((rc = slab_barrier(c, c->work, 0))) return rc;
     if (cur != x) SF_CUDA(c, cudaMemcpyAsync(x, cur, field_cells(c) * sizeof(float), cudaMemcpyDeviceToDevice, c->work));
     return SF_OK;
 }
@@ -342,16 +324,52 @@ int slab_prevalidate(sf_context *c, float coef, float dt)
     return SF_OK;
 }
 
+constexpr int STRIP_MAX = 8;   // strip heights 0..8 (HALO rows of the streaming kernel)
+
+const StripArgs *slab_strip_args(const sf_context *c, const float *xout, int rows)
+{
+    const int k = field_index(c, xout);
+    if (k < 0 || rows < 1 || rows > STRIP_MAX || rows > c->halo || !c->link.strip_table) return nullptr;
+    return c->link.strip_table + (size_t)k * (STRIP_MAX + 1) + rows;
+}
+
+// (re)write the device-resident StripArgs table: one entry per output field and strip height
+int slab_build_strip_table(sf_context *c)
+{
+    SlabLink &L = c->link;
+    const int nf = L.nfields + 1;
+    std::vector<StripArgs> tab((size_t)nf * (STRIP_MAX + 1));
+    for (int k = 0; k < nf; ++k)
+        for (int rows = 0; rows <= STRIP_MAX; ++rows) {
+            StripArgs &S = tab[(size_t)k * (STRIP_MAX + 1) + rows];
+            S.o_lo = c->g.own_lo; S.o_hi = c->g.own_hi;
+            S.error = &L.flags->error; S.timeout_ns = L.timeout_ns;
+            for (int dir = 0; dir < 2; ++dir) {
+                if (!L.nbr[dir].present) continue;
+                StripPort &P = S.port[dir];
+                P.rows = rows;
+                P.xpeer = nbr_field(c, dir, k);
+                P.peer_row_base = L.nbr[dir].row_base;
+                P.inbox = &L.flags->strip_inbox[dir];
+                P.seq = &L.flags->strip_seq[dir];
+                P.arrive = &L.flags->strip_arrive[dir];
+                P.nbr_inbox = &L.nbr[dir].flags->strip_inbox[1 - dir];    // I am the neighbour's other side
+            }
+        }
+    if (!L.strip_table) SF_CUDA(c, cudaMalloc(&L.strip_table, tab.size() * sizeof(StripArgs)));
+    SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    SF_CUDA(c, cudaMemcpy(L.strip_table, tab.data(), tab.size() * sizeof(StripArgs), cudaMemcpyHostToDevice));
+    return SF_OK;
+}
+
 void slab_release(sf_context *c)
 {
     SlabLink &L = c->link;
+    if (L.strip_table) cudaFree(L.strip_table);
     for (auto &n : L.nbr) {
         if (n.present && n.ipc && n.base) cudaIpcCloseMemHandle(n.base);
         n = SlabLink::Nbr();
     }
-    if (L.side) cudaStreamDestroy(L.side);
-    if (L.fork) cudaEventDestroy(L.fork);
-    if (L.join) cudaEventDestroy(L.join);
     if (L.base) cudaFree(L.base);
     L = SlabLink();
 }
@@ -380,11 +398,6 @@ int sf_slab_arena_create(sf_context *c, int nfields)
     L.flags = reinterpret_cast<SlabFlags *>(L.base + off);
     c->scratch = reinterpret_cast<float *>(L.base + (size_t)nfields * L.field_bytes);
     c->scratch_in_arena = true;
-    int lo_pri = 0, hi_pri = 0;
-    SF_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-    SF_CUDA(c, cudaStreamCreateWithPriority(&L.side, cudaStreamNonBlocking, hi_pri));
-    SF_CUDA(c, cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
-    SF_CUDA(c, cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming));
     {   // nothing may be loaded or allocated inside a step (see preload_jacobi_kernels)
         cudaFuncAttributes a;
         cudaFuncGetAttributes(&a, nbr_barrier_kernel);
@@ -427,7 +440,7 @@ static int connect_common(sf_context *c, int dir, char *base, bool ipc, int nbr_
     // graphs captured before the link existed do not contain the exchanges
     for (auto &e : c->graphs) if (e.exec) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
     c->graphs.clear();
-    return SF_OK;
+    return slab_build_strip_table(c);
 }
 
 static int check_connect_args(sf_context *c, int dir, int nbr_row_lo, int nbr_row_hi)
@@ -479,7 +492,7 @@ int sf_slab_set_timeout_ms(sf_context *c, int ms)
     c->link.timeout_ns = (unsigned long long)ms * 1000000ull;
     for (auto &e : c->graphs) if (e.exec) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
     c->graphs.clear();
-    return SF_OK;
+    return c->link.base ? slab_build_strip_table(c) : SF_OK;
 }
 
 int sf_slab_status(sf_context *c, unsigned int *error_bits)

@@ -62,6 +62,18 @@ def load_library() -> C.CDLL:
             f"{LIB_PATH} is missing: run `python -m fluidsimulationcuda_b200.build` (nvcc, sm_100a). "
             "There is no CPU fallback.")
     L = C.CDLL(LIB_PATH)
+    if os.environ.get("SF_LIBRARY"):
+        # experimental / older builds (A/B timing): symbols they lack resolve to a stub that raises
+        class _Tolerant:
+            def __init__(self, lib): object.__setattr__(self, "_lib", lib)
+            def __getattr__(self, name):
+                try:
+                    return getattr(self._lib, name)
+                except AttributeError:
+                    def missing(*a, **k):
+                        raise StableFluidsError(f"{LIB_PATH} does not export {name}")
+                    return missing
+        L = _Tolerant(L)
     vp, i, f, u64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64
     L.sf_create.argtypes = [C.POINTER(vp), i, i]
     L.sf_create_on_stream.argtypes = [C.POINTER(vp), i, i, vp]

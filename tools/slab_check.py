@@ -20,7 +20,10 @@ else:
 s.init_synthetic(3)
 for st in range(steps):
     if st > 0:
-        for k in ("dens_prev", "u_prev", "v_prev"): s.f[k].zero_()
+        if MODE == "peer":
+            s.zero_sources()          # on the slab's own stream
+        else:
+            for k in ("dens_prev", "u_prev", "v_prev"): s.f[k].zero_()
     s.step(None, 0.0025, 0.1, 0.016)
 s.check_reach()
 torch.cuda.synchronize()
