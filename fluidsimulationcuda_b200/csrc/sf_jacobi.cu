@@ -248,49 +248,13 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
 // TMA = false: rows are staged with per-lane cp.async (LDGSTS.128).  TMA = true: one elected lane
 // issues a 1-D bulk copy (cp.async.bulk -> UBLKCP) of the warp's whole 512-byte row piece per field,
 // completing on a per-slot mbarrier that all lanes wait on (SF_OPT_STAGING; measured in DESIGN.md).
-// VAR = 2: cp.async staging plus the fused strip exchange of peer-memory slabs (own instantiation, so
-// that the single-GPU kernels carry none of it).
-template <int T, int MODE, int VAR>
-__global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
+// The streaming pipeline of one warp over output rows [a_lo, a_hi) of band `band`.
+// STRIP = true (peer-memory slabs): general ticks only, and every produced row is also stored at
+// peer + row * pitch, the neighbour GPU's copy of the field (pre-offset so that global row numbers index it).
+template <int T, int MODE, bool TMA, bool STRIP>
+__device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, const int lane, const int warp, const int band,
+                                            const int a_lo, const int a_hi, float *peer)
 {
-    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2);
-    extern __shared__ float4 ring[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.
-    // Peer-memory slabs: the first items are the boundary strips (one warp per band and side), so they
-    // are scheduled first and their rows travel while the interior items compute.
-    int band_, a_lo_, a_hi_;
-    bool is_strip_ = false, is_top_ = false;
-    if constexpr (STRIPS) {
-        const StripArgs *S = A.strips;
-        const int item0 = blockIdx.x * WPC + warp;
-        const int rows_top = S->port[0].rows, rows_bot = S->port[1].rows;
-        const int n_top = rows_top > 0 ? A.nbands : 0, n_bot = rows_bot > 0 ? A.nbands : 0;
-        is_strip_ = item0 < n_top + n_bot; is_top_ = item0 < n_top;
-        if (is_strip_) {
-            const StripPort *P = &S->port[is_top_ ? 0 : 1];
-            strip_wait(P->seq, P->inbox, S->error, S->timeout_ns, lane);
-            band_ = is_top_ ? item0 : item0 - n_top;
-            a_lo_ = is_top_ ? S->o_lo : S->o_hi - rows_bot;
-            a_hi_ = is_top_ ? S->o_lo + rows_top : S->o_hi;
-        } else {
-            const int item = item0 - (n_top + n_bot);
-            if (item >= A.nbands * A.nchunks) return;
-            band_ = item % A.nbands;
-            a_lo_ = A.a_lo + (item / A.nbands) * A.chunk_rows;
-            a_hi_ = min(a_lo_ + A.chunk_rows, A.a_hi);
-        }
-    } else {
-        const int item = blockIdx.x * WPC + warp;
-        if (item >= A.nbands * A.nchunks) return;
-        band_ = item % A.nbands;
-        a_lo_ = A.a_lo + (item / A.nbands) * A.chunk_rows;
-        a_hi_ = min(a_lo_ + A.chunk_rows, A.a_hi);
-    }
-    const int band = band_, a_lo = a_lo_, a_hi = a_hi_;
-    const bool is_strip = is_strip_, is_top = is_top_;
-    if (a_lo >= a_hi) return;
-
     const int c = band * VALID_W - HALO_X + 4 * lane;     // first of this lane's 4 columns
     const bool indom = (c >= 0) && (c + 4 <= A.G);
     const bool ownsL = (c == 0), ownsR = (c + 4 == A.G);
@@ -372,7 +336,7 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     // cell.  The high end follows from a maximum principle: |numerator| <= (1 + 4|alpha|) * max|input|,
     // so rows whose magnitudes stay below A.hi_in can never produce a numerator above SF_DIV_HI.
     // Every row is checked when it is fetched; one outlier switches the warp to the fully guarded
-    // tick for the rest of its chunk.
+    // tick for the next rows (up to the next multiple of 64).
     auto row_is_big = [&](int row) -> bool {
         if (MODE != MODE_STRICT || row > load_hi) return false;
         const float4 a = xrow(row), b = rring[(row & (RING_R - 1)) * 32];
@@ -391,19 +355,13 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     float *orow = A.xout + cc;
     // peer-memory slabs: a boundary strip stores the rows its neighbour needs straight into the
     // neighbour's ghost rows over NVLink (plain peer stores; the exchange is part of the compute kernel)
+    // peer-memory slabs: a strip warp stores every row it produces into the neighbour's ghost rows as well
+    // (plain peer stores over NVLink: the exchange is part of the compute kernel)
     auto push = [&](int a, const float4 &o) {
-        if constexpr (STRIPS) {
-            if (is_strip) {   // the port is re-read per row (cached) rather than held in registers across the hot loop
-                const StripPort *P = &A.strips->port[is_top ? 0 : 1];
-                *reinterpret_cast<float4 *>(P->xpeer + cc + (ptrdiff_t)(a - P->peer_row_base) * (ptrdiff_t)pitch) = o;
-            }
-        }
+        if constexpr (STRIP) *reinterpret_cast<float4 *>(peer + cc + (size_t)a * pitch) = o;
     };
     auto emit_plain = [&](int a, const float4 &o) {
-        if (a >= a_lo && a < a_hi && st_ok) {
-            *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
-            push(a, o);
-        }
+        if (a >= a_lo && a < a_hi && st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
     };
     auto emit_walls = [&](int a, const float4 &o) {
         if (a < a_lo || a >= a_hi) return;
@@ -429,7 +387,9 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     // Everything else runs the wall-free tick in groups of three (one full rotation of the windows).
     const int fast_lo = T + 2;
     const int fast_hi = min(s_hi, A.N);
-    bool slow = false;   // sticky: an out-of-range numerator or an outlier row was seen in this chunk
+    // sticky: an out-of-range numerator or an outlier row was seen in this chunk.  Strip warps (peer
+    // slabs) only ever take the general tick: they live for ~3T ticks.
+    bool slow = STRIP;
 
     // general tick at phase 0 followed by the register rotation that restores phase 0
     auto general_tick = [&](int s_, const float4 &row_in) {
@@ -442,6 +402,10 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
 
     int s = s_lo;
     while (s <= s_hi) {
+        // The guarded mode is left again every 64 rows: the numerators that need it (the decaying front of
+        // a density field) occupy a band of rows, not the rest of a chunk of thousands of rows.  A retry
+        // that fails costs one wasted optimistic tick per 64 guarded ones.
+        if (MODE == MODE_STRICT && !STRIP && (s & 63) == 0) slow = false;
         if (!slow && s >= fast_lo && s + 2 <= fast_hi) {
             issue(s + PREFETCH); issue(s + PREFETCH + 1); issue(s + PREFETCH + 2);
             landed(s, 3);                    // rows <= s+2 have landed
@@ -490,21 +454,56 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
         general_tick(s, fetch(s));
         ++s;
     }
-    if constexpr (STRIPS) {   // strip warps: publish the rows stored into the neighbour's ghost rows
-        const StripArgs *S = A.strips;
-        const int it = blockIdx.x * WPC + warp;
-        const int n_top = S->port[0].rows > 0 ? A.nbands : 0, n_bot = S->port[1].rows > 0 ? A.nbands : 0;
-        if (it < n_top + n_bot) {
-            const StripPort *P = &S->port[it < n_top ? 0 : 1];
-            strip_post(P->arrive, P->seq, P->nbr_inbox, A.nbands, lane);
-        }
-    }
     if (TMA) {   // drain: rows issued beyond the last one consumed must land before the CTA's smem is released
         for (int row = s_hi + 1; row <= min(s_hi + PREFETCH + 2, load_hi); ++row)
             mbar_wait(bars + (row & (RING_X - 1)), (unsigned)((row - s_lo) >> 3) & 1u);
     } else {
         cp_async_wait<0>();
     }
+}
+
+// VAR = 2: cp.async staging plus the fused strip exchange of peer-memory slabs.  The strip warps run
+// their own (out-of-line) copy of the pipeline, so the interior warps execute exactly the code of the
+// single-GPU kernel.
+template <int T, int MODE>
+__device__ __noinline__ void strip_warp(const StreamArgs A, float4 *ring, const int lane, const int warp, const int item0, const int n_top)
+{
+    const StripArgs *S = A.strips;
+    const bool top = item0 < n_top;
+    const StripPort *P = &S->port[top ? 0 : 1];
+    strip_wait(P->seq, P->inbox, S->error, S->timeout_ns, lane);
+    const int a_lo = top ? S->o_lo : S->o_hi - P->rows;
+    const int a_hi = top ? S->o_lo + P->rows : S->o_hi;
+    float *peer = P->xpeer - (ptrdiff_t)P->peer_row_base * (ptrdiff_t)A.G;
+    stream_rows<T, MODE, false, true>(A, ring, lane, warp, top ? item0 : item0 - n_top, a_lo, a_hi, peer);
+    strip_post(P->arrive, P->seq, P->nbr_inbox, A.nbands, lane);
+}
+
+template <int T, int MODE, int VAR>
+__global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
+{
+    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2);
+    extern __shared__ float4 ring[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.
+    // Peer-memory slabs: the first items are the boundary strips (one warp per band and side), so they
+    // are scheduled first and their rows travel while the interior items compute.
+    int item = blockIdx.x * WPC + warp;
+    if constexpr (STRIPS) {
+        const StripArgs *S = A.strips;
+        const int n_top = S->port[0].rows > 0 ? A.nbands : 0, n_bot = S->port[1].rows > 0 ? A.nbands : 0;
+        if (item < n_top + n_bot) {
+            strip_warp<T, MODE>(A, ring, lane, warp, item, n_top);
+            return;
+        }
+        item -= n_top + n_bot;
+    }
+    if (item >= A.nbands * A.nchunks) return;
+    const int band = item % A.nbands, chunk = item / A.nbands;
+    const int a_lo = A.a_lo + chunk * A.chunk_rows;
+    const int a_hi = min(a_lo + A.chunk_rows, A.a_hi);
+    if (a_lo >= a_hi) return;
+    stream_rows<T, MODE, TMA, false>(A, ring, lane, warp, band, a_lo, a_hi, nullptr);
 }
 
 // ---- generic fallback: one sweep, one thread per interior cell, any G -----------------------

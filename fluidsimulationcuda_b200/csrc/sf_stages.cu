@@ -439,18 +439,29 @@ __global__ void __launch_bounds__(256) advect4_kernel(float *__restrict__ dA, fl
 struct PeerView {
     const float *loc, *up, *dn;
 };
-__device__ __forceinline__ const float *peer_row(const PeerView &f, const Geom &g, const PeerGeom &pg, int r)
+// which array holds global row r (0 = this slab, 1 = up neighbour, 2 = down neighbour) and the row's offset in it
+__device__ __forceinline__ int peer_row(const Geom &g, const PeerGeom &pg, int r, size_t &off)
 {
     const size_t G = (size_t)g.G;
     if (r < g.own_lo) {
         if (r < pg.up_lo) { atomicOr(pg.error, 2u); r = pg.up_lo; }          // SF_SLAB_ERR_REACH
-        return f.up + (size_t)(r - pg.up_row_base) * G;
+        off = (size_t)(r - pg.up_row_base) * G;
+        return 1;
     }
     if (r >= g.own_hi) {
         if (r >= pg.dn_hi) { atomicOr(pg.error, 2u); r = pg.dn_hi - 1; }
-        return f.dn + (size_t)(r - pg.dn_row_base) * G;
+        off = (size_t)(r - pg.dn_row_base) * G;
+        return 2;
     }
-    return f.loc + (size_t)(r - g.row_base) * G;
+    off = (size_t)(r - g.row_base) * G;
+    return 0;
+}
+__device__ __forceinline__ const float *peer_base(const PeerView &f, int which) { return which == 0 ? f.loc : (which == 1 ? f.up : f.dn); }
+__device__ __forceinline__ float bilinear(const float *p0, const float *p1, float wx0, float wx1, float wy0, float wy1)
+{
+    const float a00 = __ldg(p0), a10 = __ldg(p1), a01 = __ldg(p0 + 1), a11 = __ldg(p1 + 1);
+    return __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
+                     __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
 }
 template <int NF>
 __device__ __forceinline__ void advect_cell_peer(const PeerView &sA, const PeerView &sB, const Geom &g, const PeerGeom &pg,
@@ -465,18 +476,18 @@ __device__ __forceinline__ void advect_cell_peer(const PeerView &sA, const PeerV
     const int c0 = (int)px, r0 = (int)py;
     const float wx1 = __fsub_rn(px, (float)c0), wx0 = __fsub_rn(1.0f, wx1);
     const float wy1 = __fsub_rn(py, (float)r0), wy0 = __fsub_rn(1.0f, wy1);
-    {
-        const float *p0 = peer_row(sA, g, pg, r0) + c0, *p1 = peer_row(sA, g, pg, r0 + 1) + c0;
-        const float a00 = __ldg(p0), a10 = __ldg(p1), a01 = __ldg(p0 + 1), a11 = __ldg(p1 + 1);
-        oA = __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
-                       __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
+    if (r0 >= g.own_lo && r0 + 1 < g.own_hi) {
+        // both source rows are this slab's own (all but the cells within reach of the slab edges)
+        const size_t G = (size_t)g.G;
+        const size_t j = (size_t)(r0 - g.row_base) * G + c0;
+        oA = bilinear(sA.loc + j, sA.loc + j + G, wx0, wx1, wy0, wy1);
+        if (NF == 2) oB = bilinear(sB.loc + j, sB.loc + j + G, wx0, wx1, wy0, wy1);
+        return;
     }
-    if (NF == 2) {
-        const float *p0 = peer_row(sB, g, pg, r0) + c0, *p1 = peer_row(sB, g, pg, r0 + 1) + c0;
-        const float a00 = __ldg(p0), a10 = __ldg(p1), a01 = __ldg(p0 + 1), a11 = __ldg(p1 + 1);
-        oB = __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
-                       __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
-    }
+    size_t off0, off1;
+    const int w0 = peer_row(g, pg, r0, off0), w1 = peer_row(g, pg, r0 + 1, off1);
+    oA = bilinear(peer_base(sA, w0) + off0 + c0, peer_base(sA, w1) + off1 + c0, wx0, wx1, wy0, wy1);
+    if (NF == 2) oB = bilinear(peer_base(sB, w0) + off0 + c0, peer_base(sB, w1) + off1 + c0, wx0, wx1, wy0, wy1);
 }
 
 template <int NF>
