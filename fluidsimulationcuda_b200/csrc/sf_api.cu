@@ -402,6 +402,7 @@ int sf_diffuse(sf_context *c, int b, float *x, const float *x0, float alpha, flo
     SF_REQUIRE(c, b >= 0 && b <= 2, "diffuse: b not in 0..2");
     SF_REQUIRE(c, iters >= 1, "diffuse: iters < 1");
     DeviceGuard guard(c->device);
+    c->link.barrier_valid = false;   // barriers collapse only within one call (see slab_barrier)
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
     if (is_linked_slab(c)) (void)arith_mode(c, alpha, beta);   // the divisor check synchronises: before anything is enqueued
@@ -414,6 +415,7 @@ int sf_advect(sf_context *c, int b, float *d, const float *d0, const float *u, c
     SF_REQUIRE(c, d && d0 && u && v && d != d0 && d != u && d != v, "advect: null fields or output aliases an input");
     SF_REQUIRE(c, b >= 0 && b <= 2, "advect: b not in 0..2");
     DeviceGuard guard(c->device);
+    c->link.barrier_valid = false;   // barriers collapse only within one call (see slab_barrier)
     if (is_linked_slab(c)) return slab_advect(c, b, d, d0, u, v, dt, true);
     SF_CUDA(c, launch_advect(c->g, b, d, d0, u, v, dt, c->stream));
     ++c->launches;
@@ -446,6 +448,7 @@ int sf_project(sf_context *c, float *u, float *v, float *p, float *div, int iter
     if (!c) return SF_ERR_INVALID;
     SF_REQUIRE(c, u && v && p && div && iters >= 1, "project: null field or iters < 1");
     DeviceGuard guard(c->device);
+    c->link.barrier_valid = false;   // barriers collapse only within one call (see slab_barrier)
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
     return enqueue_project(c, u, v, p, div, iters);
@@ -457,6 +460,7 @@ int sf_dens_step(sf_context *c, float *x, float *x0, const float *u, const float
     SF_REQUIRE(c, x && x0 && u && v && x != x0, "dens_step: null or aliased fields");
     SF_REQUIRE(c, iters >= 1, "dens_step: iters < 1");
     DeviceGuard guard(c->device);
+    c->link.barrier_valid = false;   // barriers collapse only within one call (see slab_barrier)
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
     if (is_linked_slab(c) && (rc = slab_prevalidate(c, diff, dt))) return rc;
@@ -470,6 +474,7 @@ int sf_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float v
     SF_REQUIRE(c, u && v && u0 && v0 && u != v && u != u0 && u != v0 && v != u0 && v != v0 && u0 != v0, "vel_step: null or aliased fields");
     SF_REQUIRE(c, iters >= 1, "vel_step: iters < 1");
     DeviceGuard guard(c->device);
+    c->link.barrier_valid = false;   // barriers collapse only within one call (see slab_barrier)
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
     if (is_linked_slab(c) && (rc = slab_prevalidate(c, visc, dt))) return rc;
@@ -484,6 +489,7 @@ int sf_step(sf_context *c, float *dens, float *dens_prev, float *u, float *u_pre
     SF_REQUIRE(c, dens && dens_prev && u && u_prev && v && v_prev, "step: null field");
     SF_REQUIRE(c, iters >= 1, "step: iters < 1");
     DeviceGuard guard(c->device);
+    c->link.barrier_valid = false;   // barriers collapse only within one call (see slab_barrier)
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
     if (is_linked_slab(c) && ((rc = slab_prevalidate(c, visc, dt)) || (rc = slab_prevalidate(c, diff, dt)))) return rc;

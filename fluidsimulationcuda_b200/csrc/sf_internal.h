@@ -47,6 +47,8 @@ struct SlabLink {
         int row_lo = 0, row_hi = 0, row_base = 0;
     } nbr[2];                     // 0 = up (smaller rows), 1 = down
     unsigned long long timeout_ns = 20000000000ull;   // barrier spin limit before the error bit is set
+    bool barrier_valid = false;                 // see slab_barrier: back-to-back barriers collapse into one
+    unsigned long long launches_at_barrier = 0;
     StripArgs *strip_table = nullptr;   // device: entry [field * 9 + rows] = StripArgs of a launch writing `field`
     int world_links() const { return (nbr[0].present ? 1 : 0) + (nbr[1].present ? 1 : 0); }
 };

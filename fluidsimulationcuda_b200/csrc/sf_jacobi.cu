@@ -486,17 +486,13 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.
-    // Peer-memory slabs: the first items are the boundary strips (one warp per band and side), so they
-    // are scheduled first and their rows travel while the interior items compute.
-    int item = blockIdx.x * WPC + warp;
+    const int item = blockIdx.x * WPC + warp;
     if constexpr (STRIPS) {
+        // the first warps of the grid compute a boundary strip BEFORE their interior item: the strips are
+        // scheduled first and travel while everybody computes, and the grid still is one wave of warps
         const StripArgs *S = A.strips;
         const int n_top = S->port[0].rows > 0 ? A.nbands : 0, n_bot = S->port[1].rows > 0 ? A.nbands : 0;
-        if (item < n_top + n_bot) {
-            strip_warp<T, MODE>(A, ring, lane, warp, item, n_top);
-            return;
-        }
-        item -= n_top + n_bot;
+        if (item < n_top + n_bot) strip_warp<T, MODE>(A, ring, lane, warp, item, n_top);
     }
     if (item >= A.nbands * A.nchunks) return;
     const int band = item % A.nbands, chunk = item / A.nbands;
@@ -707,7 +703,7 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     if (chunk > rows) chunk = max(rows, 1);
     A.chunk_rows = chunk;
     A.nchunks = rows > 0 ? (rows + chunk - 1) / chunk : 0;
-    const int items = n_strip_items + A.nbands * A.nchunks;
+    const int items = max(n_strip_items, A.nbands * A.nchunks);   // strip warps go on to an interior item
     dim3 grid((items + WPC - 1) / WPC);
     const size_t smem = (size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4);
     switch (L.mode) {

@@ -114,9 +114,13 @@ float *nbr_field(const sf_context *c, int dir, int k)
 int slab_barrier(sf_context *c, cudaStream_t st, int ch)
 {
     SlabLink &L = c->link;
+    // nothing was launched since the last barrier: a second one orders nothing (every slab skips it alike)
+    if (L.barrier_valid && L.launches_at_barrier == c->launches) return SF_OK;
     SF_CUDA(c, launch_nbr_barrier(L.flags, L.nbr[0].present ? L.nbr[0].flags : nullptr,
                                   L.nbr[1].present ? L.nbr[1].flags : nullptr, ch, L.timeout_ns, st));
     ++c->launches;
+    L.barrier_valid = true;
+    L.launches_at_barrier = c->launches;
     return SF_OK;
 }
 
@@ -236,7 +240,10 @@ int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha,
     }
     // the neighbours' last strips must have landed before the stencils that follow read the ghost row
     if ((rc = slab_barrier(c, c->work, 0))) return rc;
-    if (cur != x) SF_CUDA(c, cudaMemcpyAsync(x, cur, field_cells(c) * sizeof(float), cudaMemcpyDeviceToDevice, c->work));
+    if (cur != x) {
+        SF_CUDA(c, cudaMemcpyAsync(x, cur, field_cells(c) * sizeof(float), cudaMemcpyDeviceToDevice, c->work));
+        c->link.barrier_valid = false;
+    }
     return SF_OK;
 }
 
