@@ -556,6 +556,56 @@ int sf_step_host(sf_context *c, float *dens, float *dens_prev, float *u, float *
     return SF_OK;
 }
 
+int sf_run_steps(sf_context *c, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev, float visc,
+                 float diff, float dt, int iters, int steps, int source_mode, uint64_t seed, const float *src_dens,
+                 const float *src_u, const float *src_v)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, dens && dens_prev && u && u_prev && v && v_prev, "run_steps: null field");
+    SF_REQUIRE(c, iters >= 1 && steps >= 0, "run_steps: iters < 1 or steps < 0");
+    SF_REQUIRE(c, source_mode >= SF_SOURCES_REFERENCE && source_mode <= SF_SOURCES_FIELDS, "run_steps: unknown source mode");
+    if (source_mode == SF_SOURCES_FIELDS) SF_REQUIRE(c, src_dens && src_u && src_v, "run_steps: SF_SOURCES_FIELDS needs the three source fields");
+    DeviceGuard guard(c->device);
+    const size_t bytes = field_cells(c) * sizeof(float);
+    for (int k = 0; k < steps; ++k) {
+        // the source schedule runs on the device, ordered on the context's stream like the step itself
+        if (source_mode == SF_SOURCES_REFERENCE && k > 0) {
+            SF_CUDA(c, cudaMemsetAsync(dens_prev, 0, bytes, c->stream));
+            SF_CUDA(c, cudaMemsetAsync(u_prev, 0, bytes, c->stream));
+            SF_CUDA(c, cudaMemsetAsync(v_prev, 0, bytes, c->stream));
+        } else if (source_mode == SF_SOURCES_SYNTHETIC) {
+            SF_CUDA(c, launch_init(c->g, seed + (uint64_t)k, nullptr, dens_prev, nullptr, u_prev, nullptr, v_prev, c->stream));
+            ++c->launches;
+        } else if (source_mode == SF_SOURCES_FIELDS) {
+            SF_CUDA(c, cudaMemcpyAsync(dens_prev, src_dens, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            SF_CUDA(c, cudaMemcpyAsync(u_prev, src_u, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            SF_CUDA(c, cudaMemcpyAsync(v_prev, src_v, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        int rc = sf_step(c, dens, dens_prev, u, u_prev, v, v_prev, visc, diff, dt, iters);
+        if (rc) return rc;
+    }
+    return SF_OK;
+}
+
+int sf_dump_field(sf_context *c, const float *dev_field, const char *path)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, dev_field && path, "dump_field: null argument");
+    DeviceGuard guard(c->device);
+    const size_t G = (size_t)c->g.G, own = (size_t)(c->g.own_hi - c->g.own_lo);
+    std::vector<float> host(own * G);
+    SF_CUDA(c, cudaMemcpyAsync(host.data(), dev_field + (size_t)(c->g.own_lo - c->g.row_base) * G, own * G * sizeof(float),
+                               cudaMemcpyDeviceToHost, c->stream));
+    SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return fail(c, SF_ERR_INVALID, "dump_field: cannot open the output file");
+    const int32_t hdr[8] = {0x444C4653 /* "SFLD" */, 1, c->g.N, c->g.own_lo, c->g.own_hi, c->halo, 0, 0};
+    const bool ok = std::fwrite(hdr, sizeof(hdr), 1, f) == 1 && std::fwrite(host.data(), sizeof(float), host.size(), f) == host.size();
+    std::fclose(f);
+    if (!ok) return fail(c, SF_ERR_INVALID, "dump_field: short write");
+    return SF_OK;
+}
+
 int sf_init_synthetic(sf_context *c, uint64_t seed, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev)
 {
     if (!c) return SF_ERR_INVALID;

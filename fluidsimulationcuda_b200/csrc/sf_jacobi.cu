@@ -387,8 +387,9 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
     // Everything else runs the wall-free tick in groups of three (one full rotation of the windows).
     const int fast_lo = T + 2;
     const int fast_hi = min(s_hi, A.N);
-    // sticky: an out-of-range numerator or an outlier row was seen in this chunk.  Strip warps (peer
-    // slabs) only ever take the general tick: they live for ~3T ticks.
+    // an out-of-range numerator or an outlier row was seen: guarded ticks for the next rows.  Strip warps
+    // (peer slabs) only ever take the general tick (which carries the neighbour push): they live for ~3T
+    // ticks, and a strip copy with the fast tick was measured to cost the interior path registers.
     bool slow = STRIP;
 
     // general tick at phase 0 followed by the register rotation that restores phase 0

@@ -85,7 +85,9 @@ struct PushArgs {
 };
 __global__ void __launch_bounds__(256) push_rows_kernel(PushArgs A)
 {
-    const PushSegment seg = A.s[blockIdx.y];
+    PushSegment seg = A.s[0];     // selects, not A.s[blockIdx.y]: keeps the parameter block out of local memory
+#pragma unroll
+    for (int k = 1; k < 6; ++k) if ((int)blockIdx.y == k) seg = A.s[k];
     const float4 *src = reinterpret_cast<const float4 *>(seg.src);
     float4 *dst = reinterpret_cast<float4 *>(seg.dst);
     const size_t n4 = seg.count / 4;

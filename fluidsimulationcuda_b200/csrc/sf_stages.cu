@@ -90,8 +90,9 @@ struct AddSrcArgs {
 };
 __global__ void add_source_kernel(AddSrcArgs A)
 {
-    float *x = A.x[blockIdx.y];
-    const float *s = A.s[blockIdx.y];
+    // selects, not A.x[blockIdx.y]: a dynamic index would copy the parameter block to local memory
+    float *x = blockIdx.y == 0 ? A.x[0] : (blockIdx.y == 1 ? A.x[1] : A.x[2]);
+    const float *s = blockIdx.y == 0 ? A.s[0] : (blockIdx.y == 1 ? A.s[1] : A.s[2]);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (A.vec) {

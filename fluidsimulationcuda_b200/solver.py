@@ -37,11 +37,12 @@ ABI_SYMBOLS = [
     "sf_alloc_field", "sf_free_field", "sf_upload", "sf_download",
     "sf_set_bnd", "sf_add_source", "sf_diffuse", "sf_advect", "sf_compute_divergence_and_pressure",
     "sf_last_project", "sf_project", "sf_dens_step", "sf_vel_step", "sf_step", "sf_step_host",
-    "sf_init_synthetic", "sf_init_sources", "sf_reduce_max_abs", "sf_reduce_max_abs_async", "sf_residual_l2",
+    "sf_run_steps", "sf_dump_field", "sf_init_synthetic", "sf_init_sources", "sf_reduce_max_abs", "sf_reduce_max_abs_async", "sf_residual_l2",
     "sf_division_check", "sf_halo_rows_needed", "sf_jacobi_launch",
     "sf_slab_arena_create", "sf_slab_field", "sf_slab_ipc_handle", "sf_slab_connect_ipc", "sf_slab_connect_local",
     "sf_slab_set_timeout_ms", "sf_slab_status",
 ]
+SOURCES_REFERENCE, SOURCES_SYNTHETIC, SOURCES_FIELDS = 0, 1, 2
 SF_SLAB_UP, SF_SLAB_DOWN = 0, 1
 SF_SLAB_ERR_TIMEOUT, SF_SLAB_ERR_REACH = 1, 2
 
@@ -105,6 +106,8 @@ def load_library() -> C.CDLL:
     L.sf_vel_step.argtypes = [vp, vp, vp, vp, vp, f, f, i]
     L.sf_step.argtypes = [vp] + [vp] * 6 + [f, f, f, i]
     L.sf_step_host.argtypes = [vp] + [vp] * 6 + [f, f, f, i, i]
+    L.sf_run_steps.argtypes = [vp] + [vp] * 6 + [f, f, f, i, i, i, u64, vp, vp, vp]
+    L.sf_dump_field.argtypes = [vp, vp, C.c_char_p]
     L.sf_init_synthetic.argtypes = [vp, u64] + [vp] * 6
     L.sf_init_sources.argtypes = [vp, u64] + [vp] * 3
     L.sf_reduce_max_abs.argtypes = [vp, vp, C.POINTER(f)]
@@ -252,6 +255,19 @@ class StableFluids:
     def step(self, dens, dens_prev, u, u_prev, v, v_prev, visc, diff, dt, iters):
         self._check(self.L.sf_step(self.h, self._p(dens), self._p(dens_prev), self._p(u), self._p(u_prev),
                                    self._p(v), self._p(v_prev), visc, diff, dt, iters))
+
+    def run_steps(self, dens, dens_prev, u, u_prev, v, v_prev, visc, diff, dt, iters, steps, sources=SOURCES_REFERENCE,
+                  seed=0, src_dens=None, src_u=None, src_v=None):
+        """The reference's main loop (FluidSequential.c:289-312) resident on the device: `steps` iterations of
+        { source schedule; vel_step; dens_step } with no host round trip in between."""
+        opt = lambda t: C.c_void_p(0) if t is None else self._p(t)
+        self._check(self.L.sf_run_steps(self.h, self._p(dens), self._p(dens_prev), self._p(u), self._p(u_prev), self._p(v),
+                                        self._p(v_prev), visc, diff, dt, iters, steps, sources, seed, opt(src_dens),
+                                        opt(src_u), opt(src_v)))
+
+    def dump_field(self, field, path: str):
+        """Binary dump (32-byte header + owned rows as float32) -- replaces the reference's printStateGrid."""
+        self._check(self.L.sf_dump_field(self.h, self._p(field), str(path).encode()))
 
     def step_host(self, dens, dens_prev, u, u_prev, v, v_prev, visc, diff, dt, iters, download_scratch=False):
         """Same loop body with HOST fields (numpy float32 arrays or CPU tensors, ideally pinned)."""

@@ -139,6 +139,28 @@ int sf_step(sf_context *ctx, float *dens, float *dens_prev, float *u, float *u_p
 int sf_step_host(sf_context *ctx, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev,
                  float visc, float diff, float dt, int iters, int download_scratch);
 
+/* ---- device-resident driver loop -------------------------------------------------------------------
+ * The reference's main loop (seq:289-312; gpu:400-439 / optPar LOOPUNROLLED-Interleaved2.cu:680-724)
+ * zeroes the three source fields on the HOST and re-uploads them before every step -- about a third
+ * of its per-step time at 8192^2.  sf_run_steps keeps the whole loop on the device: `steps` iterations
+ * of { source schedule; vel_step; dens_step } are enqueued (graph replays) without any host round
+ * trip in between.  Source schedule for the *_prev fields, which every step clobbers:
+ *   SF_SOURCES_REFERENCE  step 0 uses the *_prev fields as passed in; later steps see zeros
+ *                         (the reference's rule, seq:298-302);
+ *   SF_SOURCES_SYNTHETIC  every step k regenerates them from the counter-based hash with seed + k
+ *                         (same distributions as seq:244-271; see sf_init_sources);
+ *   SF_SOURCES_FIELDS     every step copies src_dens / src_u / src_v (device fields the caller owns,
+ *                         never written) into dens_prev / u_prev / v_prev.
+ * Works on full-grid contexts and (collectively) on connected peer slabs. */
+enum { SF_SOURCES_REFERENCE = 0, SF_SOURCES_SYNTHETIC = 1, SF_SOURCES_FIELDS = 2 };
+int sf_run_steps(sf_context *ctx, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev,
+                 float visc, float diff, float dt, int iters, int steps, int source_mode, uint64_t seed,
+                 const float *src_dens, const float *src_u, const float *src_v);
+/* Binary dump of one (local) device field -- the replacement for the reference's printStateGrid
+ * (seq:32-52): a 32-byte header { "SFLD", int32 version = 1, N, row_lo, row_hi, halo, reserved }
+ * followed by the owned rows as raw little-endian float32, row-major.  Synchronises. */
+int sf_dump_field(sf_context *ctx, const float *dev_field, const char *path);
+
 /* ---- synthetic initial conditions (seq:244-271 value distributions, counter-based) ---------- */
 int sf_init_synthetic(sf_context *ctx, uint64_t seed, float *dens, float *dens_prev, float *u, float *u_prev,
                       float *v, float *v_prev);

@@ -346,3 +346,65 @@ def test_full_size_properties_8192(SF):
     for k in ("dens", "u", "v"):
         assert torch.equal(outs[0][k].view(torch.int32), outs[1][k].view(torch.int32)), f"non-deterministic {k}"
         assert torch.equal(outs[0][k].view(torch.int32), outs[2][k].view(torch.int32)), f"blocking depth changed {k}"
+
+
+# ---- device-resident driver loop (sf_run_steps) and the binary field dump -----------------------------
+def test_run_steps_reference_schedule_matches_the_reference_loop(SF, oracle):
+    """SF_SOURCES_REFERENCE = the reference's main loop (FluidSequential.c:289-312): sources act in step 0,
+    are zeroed before every later step -- all on the device, no host round trip between steps."""
+    N, K, steps = 254, 20, 5
+    s = SF.StableFluids(N)
+    names = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
+    w = oracle.init_synthetic(N, 11)
+    f = {k: dev(w[k]) for k in names}
+    s.run_steps(*[f[k] for k in names], VIS, DIFF, DT, K, steps, SF.SOURCES_REFERENCE)
+    oracle.run_steps(N, steps, w, VIS, DIFF, DT, K)
+    import torch
+    torch.cuda.synchronize()
+    for k in names:
+        assert bits_equal(host(f[k]), w[k]), mismatch_report(host(f[k]), w[k], k)
+
+
+def test_run_steps_live_source_fields_and_dump(SF, oracle, tmp_path):
+    N, K, steps = 126, 8, 3
+    s = SF.StableFluids(N)
+    names = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
+    w = oracle.init_synthetic(N, 4)
+    src = {k: w[k].copy() for k in ("dens_prev", "u_prev", "v_prev")}
+    f = {k: dev(w[k]) for k in names}
+    dsrc = {k: dev(a) for k, a in src.items()}
+    s.run_steps(*[f[k] for k in names], VIS, DIFF, DT, K, steps, SF.SOURCES_FIELDS, 0,
+                dsrc["dens_prev"], dsrc["u_prev"], dsrc["v_prev"])
+    for _ in range(steps):
+        for k in src:
+            w[k][...] = src[k]
+        oracle.vel_step(N, w["u"], w["v"], w["u_prev"], w["v_prev"], VIS, DT, K)
+        oracle.dens_step(N, w["dens"], w["dens_prev"], w["u"], w["v"], DIFF, DT, K)
+    import torch
+    torch.cuda.synchronize()
+    for k in names:
+        assert bits_equal(host(f[k]), w[k]), mismatch_report(host(f[k]), w[k], k)
+    # binary dump: 32-byte header + the field
+    path = tmp_path / "dens.sfld"
+    s.dump_field(f["dens"], path)
+    raw = path.read_bytes()
+    hdr = np.frombuffer(raw[:32], dtype=np.int32)
+    assert raw[:4] == b"SFLD" and hdr[1] == 1 and hdr[2] == N and hdr[3] == 0 and hdr[4] == N + 2
+    assert bits_equal(np.frombuffer(raw[32:], dtype=np.float32).reshape(N + 2, N + 2), w["dens"])
+
+
+def test_run_steps_synthetic_schedule_equals_explicit_refresh(SF):
+    N, K, steps = 254, 6, 3
+    names = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
+    a, b = SF.StableFluids(N), SF.StableFluids(N)
+    fa = [a.new_field() for _ in names]
+    fb = [b.new_field() for _ in names]
+    a.init_synthetic(2, *fa); b.init_synthetic(2, *fb)
+    a.run_steps(*fa, VIS, DIFF, DT, K, steps, SF.SOURCES_SYNTHETIC, 40)
+    for k in range(steps):
+        b.init_sources(40 + k, fb[1], fb[3], fb[5])
+        b.step(*fb, VIS, DIFF, DT, K)
+    import torch
+    torch.cuda.synchronize()
+    for x, y, n in zip(fa, fb, names):
+        assert bits_equal(host(x), host(y)), n
