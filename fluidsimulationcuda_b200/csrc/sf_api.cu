@@ -20,6 +20,19 @@ namespace sf {
 int ensure_scratch(sf_context *c)
 {
     if (!c->scratch) SF_CUDA(c, cudaMalloc(&c->scratch, field_cells(c) * sizeof(float)));
+    if (!c->steal) {
+        c->steal_capacity = 16384;
+        const size_t bytes = sizeof(StealCtl) + (size_t)c->steal_capacity * sizeof(StealSlot);
+        SF_CUDA(c, cudaMalloc(&c->steal, bytes));
+        {   // every slot starts out as "nothing to take here" (pos beyond any row), tag 0 = no launch
+            std::vector<char> init(bytes, 0);
+            StealCtl *h = reinterpret_cast<StealCtl *>(init.data());
+            h->min_pct = c->steal_opt;
+            for (int k = 0; k < c->steal_capacity; ++k) h->slots[k].pos = 0x3fffffff;
+            SF_CUDA(c, cudaMemcpyAsync(c->steal, init.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+            SF_CUDA(c, cudaStreamSynchronize(c->stream));   // the staging vector goes out of scope
+        }
+    }
     if (!c->red_f) {
         SF_CUDA(c, cudaMalloc(&c->red_f, sizeof(float)));
         SF_CUDA(c, cudaMalloc(&c->red_d, sizeof(double)));
@@ -69,6 +82,7 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
     L.chunk_rows = c->chunk_rows;
     L.zero_guess = zero_guess;
     L.staging = c->staging;
+    if (c->steal_opt && c->steal_now && c->steal) { L.steal = c->steal; L.steal_capacity = c->steal_capacity; }
     if (strip_rows > 0) {
         L.strips = slab_strip_args(c, xout, strip_rows);
         SF_REQUIRE(c, L.strips != nullptr, "peer slab: output field is not an arena field or strip too high");
@@ -134,7 +148,11 @@ int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const 
     alpha = alpha * fN;
     float beta = 4.0f * alpha;    // :180
     beta = 1.0f + beta;
+    // Density fields have compact support with a decaying front, where the exact division needs its
+    // guarded ticks: the one solve of a step whose warps are worth balancing (velocity fields are dense).
+    c->steal_now = true;
     int rc = lin_solve(c, 0, x0, x, alpha, beta, iters, 0);   // SWAP; diffuse(0, x, x0): solves into the old x0
+    c->steal_now = false;
     if (rc) return rc;
     SF_CUDA(c, launch_advect(c->g, 0, x, x0, u, v, dt, c->work));   // SWAP; advect(0, x, x0, u, v)
     ++c->launches;
@@ -189,7 +207,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.f[0] = f0; k.f[1] = f1; k.f[2] = f2;
     k.iters = iters;
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
-    k.opts[4] = c->staging;
+    k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0);
     return k;
 }
 
@@ -257,6 +275,7 @@ int sf_destroy(sf_context *c)
     for (auto &e : c->graphs) if (e.exec) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
     if (c->scratch && !c->scratch_in_arena) cudaFree(c->scratch);
     slab_release(c);
+    if (c->steal) cudaFree(c->steal);
     if (c->red_f) cudaFree(c->red_f);
     if (c->red_d) cudaFree(c->red_d);
     for (auto &s : c->stage) if (s) cudaFree(s);
@@ -281,6 +300,16 @@ int sf_set_option(sf_context *c, int option, int value)
         case SF_OPT_FORCE_GENERIC: c->force_generic = value ? 1 : 0; break;
         case SF_OPT_CHUNK_ROWS: SF_REQUIRE(c, value >= 0, "chunk rows >= 0"); c->chunk_rows = value; break;
         case SF_OPT_STAGING: SF_REQUIRE(c, value == 0 || value == 1, "staging: 0 cp.async / 1 bulk copy"); c->staging = value; break;
+        case SF_OPT_WORK_STEALING: {
+            SF_REQUIRE(c, value >= 0 && value <= 100, "work stealing: 0 = off, 1..100 = smallest remaining share of a chunk (percent) worth halving");
+            DeviceGuard guard(c->device);
+            int rc = ensure_scratch(c);
+            if (rc) return rc;
+            c->steal_opt = value;
+            SF_CUDA(c, cudaMemcpyAsync(&c->steal->min_pct, &c->steal_opt, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            SF_CUDA(c, cudaStreamSynchronize(c->stream));
+            break;
+        }
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }
     return SF_OK;
@@ -296,6 +325,16 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_FORCE_GENERIC: *value = c->force_generic; break;
         case SF_OPT_CHUNK_ROWS: *value = c->chunk_rows; break;
         case SF_OPT_STAGING: *value = c->staging; break;
+        case SF_OPT_WORK_STEALING: *value = c->steal_opt; break;
+        case SF_OPT_STEAL_COUNT: {   // diagnostics: row ranges taken over by another warp so far (synchronises)
+            *value = 0;
+            if (c->steal) {
+                DeviceGuard guard(c->device);
+                if (cudaStreamSynchronize(c->stream) != cudaSuccess ||
+                    cudaMemcpy(value, &c->steal->taken, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return SF_ERR_CUDA;
+            }
+            break;
+        }
         default: return SF_ERR_INVALID;
     }
     return SF_OK;
@@ -406,7 +445,10 @@ int sf_diffuse(sf_context *c, int b, float *x, const float *x0, float alpha, flo
     int rc = check_multi_launch_ok(c, iters);
     if (rc) return rc;
     if (is_linked_slab(c)) (void)arith_mode(c, alpha, beta);   // the divisor check synchronises: before anything is enqueued
-    return lin_solve(c, b, x, x0, alpha, beta, iters, 0);
+    c->steal_now = (b == 0);     // scalar (density-like) fields: see enqueue_dens_step
+    rc = lin_solve(c, b, x, x0, alpha, beta, iters, 0);
+    c->steal_now = false;
+    return rc;
 }
 
 int sf_advect(sf_context *c, int b, float *d, const float *d0, const float *u, const float *v, float dt)

@@ -160,6 +160,28 @@ struct StripArgs {
     unsigned long long timeout_ns = 0;
 };
 
+// ---- row-level work stealing between the warps of one Jacobi launch --------------------------------
+// All work items of a launch cost the same EXCEPT where the exact division needs its guarded
+// (binary64) ticks -- the decaying front of a density field -- and there a warp runs ~1.5-2x slower and
+// would set the duration of the whole single-wave launch.  Every warp therefore publishes the row range
+// it is working on; a warp that has finished samples a few slots, halves the largest remaining range
+// with a compare-and-swap on its end and processes the upper half with a fresh pipeline (temporal
+// blocking reads only level-0 rows, so a range can be split anywhere at the cost of 2T halo rows).
+// Double coverage is harmless: both warps would write bit-identical values.
+struct StealSlot {
+    int pos;    // input row the owner has reached (published every few ticks)
+    int end;    // one past the last output row the owner will produce; lowered by a thief
+    int band;
+    int tag;    // launch the slot belongs to (StealCtl::epoch + 1): stale slots are ignored
+};
+struct StealCtl {
+    int epoch;      // launches completed
+    int done;       // warps of the current launch that have finished
+    int min_pct;    // a range is only halved while at least this percentage of a chunk remains (and >= 64 rows)
+    int taken;      // statistics: ranges taken over
+    StealSlot slots[1];   // [capacity]
+};
+
 // ---- launch wrappers implemented in the .cu files (all enqueue on `st`, return cudaError_t) ----
 struct JacobiLaunch {
     const float *xin, *rhs;
@@ -176,6 +198,9 @@ struct JacobiLaunch {
     // for the host-side launch geometry, the strip heights it holds (0 = no strip on that side)
     const StripArgs *strips = nullptr;
     int strip_rows[2] = {0, 0};
+    // row-level work stealing (nullptr = off): device control block with room for steal_capacity items
+    StealCtl *steal = nullptr;
+    int steal_capacity = 0;
 };
 cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_count, cudaStream_t st);
 cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStream_t st);

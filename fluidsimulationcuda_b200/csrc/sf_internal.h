@@ -72,6 +72,10 @@ struct sf_context {
     int staging = 0;
     float *scratch = nullptr;        // lin_solve ping-pong partner (inside the arena for peer slabs)
     bool scratch_in_arena = false;
+    sf::StealCtl *steal = nullptr;   // row-level work stealing between the warps of a Jacobi launch
+    int steal_capacity = 0;
+    int steal_opt = 30;              // SF_OPT_WORK_STEALING (percent; 0 = off)
+    bool steal_now = false;          // set by the drivers around the solves that are worth it (see lin_solve)
     float *red_f = nullptr;          // reduction outputs
     double *red_d = nullptr;
     unsigned long long launches = 0;

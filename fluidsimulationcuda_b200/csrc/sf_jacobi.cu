@@ -38,6 +38,7 @@ namespace {
 constexpr int BAND_W = 128;   // columns per warp (32 lanes x float4)
 constexpr int HALO_X = 8;     // band halo columns on each side (>= max T, multiple of 4)
 constexpr int VALID_W = BAND_W - 2 * HALO_X;  // 112 output columns per band
+constexpr int STEAL_MIN_ROWS = 64;            // work stealing: smallest remaining range worth halving
 #ifndef SF_WPC
 #define SF_WPC 4
 #define SF_RING_X 8
@@ -66,7 +67,26 @@ struct StreamArgs {
     float hi_in;         // level-0 magnitudes up to this keep every numerator of the launch <= SF_DIV_HI
     DivConst div;        // beta and its reciprocals
     const StripArgs *strips;   // peer-memory slabs: the fused exchange of the top / bottom strip (device memory)
+    StealCtl *steal;           // row-level work stealing (VAR 3 / 4), device memory
 };
+
+// GPU-scope relaxed accesses for the stealing words (plain `volatile` would be system-scope strong accesses)
+__device__ __forceinline__ int ld_relaxed_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(int *p, int v)
+{
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
 
 // ---- fused strip exchange (peer-memory slabs) -----------------------------------------------------
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
@@ -251,7 +271,9 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
 // The streaming pipeline of one warp over output rows [a_lo, a_hi) of band `band`.
 // STRIP = true (peer-memory slabs): general ticks only, and every produced row is also stored at
 // peer + row * pitch, the neighbour GPU's copy of the field (pre-offset so that global row numbers index it).
-template <int T, int MODE, bool TMA, bool STRIP>
+// STEAL = true: the warp's slot (A.steal->slots[global warp]) holds its published range; the end may be
+// lowered by another warp at any time.
+template <int T, int MODE, bool TMA, bool STRIP, bool STEAL>
 __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, const int lane, const int warp, const int band,
                                             const int a_lo, const int a_hi, float *peer)
 {
@@ -387,6 +409,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
     // Everything else runs the wall-free tick in groups of three (one full rotation of the windows).
     const int fast_lo = T + 2;
     const int fast_hi = min(s_hi, A.N);
+    [[maybe_unused]] int end_seen = a_hi;    // STEAL: the slot's end as of the previous poll
     // an out-of-range numerator or an outlier row was seen: guarded ticks for the next rows.  Strip warps
     // (peer slabs) only ever take the general tick (which carries the neighbour push): they live for ~3T
     // ticks, and a strip copy with the fast tick was measured to cost the interior path registers.
@@ -403,6 +426,19 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
 
     int s = s_lo;
     while (s <= s_hi) {
+        if constexpr (STEAL) {
+            // once per 32 rows (the test hits exactly one s of any window of 32, in steps of 1 or 3): publish
+            // the progress and look at the slot's end.  Rows leave the pipeline in increasing order, so once
+            // every row below an end lowered by a thief has been emitted (s - T >= end) this warp is done;
+            // nothing else about the loop changes.  The load is consumed one poll LATER: no stall.
+            if (((s - a_lo) & 31) < 3) {
+                if (end_seen <= s - T) break;
+                // (the slot address is recomputed here rather than kept in registers across the hot loop)
+                StealSlot *slot = A.steal->slots + (blockIdx.x * WPC + (threadIdx.x >> 5));
+                if (lane == 0) st_relaxed_gpu(&slot->pos, s);
+                end_seen = ld_relaxed_gpu(&slot->end);
+            }
+        }
         // The guarded mode is left again every 64 rows: the numerators that need it (the decaying front of
         // a density field) occupy a band of rows, not the rest of a chunk of thousands of rows.  A retry
         // that fails costs one wasted optimistic tick per 64 guarded ones.
@@ -463,6 +499,78 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
     }
 }
 
+// ---- row-level work stealing (see StealSlot in sf_common.cuh) -------------------------------------
+// Out of line and self-contained (they recompute the warp's item from blockIdx / threadIdx), so that
+// nothing of the bookkeeping is live in registers across the streaming loop.
+__device__ __noinline__ void steal_publish(StealCtl *ctl, int band, int lo, int hi)
+{
+    if ((threadIdx.x & 31) == 0) {
+        StealSlot *slot = ctl->slots + (blockIdx.x * WPC + (threadIdx.x >> 5));
+        st_relaxed_gpu(&slot->end, hi); st_relaxed_gpu(&slot->band, band);
+        st_relaxed_gpu(&slot->tag, ld_relaxed_gpu(&ctl->epoch) + 1);
+        __threadfence();
+        st_relaxed_gpu(&slot->pos, lo);      // a stale slot has pos = 0x3fffffff: pos goes last
+    }
+    __syncwarp();
+}
+// The warp has finished its range: sample 32 slots per attempt and halve the largest remaining range
+// (returns the upper half in band / lo / hi), or close the warp's part of the launch and return false.
+// seg_lo / seg_hi: the launch's interior segment; a candidate that does not lie inside it is never touched.
+__device__ __noinline__ bool steal_next(StealCtl *ctl, int nitems, int chunk_rows, int seg_lo, int seg_hi, int &band, int &lo, int &hi)
+{
+    const int lane = threadIdx.x & 31, item = blockIdx.x * WPC + (threadIdx.x >> 5);
+    StealSlot *slot = ctl->slots + item;
+    const int tag = ld_relaxed_gpu(&ctl->epoch) + 1;
+    // only clear outliers are worth the 2T halo rows and the pipeline fill of a fresh start: warps of a
+    // balanced launch finish up to ~20 % apart anyway (the schedulers favour the oldest warp)
+    // (for chunks of thousands of rows a fresh start is cheap in proportion: the threshold stops growing at 256 rows)
+    const int steal_min = max(STEAL_MIN_ROWS, min(chunk_rows * ctl->min_pct / 100, 256));
+    if (lane == 0) st_relaxed_gpu(&slot->pos, 0x3fffffff);     // nothing left to take here
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int cand = (int)(((unsigned)item + 1u + (unsigned)lane * 37u + (unsigned)attempt * 1187u) % (unsigned)nitems);
+        const StealSlot *S = ctl->slots + cand;
+        // pos is written last by its owner (after a fence) and read first here: a valid pos vouches for the rest
+        const int cpos = ld_acquire_gpu(&S->pos);
+        const int ctag = ld_relaxed_gpu(&S->tag), cend = ld_relaxed_gpu(&S->end);
+        const bool valid = ctag == tag && cand != item && cpos >= seg_lo - HALO_X && cend <= seg_hi && cend > cpos;
+        const int rem = valid ? cend - cpos : 0;    // rows the owner has not reached yet
+        int best = rem, who = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, best, o), ow = __shfl_xor_sync(0xffffffffu, who, o);
+            if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; }
+        }
+        if (best < steal_min) continue;
+        int mid = 0, ok = 0;
+        if (lane == who) {
+            mid = cend - rem / 2;                       // the thief takes the upper half [mid, cend)
+            ok = (atomicCAS(&ctl->slots[cand].end, cend, mid) == cend) ? 1 : 0;
+            if (ok) atomicAdd(&ctl->taken, 1);
+        }
+        ok = __shfl_sync(0xffffffffu, ok, who);
+        if (ok) {
+            lo = __shfl_sync(0xffffffffu, mid, who);
+            hi = __shfl_sync(0xffffffffu, cend, who);
+            band = __shfl_sync(0xffffffffu, ld_relaxed_gpu(&S->band), who);
+            if (lane == 0) {     // the taken range is this warp's published range now
+                st_relaxed_gpu(&slot->end, hi); st_relaxed_gpu(&slot->band, band);
+                __threadfence();
+                st_relaxed_gpu(&slot->pos, lo);
+            }
+            __syncwarp();
+            return true;
+        }
+    }
+    if (lane == 0) {     // the last warp of the launch closes the epoch: the next launch ignores these slots
+        if (atomicAdd(&ctl->done, 1) == nitems - 1) {
+            st_relaxed_gpu(&ctl->done, 0);
+            __threadfence();
+            st_relaxed_gpu(&ctl->epoch, tag);
+        }
+    }
+    return false;
+}
+
 // VAR = 2: cp.async staging plus the fused strip exchange of peer-memory slabs.  The strip warps run
 // their own (out-of-line) copy of the pipeline, so the interior warps execute exactly the code of the
 // single-GPU kernel.
@@ -476,14 +584,14 @@ __device__ __noinline__ void strip_warp(const StreamArgs A, float4 *ring, const 
     const int a_lo = top ? S->o_lo : S->o_hi - P->rows;
     const int a_hi = top ? S->o_lo + P->rows : S->o_hi;
     float *peer = P->xpeer - (ptrdiff_t)P->peer_row_base * (ptrdiff_t)A.G;
-    stream_rows<T, MODE, false, true>(A, ring, lane, warp, top ? item0 : item0 - n_top, a_lo, a_hi, peer);
+    stream_rows<T, MODE, false, true, false>(A, ring, lane, warp, top ? item0 : item0 - n_top, a_lo, a_hi, peer);
     strip_post(P->arrive, P->seq, P->nbr_inbox, A.nbands, lane);
 }
 
 template <int T, int MODE, int VAR>
 __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
 {
-    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2);
+    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2 || VAR == 4), STEALS = (VAR == 3 || VAR == 4);
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.
@@ -495,12 +603,22 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
         const int n_top = S->port[0].rows > 0 ? A.nbands : 0, n_bot = S->port[1].rows > 0 ? A.nbands : 0;
         if (item < n_top + n_bot) strip_warp<T, MODE>(A, ring, lane, warp, item, n_top);
     }
-    if (item >= A.nbands * A.nchunks) return;
+    const int nitems = A.nbands * A.nchunks;
+    if (item >= nitems) return;
     const int band = item % A.nbands, chunk = item / A.nbands;
     const int a_lo = A.a_lo + chunk * A.chunk_rows;
     const int a_hi = min(a_lo + A.chunk_rows, A.a_hi);
-    if (a_lo >= a_hi) return;
-    stream_rows<T, MODE, TMA, false>(A, ring, lane, warp, band, a_lo, a_hi, nullptr);
+    if constexpr (!STEALS) {
+        if (a_lo >= a_hi) return;
+        stream_rows<T, MODE, TMA, false, false>(A, ring, lane, warp, band, a_lo, a_hi, nullptr);
+    } else {
+        int b = band, lo = a_lo, hi = a_hi;
+        steal_publish(A.steal, b, lo, hi);
+        for (;;) {
+            if (lo < hi) stream_rows<T, MODE, false, false, true>(A, ring, lane, warp, b, lo, hi, nullptr);
+            if (!steal_next(A.steal, nitems, A.chunk_rows, A.a_lo, A.a_hi, b, lo, hi)) break;
+        }
+    }
 }
 
 // ---- generic fallback: one sweep, one thread per interior cell, any G -----------------------
@@ -563,6 +681,14 @@ cudaError_t launch_stream_T(const StreamArgs &A, dim3 grid, size_t smem, bool tm
         jacobi_stream_kernel<TT, MM, 1><<<grid, WPC * 32, smem_tma, st>>>(A);
         return cudaGetLastError();
     }
+    if constexpr (MODE == MODE_STRICT) {
+        // work stealing is built for the one mode whose ticks have a data-dependent cost
+        if (A.steal != nullptr) {
+            if (A.strips != nullptr) jacobi_stream_kernel<T, MODE_STRICT, 4><<<grid, WPC * 32, smem, st>>>(A);
+            else jacobi_stream_kernel<T, MODE_STRICT, 3><<<grid, WPC * 32, smem, st>>>(A);
+            return cudaGetLastError();
+        }
+    }
     if (A.strips != nullptr) {
         // the peer-slab variant is built for the arithmetic modes a step uses
         if (MODE == MODE_FAST || MODE == MODE_IEEE) {
@@ -608,6 +734,10 @@ void preload_T(cudaFuncAttributes &a)
 {
     cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE, 0>);
     if (MODE != MODE_FAST) cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE == MODE_FAST ? MODE_IEEE : MODE, 2>);
+    if (MODE == MODE_STRICT) {
+        cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE_STRICT, 3>);
+        cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE_STRICT, 4>);
+    }
 }
 template <int MODE>
 void preload_mode()
@@ -705,6 +835,8 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     A.chunk_rows = chunk;
     A.nchunks = rows > 0 ? (rows + chunk - 1) / chunk : 0;
     const int items = max(n_strip_items, A.nbands * A.nchunks);   // strip warps go on to an interior item
+    A.steal = (L.steal != nullptr && L.mode == MODE_STRICT && L.staging != 1 && A.nbands * A.nchunks <= L.steal_capacity &&
+               A.nbands * A.nchunks > 1) ? L.steal : nullptr;
     dim3 grid((items + WPC - 1) / WPC);
     const size_t smem = (size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4);
     switch (L.mode) {

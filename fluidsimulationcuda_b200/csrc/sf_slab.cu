@@ -313,7 +313,9 @@ int slab_dens_step(sf_context *c, float *x, float *x0, const float *u, const flo
     alpha = alpha * fN;
     float beta = 4.0f * alpha;    // :180
     beta = 1.0f + beta;
+    c->steal_now = true;          // see enqueue_dens_step
     int rc = slab_lin_solve(c, 0, x0, x, alpha, beta, iters, 0);      // :182
+    c->steal_now = false;
     if (rc) return rc;
     return slab_advect(c, 0, x, x0, u, v, dt, true);                   // :185
 }

@@ -28,6 +28,8 @@ SF_OPT_USE_GRAPH = 3
 SF_OPT_FORCE_GENERIC = 4
 SF_OPT_CHUNK_ROWS = 5
 SF_OPT_STAGING = 6
+SF_OPT_WORK_STEALING = 7
+SF_OPT_STEAL_COUNT = 8
 STRICT, FAST = 0, 1
 
 # every symbol include/stablefluids.h declares (tests/test_abi.py checks the library exports them)
@@ -210,6 +212,11 @@ class StableFluids:
 
     def set_option(self, opt: int, value: int):
         self._check(self.L.sf_set_option(self.h, opt, int(value)))
+
+    def get_option(self, opt: int) -> int:
+        v = C.c_int(0)
+        self._check(self.L.sf_get_option(self.h, opt, C.byref(v)))
+        return int(v.value)
 
     def new_field(self):
         return self.torch.zeros((self.local_rows, self.G), dtype=self.torch.float32, device=f"cuda:{self.device}")

@@ -66,7 +66,15 @@ enum {
     SF_OPT_CHUNK_ROWS = 5,
     /* how the Jacobi kernel stages rows global -> shared: 0 (default) = cp.async per lane
      * (LDGSTS.128), 1 = one bulk copy per warp row through the TMA unit (cp.async.bulk + mbarrier). */
-    SF_OPT_STAGING = 6
+    SF_OPT_STAGING = 6,
+    /* > 0 (default 30): the warps of a STRICT Jacobi launch on a scalar field (dens_step's solve,
+     * sf_diffuse with b = 0) balance their load by row-level work stealing: a warp that has finished
+     * halves the largest remaining row range it finds.  Evens out the guarded binary64 ticks that the
+     * decaying front of a density field needs.  The value is the smallest remaining share of a chunk,
+     * in percent, that is worth halving (1..100); 0 = off.  Results are unchanged. */
+    SF_OPT_WORK_STEALING = 7,
+    /* read-only (sf_get_option): row ranges taken over by another warp so far; synchronises. */
+    SF_OPT_STEAL_COUNT = 8
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 

@@ -408,3 +408,48 @@ def test_run_steps_synthetic_schedule_equals_explicit_refresh(SF):
     torch.cuda.synchronize()
     for x, y, n in zip(fa, fb, names):
         assert bits_equal(host(x), host(y)), n
+
+
+# ---- row-level work stealing (SF_OPT_WORK_STEALING): same bits, whatever the warps steal ---------------
+@pytest.mark.parametrize("N,K", [(254, 20), (1022, 20), (2046, 13)])
+def test_work_stealing_is_bit_identical(SF, oracle_mt, N, K):
+    import torch
+    rng = np.random.default_rng(N)
+    G = N + 2
+    x = rnd(rng, G, 0.0, 1.0)
+    x0 = rnd(rng, G, 0.0, 1.0)
+    # a block of tiny values (down to subnormals): the guarded binary64 ticks make the warps that own it
+    # slower than the rest, which is what the stealing evens out
+    x[G // 4: G // 2, G // 3: G // 2] *= np.float32(1e-37)
+    x0[G // 4: G // 2, G // 3: G // 2] *= np.float32(1e-38)
+    x0[G // 2:, :] = 0.0
+    x[G // 2:, :] = 0.0
+    al, be = 2683.2, 10733.8
+    for chunk in (0, 32):
+        s = SF.StableFluids(N, use_graph=False)
+        s.set_option(SF.SF_OPT_WORK_STEALING, 1 if chunk else 30)
+        s.set_option(SF.SF_OPT_CHUNK_ROWS, chunk)
+        dx, dx0 = dev(x), dev(x0)
+        want = x.copy()
+        oracle_mt.diffuse(N, 0, want, x0, al, be, K)
+        for rep in range(3):          # epochs advance launch after launch
+            dx.copy_(torch.from_numpy(x).cuda())
+            s.diffuse(0, dx, dx0, al, be, K)
+            torch.cuda.synchronize()
+            assert_same(host(dx), want, f"stealing chunk={chunk} rep={rep}")
+        s.close()
+
+
+def test_work_stealing_full_step(SF, oracle_mt):
+    import torch
+    N, K = 1022, 20
+    names = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
+    s = SF.StableFluids(N)
+    s.set_option(SF.SF_OPT_WORK_STEALING, 1)
+    w = oracle_mt.init_synthetic(N, 3)
+    f = {k: dev(w[k]) for k in names}
+    s.run_steps(*[f[k] for k in names], VIS, DIFF, DT, K, 4, SF.SOURCES_REFERENCE)
+    oracle_mt.run_steps(N, 4, w, VIS, DIFF, DT, K)
+    torch.cuda.synchronize()
+    for k in names:
+        assert_same(host(f[k]), w[k], k)

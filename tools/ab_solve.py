@@ -17,6 +17,8 @@ for T in (6, 7):
         print(f"T={T} {mode:8s} min {min(ts):8.3f} ms  median {sorted(ts)[3]:8.3f}", flush=True)
         s.close()
 s = SF.StableFluids(G - 2)
+if os.environ.get("SF_STEAL"):
+    s.set_option(SF.SF_OPT_WORK_STEALING, int(os.environ["SF_STEAL"]))
 f = [s.new_field() for _ in range(6)]
 s.init_synthetic(1, *f)
 for i in range(4):

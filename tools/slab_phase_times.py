@@ -18,6 +18,8 @@ DT, VIS, DIFF = 0.016, 0.0025, 0.1
 s = PeerSlabSolver(N, rank, world, iters=K, use_graph=False)
 if world > 1:
     s.connect_dist()
+if os.environ.get("SF_STEAL"):
+    s.ctx.set_option(SF.SF_OPT_WORK_STEALING, int(os.environ["SF_STEAL"]))
 s.init_synthetic(1)
 for i in range(3):
     s.step(100 + i, VIS, DIFF, DT)
