@@ -317,9 +317,35 @@ def run_ours(args):
         except Exception as e:
             out["e2e"] = {"value": None, "unit": "cell-updates/s", "error": repr(e)}
         out["cpu_baseline"] = cpu_baseline(G, K)
+    elif world > 1 and args.slab_comm == "peer" and not args.skip_extras:
+        # ---- end to end on N GPUs: every rank keeps its slab of the six fields in pinned host memory;
+        # per step it uploads them, steps (collectively) and downloads dens, u, v -- all inside the timed region
+        try:
+            hf = sim.new_host_fields()
+            for h, name in zip(hf, sim.names):
+                h.copy_(sim.owned(sim.f[name]))
+            torch.cuda.synchronize(); dist.barrier()
+            sim.step_host(hf, VIS, DIFF, DT)
+            torch.cuda.synchronize(); dist.barrier()
+            n_e2e = 3
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                sim.step_host(hf, VIS, DIFF, DT)
+            sim.status()
+            dt_ = (time.perf_counter() - t0) / n_e2e
+            tt = torch.tensor([dt_], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt_ = float(tt.item())
+            out["e2e"] = {"value": 5.0 * K * N * N / dt_, "unit": "cell-updates/s", "ms_per_step": dt_ * 1e3,
+                          "h2d_bytes_per_step": 6 * cells * 4, "d2h_bytes_per_step": 3 * cells * 4,
+                          "api": "PeerSlabSolver.step_host: every rank uploads its slab of the six pinned host fields, steps, "
+                                 "downloads dens/u/v (bytes are the sum over ranks; max over ranks of the wall time)"}
+            del hf
+        except Exception as e:
+            out["e2e"] = {"value": None, "unit": "cell-updates/s", "error": repr(e)}
     elif rank == 0:
         out["e2e"] = {"value": None, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                      "note": "host-buffer entry point is single-GPU; see the N=1 line"}
+                      "note": "not measured in this run (--skip-extras or --slab-comm nccl); see the N=1 line"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -499,6 +499,53 @@ class PeerSlabSolver(SlabLayout):
                 self.ctx.init_sources(seed, f["dens_prev"], f["u_prev"], f["v_prev"])
             self.ctx.step(f["dens"], f["dens_prev"], f["u"], f["u_prev"], f["v"], f["v_prev"], visc, diff, dt, self.iters)
 
+    def new_host_fields(self):
+        """Six pinned host arrays holding this rank's OWNED rows (own_rows, G), in NAMES order."""
+        t = self.torch
+        return [t.empty((self.own_rows, self.G), dtype=t.float32, pin_memory=True).zero_() for _ in self.NAMES]
+
+    def step_host(self, host_fields, visc: float, diff: float, dt: float):
+        """``step_host_begin`` + ``step_host_end`` (one process per GPU)."""
+        self.step_host_begin(host_fields, visc, diff, dt)
+        self.step_host_end()
+
+    def step_host_end(self):
+        """Returns when the host arrays of the step begun last are valid."""
+        self._d2h.synchronize()
+
+    def step_host_begin(self, host_fields, visc: float, diff: float, dt: float):
+        """The loop body for a caller whose fields live in HOST memory (the reference's CPU calling
+        convention, FluidSequential.c:305-306), per slab: upload the owned rows of the six fields, step,
+        download dens, u, v.  Enqueues only (several slabs of one process must all have begun before anyone
+        waits); ``step_host_end`` waits.  Collective like ``step``.
+        Ghost rows need no upload: every stage that reads them refreshes them from the neighbour first."""
+        t, f = self.torch, self.f
+        if not hasattr(self, "_h2d"):
+            self._h2d, self._d2h = t.cuda.Stream(device=self.ctx.device), t.cuda.Stream(device=self.ctx.device)
+        h = dict(zip(self.NAMES, host_fields))
+        up = lambda name: self.owned(f[name]).copy_(h[name], non_blocking=True)
+        down = lambda name: h[name].copy_(self.owned(f[name]), non_blocking=True)
+        self._h2d.wait_stream(self.stream)           # the previous step is done with the device fields
+        with t.cuda.stream(self._h2d):               # velocity first: vel_step starts while the density fields travel
+            for name in ("u", "u_prev", "v", "v_prev"):
+                up(name)
+            vel_in = t.cuda.Event(); vel_in.record(self._h2d)
+            for name in ("dens", "dens_prev"):
+                up(name)
+            dens_in = t.cuda.Event(); dens_in.record(self._h2d)
+        with t.cuda.stream(self.stream):
+            self.stream.wait_event(vel_in)
+            self.ctx.vel_step(f["u"], f["v"], f["u_prev"], f["v_prev"], visc, dt, self.iters)
+            vel_out = t.cuda.Event(); vel_out.record(self.stream)
+            self.stream.wait_event(dens_in)
+            self.ctx.dens_step(f["dens"], f["dens_prev"], f["u"], f["v"], diff, dt, self.iters)
+            dens_out = t.cuda.Event(); dens_out.record(self.stream)
+        with t.cuda.stream(self._d2h):               # u, v drain while dens_step runs
+            self._d2h.wait_event(vel_out)
+            down("u"); down("v")
+            self._d2h.wait_event(dens_out)
+            down("dens")
+
     def status(self) -> int:
         """Synchronise; raise if a neighbour barrier timed out or a back-trace left the neighbour's slab."""
         bits = self.ctx.slab_status() if self.world > 1 else 0

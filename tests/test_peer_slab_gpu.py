@@ -105,6 +105,36 @@ def test_peer_slab_long_reach_advect(oracle):
         s.close()
 
 
+def test_peer_slab_host_field_step(oracle):
+    """step_host: every slab uploads its rows of the six pinned host fields, steps, downloads dens/u/v."""
+    N, K, world = 254, 12, 2
+    solvers = make(N, world, K)
+    w = oracle.init_synthetic(N, 8)
+    hosts = []
+    for s in solvers:
+        hf = s.new_host_fields()
+        for h, name in zip(hf, s.names):
+            h.copy_(torch.from_numpy(w[name][s.row_lo:s.row_hi]))
+        hosts.append(hf)
+    for step in range(3):
+        for s, hf in zip(solvers, hosts):
+            s.step_host_begin(hf, VIS, DIFF, DT)
+        for s in solvers:
+            s.step_host_end()
+        oracle.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=0)
+        for i, name in enumerate(solvers[0].names):
+            if name in ("dens", "u", "v"):
+                got = torch.cat([hf[i] for hf in hosts], dim=0).numpy()
+                assert bits_equal(got, w[name]), mismatch_report(got, w[name], f"step {step} {name}")
+        # the *_prev host arrays were not downloaded: they still hold the sources; mirror that in the oracle
+        for i, name in enumerate(solvers[0].names):
+            if name.endswith("_prev"):
+                w[name][...] = torch.cat([hf[i] for hf in hosts], dim=0).numpy()
+    for s in solvers:
+        s.status()
+        s.close()
+
+
 def test_missing_neighbour_times_out_instead_of_hanging():
     from fluidsimulationcuda_b200.slab import PeerSlabSolver
     from fluidsimulationcuda_b200.solver import StableFluidsError
