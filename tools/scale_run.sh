@@ -1,9 +1,9 @@
 #!/bin/bash
-# Strong-scaling runs on one box.  usage: scale_run.sh "<G> <K> <steps>" "1 2 4 8"   (run under gpurun --gpus 8)
+# Strong-scaling runs on one box.  usage: scale_run.sh "<G> <K> <steps>" "1 2 4 8" [extra bench flags]   (run under gpurun --gpus 8)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 set -- $1 "$2"
-G=$1; K=$2; S=$3; NS=$4
+G=$1; K=$2; S=$3; NS=$4; EXTRA=$5
 port=$((29600 + RANDOM % 200))
 for n in $NS; do
   port=$((port+1))
@@ -12,7 +12,7 @@ for n in $NS; do
     python bench.py --grid $G --iters $K --steps $S --warmup 3 --skip-extras > $out 2> ${out%.json}.err
   else
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
-      bench.py --gpus $n --grid $G --iters $K --steps $S --warmup 3 > $out 2> ${out%.json}.err
+      bench.py --gpus $n --grid $G --iters $K --steps $S --warmup 3 $EXTRA > $out 2> ${out%.json}.err
   fi
   python - "$out" <<'PY'
 import json,sys
