@@ -106,7 +106,7 @@ class SlabSolver(SlabLayout):
     """One rank's slab.  Fields are local tensors of (own_rows + 2*halo, G)."""
 
     def __init__(self, N: int, rank: int, world: int, *, iters: int = 40, halo: int = 0, arithmetic: int = SF.STRICT,
-                 sweeps_per_launch: int = 8, device: Optional[int] = None, comm=None, allocate: bool = True,
+                 sweeps_per_launch: int = 7, device: Optional[int] = None, comm=None, allocate: bool = True,
                  overlap: bool = True, deferred_reach: bool = True):
         SlabLayout.__init__(self, N + 2, rank, world, 0)
         self.N = N
@@ -425,15 +425,16 @@ class PeerSlabSolver(SlabLayout):
     NAMES = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
 
     def __init__(self, N: int, rank: int, world: int, *, iters: int = 40, halo: int = 8, arithmetic: int = SF.STRICT,
-                 sweeps_per_launch: int = 8, device: Optional[int] = None, stream=None, use_graph: bool = True,
+                 sweeps_per_launch: int = 0, device: Optional[int] = None, stream=None, use_graph: bool = True,
                  timeout_ms: Optional[int] = None):
         if world == 1:
             halo = 0
         SlabLayout.__init__(self, N + 2, rank, world, halo)
         self.N, self.iters, self.names = N, iters, self.NAMES
-        if world > 1 and halo < sweeps_per_launch:
+        depth = sweeps_per_launch or 8            # 0 = the library's default depth (at most 8)
+        if world > 1 and halo < depth:
             raise ValueError("halo must cover the temporal-blocking depth")
-        if world > 1 and self.own_rows < 2 * sweeps_per_launch:
+        if world > 1 and self.own_rows < 2 * depth:
             raise ValueError("slab thinner than two boundary strips")
         import torch
         self.torch = torch
