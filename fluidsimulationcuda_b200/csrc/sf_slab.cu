@@ -4,12 +4,13 @@
 // B200-first design, not NCCL send/recv around single-GPU kernels:
 //   * every slab keeps its fields in ONE device allocation (the arena) that its two neighbours map
 //     (CUDA IPC between processes, plain peer access inside one process);
-//   * lin_solve: every temporally blocked launch is ONE kernel that computes AND exchanges.  Its first
-//     work items are the two boundary strips (one warp per 128-column band and side): they wait for
-//     the neighbour's previous strips (acquire on a word the neighbour posts to), store the rows they
-//     produce STRAIGHT INTO THE NEIGHBOUR'S GHOST ROWS over NVLink as well as locally, and the last
-//     strip warp to finish posts the new count to the neighbour (release, system scope).  All other
-//     warps are interior work items that never touch a ghost row and never wait;
+//   * lin_solve: every temporally blocked launch is ONE kernel that computes AND exchanges.  The first
+//     warps of its grid start with a boundary strip (one warp per 128-column band and side): they wait
+//     for the neighbour's previous strips (acquire on a word the neighbour posts to), store the rows
+//     they produce STRAIGHT INTO THE NEIGHBOUR'S GHOST ROWS over NVLink as well as locally, and the last
+//     strip warp to finish posts the new count to the neighbour (release, system scope).  Then they
+//     take an interior work item like every other warp; interior items never touch a ghost row and
+//     never wait;
 //   * advect: no halo exchange at all -- a back-trace that leaves the slab reads the neighbour's rows
 //     through the peer mapping (advect4_peer_kernel);
 //   * the few remaining exchanges (right-hand sides, one row of u, v) are a push kernel between two
