@@ -412,6 +412,28 @@ def run_lockstep(solvers: Sequence[SlabSolver], visc: float, diff: float, dt: fl
 # =================================================================================================
 # Peer-memory slabs: the product path on an NVLink / NVSwitch box
 # =================================================================================================
+def neighbour_links(G: int, rank: int, world: int, handles: Sequence[bytes]):
+    """Which arenas rank `rank` maps, given every rank's 64-byte handle:
+    [(SF_SLAB_UP | SF_SLAB_DOWN, handle, neighbour_row_lo, neighbour_row_hi)]."""
+    parts = partition_rows(G, world)
+    links = []
+    if rank > 0:
+        links.append((SF.SF_SLAB_UP, handles[rank - 1], *parts[rank - 1]))
+    if rank < world - 1:
+        links.append((SF.SF_SLAB_DOWN, handles[rank + 1], *parts[rank + 1]))
+    return links
+
+
+def exchange_handles(G: int, rank: int, world: int, my_handle: bytes, group=None):
+    """All-gather the handles over torch.distributed (any backend) and return this rank's links."""
+    import torch.distributed as dist
+    if len(my_handle) != 64:
+        raise ValueError("a CUDA IPC memory handle is 64 bytes")
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(my_handle), group=group)
+    return neighbour_links(G, rank, world, handles)
+
+
 class PeerSlabSolver(SlabLayout):
     """One rank's slab with its neighbours' memory mapped (CUDA IPC between processes, peer access
     inside one process).  The whole step -- halo pushes fused into the boundary strips of every
@@ -472,13 +494,8 @@ class PeerSlabSolver(SlabLayout):
         import torch.distributed as dist
         if self.world == 1:
             return
-        handles = [None] * self.world
-        dist.all_gather_object(handles, self.ctx.ipc_handle(), group=group)
-        parts = partition_rows(self.G, self.world)
-        if self.rank > 0:
-            self.ctx.connect_ipc(SF.SF_SLAB_UP, handles[self.rank - 1], *parts[self.rank - 1])
-        if self.rank < self.world - 1:
-            self.ctx.connect_ipc(SF.SF_SLAB_DOWN, handles[self.rank + 1], *parts[self.rank + 1])
+        for direction, handle, lo, hi in exchange_handles(self.G, self.rank, self.world, self.ctx.ipc_handle(), group):
+            self.ctx.connect_ipc(direction, handle, lo, hi)
         dist.barrier(group=group)       # every arena is mapped before anyone enqueues a push
 
     # ---- drivers -----------------------------------------------------------------------------

@@ -9,8 +9,9 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fluidsimulationcuda_b200.slab import (HaloSpec, SlabLayout, TorchDistComm, f32_coeffs, partition_rows,
-                                            plan_launches)
+from fluidsimulationcuda_b200.slab import (HaloSpec, SlabLayout, TorchDistComm, exchange_handles, f32_coeffs,
+                                            neighbour_links, partition_rows, plan_launches)
+from fluidsimulationcuda_b200 import solver as SF
 
 
 def test_partition_covers_grid():
@@ -84,3 +85,38 @@ def _worker(rank, world, port, G, halo, h):
 def test_halo_exchange_gloo(world):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, 48, 6, 4), nprocs=world, join=True)
+
+
+# ---- peer-memory slabs: the only host-side communication is the exchange of the arenas' IPC handles ----
+def test_neighbour_links():
+    G = 1024
+    hs = [bytes([r]) * 64 for r in range(4)]
+    assert neighbour_links(G, 0, 4, hs) == [(SF.SF_SLAB_DOWN, hs[1], 256, 512)]
+    assert neighbour_links(G, 2, 4, hs) == [(SF.SF_SLAB_UP, hs[1], 256, 512), (SF.SF_SLAB_DOWN, hs[3], 768, 1024)]
+    assert neighbour_links(G, 3, 4, hs) == [(SF.SF_SLAB_UP, hs[2], 512, 768)]
+    assert neighbour_links(G, 0, 1, hs[:1]) == []
+
+
+def _handle_worker(rank, world, port, G):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = bytes([rank + 1]) * 64                     # stands in for cudaIpcGetMemHandle's 64 bytes
+        links = exchange_handles(G, rank, world, mine)
+        parts = partition_rows(G, world)
+        want = []
+        if rank > 0:
+            want.append((SF.SF_SLAB_UP, bytes([rank]) * 64, *parts[rank - 1]))
+        if rank < world - 1:
+            want.append((SF.SF_SLAB_DOWN, bytes([rank + 2]) * 64, *parts[rank + 1]))
+        assert links == want, (rank, links, want)
+        with pytest.raises(ValueError):
+            exchange_handles(G, rank, world, b"short")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ipc_handle_exchange_gloo(world):
+    port = _free_port()
+    mp.spawn(_handle_worker, args=(world, port, 130), nprocs=world, join=True)
