@@ -453,3 +453,36 @@ def test_work_stealing_full_step(SF, oracle_mt):
     torch.cuda.synchronize()
     for k in names:
         assert_same(host(f[k]), w[k], k)
+
+
+# ---- out-of-bounds guard: canaries around every field stay untouched ------------------------------------
+@pytest.mark.parametrize("N,K", [(254, 20), (1022, 9), (128, 6)])
+def test_no_write_outside_the_fields(SF, oracle_mt, N, K):
+    """The six fields are carved out of one buffer with canary bands between them (compute-sanitizer is not
+    available on the GPU pool): two whole steps -- graphs, work stealing, fused boundaries -- must leave
+    every canary word intact and still match the oracle."""
+    import torch
+    G = N + 2
+    cells, pad = G * G, 4096 + 4 * ((G * 3) // 4)     # pads keep every field 16-byte aligned
+    names = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
+    buf = torch.full((pad + len(names) * (cells + pad),), float("nan"), dtype=torch.float32, device="cuda")
+    canary = buf.view(torch.int32)
+    canary.fill_(0x7FC0DEAD)
+    f = {}
+    for i, k in enumerate(names):
+        lo = pad + i * (cells + pad)
+        f[k] = buf[lo: lo + cells].view(G, G)
+    w = oracle_mt.init_synthetic(N, 21)
+    for k in names:
+        f[k].copy_(torch.from_numpy(w[k]))
+    s = SF.StableFluids(N)
+    s.run_steps(*[f[k] for k in names], VIS, DIFF, DT, K, 3, SF.SOURCES_REFERENCE)
+    oracle_mt.run_steps(N, 3, w, VIS, DIFF, DT, K)
+    torch.cuda.synchronize()
+    for k in names:
+        assert_same(host(f[k]), w[k], k)
+    flat = canary.cpu().numpy()
+    for i in range(len(names) + 1):
+        lo = i * (cells + pad)
+        band = flat[lo: lo + pad]
+        assert (band == 0x7FC0DEAD).all(), f"canary band {i} was written ({int((band != 0x7FC0DEAD).sum())} words)"
