@@ -175,6 +175,32 @@ int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int
     return SF_OK;
 }
 
+// vel_step in three pieces, so that a caller whose fields arrive one by one (sf_step_host) can start the u
+// solve while v is still in flight: viscosity solve of one component (add_source + lin_solve, :193-210) ...
+int enqueue_vel_diffuse(sf_context *c, int b, float *x, float *x0, float visc, float dt, int iters)
+{
+    float *xs[1] = {x};
+    const float *ss[1] = {x0};
+    SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->work));
+    ++c->launches;
+    const float fN = (float)c->g.N;
+    float alpha = dt * visc;      // :199
+    alpha = alpha * fN;
+    alpha = alpha * fN;
+    float beta = 4.0f * alpha;    // :200
+    beta = 1.0f + beta;
+    return lin_solve(c, b, x0, x, alpha, beta, iters, 0);
+}
+// ... and everything after the two solves (:213-240)
+int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, float dt, int iters)
+{
+    int rc = enqueue_project(c, u0, v0, u, v, iters);                  // :213-223 (p in u, div in v)
+    if (rc) return rc;
+    SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, c->work));   // :228-237
+    ++c->launches;
+    return enqueue_project(c, u, v, u0, v0, iters);                    // :238-240 (p in u0, div in v0)
+}
+
 int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
 {
     if (is_linked_slab(c)) return slab_vel_step(c, u, v, u0, v0, visc, dt, iters);
@@ -566,9 +592,11 @@ int sf_step_host(sf_context *c, float *dens, float *dens_prev, float *u, float *
     // the previous call's work on the compute stream must be done before staging is overwritten
     SF_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     SF_CUDA(c, cudaStreamWaitEvent(c->h2d, c->ev[5], 0));
-    // velocity inputs first: vel_step can start while the density fields are still in flight
+    // u first, then v, then the density fields: the u solve starts while v is still in flight, the rest of
+    // vel_step while the density fields are
     SF_CUDA(c, cudaMemcpyAsync(d_u, u, bytes, cudaMemcpyHostToDevice, c->h2d));
     SF_CUDA(c, cudaMemcpyAsync(d_u0, u_prev, bytes, cudaMemcpyHostToDevice, c->h2d));
+    SF_CUDA(c, cudaEventRecord(c->ev[4], c->h2d));
     SF_CUDA(c, cudaMemcpyAsync(d_v, v, bytes, cudaMemcpyHostToDevice, c->h2d));
     SF_CUDA(c, cudaMemcpyAsync(d_v0, v_prev, bytes, cudaMemcpyHostToDevice, c->h2d));
     SF_CUDA(c, cudaEventRecord(c->ev[0], c->h2d));
@@ -576,8 +604,13 @@ int sf_step_host(sf_context *c, float *dens, float *dens_prev, float *u, float *
     SF_CUDA(c, cudaMemcpyAsync(d_dens0, dens_prev, bytes, cudaMemcpyHostToDevice, c->h2d));
     SF_CUDA(c, cudaEventRecord(c->ev[1], c->h2d));
 
+    SF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[4], 0));
+    rc = run_graphed(c, make_key(c, 4, {d_u, d_u0}, visc, dt, 0.f, iters), [&] { return enqueue_vel_diffuse(c, 1, d_u, d_u0, visc, dt, iters); });
+    if (rc) return rc;
     SF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[0], 0));
-    rc = sf_vel_step(c, d_u, d_v, d_u0, d_v0, visc, dt, iters);
+    rc = run_graphed(c, make_key(c, 5, {d_v, d_v0}, visc, dt, 0.f, iters), [&] { return enqueue_vel_diffuse(c, 2, d_v, d_v0, visc, dt, iters); });
+    if (rc) return rc;
+    rc = run_graphed(c, make_key(c, 6, {d_u, d_v, d_u0, d_v0}, dt, 0.f, 0.f, iters), [&] { return enqueue_vel_tail(c, d_u, d_v, d_u0, d_v0, dt, iters); });
     if (rc) return rc;
     SF_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     SF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[1], 0));

@@ -135,6 +135,8 @@ int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, floa
 int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters);
 int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters);
 int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters);
+int enqueue_vel_diffuse(sf_context *c, int b, float *x, float *x0, float visc, float dt, int iters);
+int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, float dt, int iters);
 GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const void *> ptrs, float f0, float f1, float f2, int iters);
 
 // ---- implemented in sf_slab.cu (peer-memory slabs; every rank must issue the same call sequence) ----
