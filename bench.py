@@ -266,6 +266,10 @@ def run_ours(args):
         "effective_hbm_gbs": eff_gbs, "effective_hbm_frac_of_measured_peak": eff_gbs / (peak * world),
         "gpu_launches": n_launch, "clocks": clocks,
     }
+    if world > 1:
+        out["scaling_note"] = (f"strong scaling of the G={G} problem over {world} GPUs; the N=1 bench line runs G=8192 (the size the "
+                               "metric is quoted on), so compare with the single-GPU time of THIS problem in "
+                               "profiles/r01_scaling/README.md (G=32768, K=40: 151.4 ms/step; G=16384, K=200: 156.6 ms/step)")
 
     if world == 1 and not args.skip_extras:
         # ---- roofline of the dominant kernel: jacobi_stream_kernel, timed per lin_solve with CUDA events on
