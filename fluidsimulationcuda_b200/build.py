@@ -38,14 +38,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), target: str = LIB) -> str:
     """One nvcc -c per source file, in parallel (sf_jacobi.cu with its ~150 kernel instantiations dominates),
-    then one link step.  No relocatable device code is needed: no device function crosses a file."""
-    if not force and not needs_build():
+    then one link step.  No relocatable device code is needed: no device function crosses a file.
+    `extra_flags` / `target` build an experimental variant next to the product library (A/B timing through
+    SF_LIBRARY, see solver.load_library): `python -m fluidsimulationcuda_b200.build --out build/x.so -DSF_PACKED_F32=0`."""
+    if target == LIB and not extra_flags and not force and not needs_build():
         return LIB
     import tempfile
     from concurrent.futures import ThreadPoolExecutor
-    base = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"]
+    base = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags)
     if os.path.exists("/usr/bin/g++"):
         base += ["-ccbin", "/usr/bin/g++"]    # this image's $CC/$CXX wrapper lacks pieces the host pass needs
     if verbose:
@@ -62,7 +64,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out = "".join(r.stdout for r in results)
         ok = all(r.returncode == 0 for r in results)
         if ok:
-            link = [_nvcc(), "-shared", "-o", LIB] + objs
+            os.makedirs(os.path.dirname(os.path.abspath(target)), exist_ok=True)
+            link = [_nvcc(), "-shared", "-o", target] + objs
             if os.path.exists("/usr/bin/g++"):
                 link += ["-ccbin", "/usr/bin/g++"]
             r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -72,8 +75,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stdout.write(out)
     if not ok:
         raise RuntimeError("nvcc failed building libstablefluids_b200.so")
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    argv = sys.argv[1:]
+    target = LIB
+    if "--out" in argv:
+        k = argv.index("--out")
+        target = os.path.abspath(argv[k + 1])
+        del argv[k:k + 2]
+    print(build(force="--force" in argv, verbose="--verbose" in argv,
+                extra_flags=[a for a in argv if a.startswith("-D")], target=target))

@@ -84,7 +84,7 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
     L.chunk_rows = c->chunk_rows;
     L.zero_guess = zero_guess;
     L.staging = c->staging;
-    if (c->steal_opt && c->steal_now && c->steal) { L.steal = c->steal; L.steal_capacity = c->steal_capacity; }
+    if (c->steal_opt && (c->steal_now || c->steal_scope == 1) && c->steal) { L.steal = c->steal; L.steal_capacity = c->steal_capacity; }
     if (strip_rows > 0) {
         L.strips = slab_strip_args(c, xout, strip_rows);
         SF_REQUIRE(c, L.strips != nullptr, "peer slab: output field is not an arena field or strip too high");
@@ -235,7 +235,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.f[0] = f0; k.f[1] = f1; k.f[2] = f2;
     k.iters = iters;
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
-    k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0);
+    k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope;
     return k;
 }
 
@@ -338,6 +338,7 @@ int sf_set_option(sf_context *c, int option, int value)
             SF_CUDA(c, cudaStreamSynchronize(c->stream));
             break;
         }
+        case SF_OPT_STEAL_SCOPE: SF_REQUIRE(c, value == 0 || value == 1, "steal scope: 0 scalar fields / 1 every strict solve"); c->steal_scope = value; break;
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }
     return SF_OK;
@@ -354,6 +355,7 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_CHUNK_ROWS: *value = c->chunk_rows; break;
         case SF_OPT_STAGING: *value = c->staging; break;
         case SF_OPT_WORK_STEALING: *value = c->steal_opt; break;
+        case SF_OPT_STEAL_SCOPE: *value = c->steal_scope; break;
         case SF_OPT_STEAL_COUNT: {   // diagnostics: row ranges taken over by another warp so far (synchronises)
             *value = 0;
             if (c->steal) {

@@ -44,12 +44,14 @@ enum ArithMode {
 #define SF_DIV_HI 1e30f
 struct DivConst {
     float b, y;      // divisor, RN32(1/b)
+    float nz, pad;   // -0.0f as a RUN-TIME value (see mul2_exact)
     double bd, yd;   // (double)b, RN64(1/b)
 };
 inline DivConst make_div_const(float b)
 {
     DivConst d;
     d.b = b; d.y = 1.0f / b;
+    d.nz = -0.0f; d.pad = 0.0f;
     d.bd = (double)b; d.yd = 1.0 / (double)b;
     return d;
 }
@@ -84,6 +86,56 @@ __device__ __forceinline__ float div_const(float a, const DivConst &d)
     return div_in_range(a) ? q : div_const_slow(a, d);
 }
 
+// ---- packed binary32 pairs ------------------------------------------------------------------------
+// sm_100 has two-wide binary32 instructions (PTX add/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2) that
+// work on an even-aligned register pair: each half is an ordinary IEEE round-to-nearest operation (no
+// flush to zero), so results are bit-identical to the scalar instruction -- at half the issue slots, which
+// is what bounds the temporally blocked Jacobi kernels.  ptxas folds the sign flips below into the
+// instruction's operand modifiers and takes lane-invariant operands from uniform registers.
+#ifndef SF_PACKED_F32
+#define SF_PACKED_F32 1
+#endif
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b)
+{
+    float2 r;
+    asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nadd.rn.f32x2 rc, ra, rb;\nmov.b64 {%0, %1}, rc;\n}\n"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b)
+{
+    float2 r;
+    asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rc, ra, rb;\nmov.b64 {%0, %1}, rc;\n}\n"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2_rn(float2 a, float2 b, float2 c)
+{
+    float2 r;
+    asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}\n"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+// A packed product that FEEDS A PACKED ADD must not be written with mul2_rn: ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (one rounding instead of two) although both carry an explicit
+// .rn, which forbids exactly that for the scalar forms -- and it does so with --fmad=false as well, and
+// after first rewriting fma(a, b, -0.0) into a multiply.  RN(a*b + (-0)) == RN(a*b) bit for bit (signed
+// zeros included), so the product is taken with an FFMA2 whose addend is -0.0f held in a register whose
+// value ptxas cannot know (DivConst::nz, a kernel parameter): same instruction count, nothing to contract.
+// tests/test_parity_gpu.py (alpha = 0.635 diffusion, every depth) fails by one ulp without this.
+__device__ __forceinline__ float2 mul2_exact(float2 a, float2 b, float nz) { return fma2_rn(a, b, make_float2(nz, nz)); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+// div_const_fast on a pair: the same three roundings per half (residual as b*q0 - a, see above)
+__device__ __forceinline__ float2 div_const_fast2(float2 a, const DivConst &d)
+{
+    const float2 y = dup2(d.y);
+    const float2 q0 = mul2_rn(a, y);
+    const float2 e = fma2_rn(dup2(d.b), q0, neg2(a));
+    return fma2_rn(neg2(e), y, q0);
+}
+
 // One Jacobi cell update with the reference's operand order (FluidSequential.c:95-96):
 //   ((left + right) + up) + down ;  x0 + alpha*sum ;  / beta.
 // __fadd_rn/__fmul_rn are never contracted into FMAs by nvcc.
@@ -97,6 +149,16 @@ __device__ __forceinline__ float jacobi_numerator(float l, float r, float up, fl
     if (MODE == MODE_PRESSURE) return __fadd_rn(b, s);
     if (MODE == MODE_FAST) return __fmaf_rn(alpha, s, b);
     return __fadd_rn(b, __fmul_rn(alpha, s));
+}
+// Two adjacent cells' numerators from h = left + right (formed by the caller with scalar adds: the operand
+// pairs of that first addition straddle the register pairs): ((h + up) + down, then x0 + alpha * sum.
+template <int MODE>
+__device__ __forceinline__ float2 jacobi_numerator2(float2 h, float2 up, float2 dn, float2 b, float alpha, float nz)
+{
+    const float2 s = add2_rn(add2_rn(h, up), dn);
+    if (MODE == MODE_PRESSURE) return add2_rn(b, s);
+    if (MODE == MODE_FAST) return fma2_rn(dup2(alpha), s, b);
+    return add2_rn(b, mul2_exact(dup2(alpha), s, nz));
 }
 template <int MODE>
 __device__ __forceinline__ float jacobi_cell(float l, float r, float up, float dn, float b, float alpha,

@@ -75,6 +75,7 @@ struct sf_context {
     sf::StealCtl *steal = nullptr;   // row-level work stealing between the warps of a Jacobi launch
     int steal_capacity = 0;
     int steal_opt = 30;              // SF_OPT_WORK_STEALING (percent; 0 = off)
+    int steal_scope = 0;             // SF_OPT_STEAL_SCOPE
     bool steal_now = false;          // set by the drivers around the solves that are worth it (see lin_solve)
     float *red_f = nullptr;          // reduction outputs
     double *red_d = nullptr;

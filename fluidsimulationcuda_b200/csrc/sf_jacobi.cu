@@ -197,6 +197,32 @@ __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rg
                                           const float4 &r, float alpha, const DivConst &d, bool &ok)
 {
     float4 o;
+#if SF_PACKED_F32
+    {
+        // l + r with scalar adds, everything after that two cells per instruction (FADD2 / FMUL2 / FFMA2)
+        const float2 h01 = make_float2(__fadd_rn(lft, mid.y), __fadd_rn(mid.x, mid.z));
+        const float2 h23 = make_float2(__fadd_rn(mid.y, mid.w), __fadd_rn(mid.z, rgt));
+        const float2 a01 = jacobi_numerator2<MODE>(h01, make_float2(up.x, up.y), make_float2(dn.x, dn.y), make_float2(r.x, r.y), alpha, d.nz);
+        const float2 a23 = jacobi_numerator2<MODE>(h23, make_float2(up.z, up.w), make_float2(dn.z, dn.w), make_float2(r.z, r.w), alpha, d.nz);
+        if (MODE == MODE_PRESSURE) {
+            const float2 o01 = mul2_rn(a01, dup2(0.25f)), o23 = mul2_rn(a23, dup2(0.25f));
+            return make_float4(o01.x, o01.y, o23.x, o23.y);
+        }
+        if (MODE == MODE_FAST) {
+            const float2 o01 = mul2_rn(a01, dup2(d.y)), o23 = mul2_rn(a23, dup2(d.y));
+            return make_float4(o01.x, o01.y, o23.x, o23.y);
+        }
+        if (MODE == MODE_STRICT && !GUARDED) {
+            const float2 o01 = div_const_fast2(a01, d), o23 = div_const_fast2(a23, d);
+            ok = ok & div_low_ok(a01.x) & div_low_ok(a01.y) & div_low_ok(a23.x) & div_low_ok(a23.y);
+            return make_float4(o01.x, o01.y, o23.x, o23.y);
+        }
+        if (MODE == MODE_STRICT) {
+            return make_float4(div_const_slow(a01.x, d), div_const_slow(a01.y, d), div_const_slow(a23.x, d), div_const_slow(a23.y, d));
+        }
+        return make_float4(__fdiv_rn(a01.x, d.b), __fdiv_rn(a01.y, d.b), __fdiv_rn(a23.x, d.b), __fdiv_rn(a23.y, d.b));
+    }
+#endif
     if (MODE == MODE_STRICT) {
         const float a0 = jacobi_numerator<MODE>(lft, mid.y, up.x, dn.x, r.x, alpha);
         const float a1 = jacobi_numerator<MODE>(mid.x, mid.z, up.y, dn.y, r.y, alpha);
@@ -658,6 +684,12 @@ __global__ void validate_division_kernel(DivConst d, unsigned long long *mismatc
         const unsigned want = __float_as_uint(__fdiv_rn(a, d.b));
         bad += (want != __float_as_uint(div_const(a, d)));        // guarded fast path + slow path outside the range
         bad += (want != __float_as_uint(div_const_slow(a, d)));   // the binary64 step on its own, every numerator
+#if SF_PACKED_F32
+        if (div_in_range(a)) {   // the two-wide form the streaming kernel uses (FMUL2 / FFMA2), both halves
+            const float2 q = div_const_fast2(make_float2(a, __uint_as_float((unsigned)u ^ 0x80000000u)), d);
+            bad += (want != __float_as_uint(q.x)) + ((want ^ 0x80000000u) != __float_as_uint(q.y));
+        }
+#endif
     }
     if (bad) atomicAdd(mismatches, bad);
 }

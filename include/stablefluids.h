@@ -74,7 +74,10 @@ enum {
      * in percent, that is worth halving (1..100); 0 = off.  Results are unchanged. */
     SF_OPT_WORK_STEALING = 7,
     /* read-only (sf_get_option): row ranges taken over by another warp so far; synchronises. */
-    SF_OPT_STEAL_COUNT = 8
+    SF_OPT_STEAL_COUNT = 8,
+    /* which STRICT solves use work stealing: 0 (default) = scalar fields only (see above), 1 = every
+     * STRICT lin_solve (the velocity solves of vel_step too).  Results are unchanged. */
+    SF_OPT_STEAL_SCOPE = 9
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 

@@ -1,10 +1,10 @@
 """A/B timing of one 40-sweep lin_solve per (T, mode) and of the full step: default library vs SF_LIBRARY."""
-import sys; sys.path.insert(0, ".")
-import torch, os
+import os, sys; sys.path.insert(0, ".")
+import torch
 from fluidsimulationcuda_b200 import solver as SF
 print("lib", os.environ.get("SF_LIBRARY", "default"), flush=True)
 G = 8192; K = 40
-for T in (6, 7):
+for T in [int(t) for t in os.environ.get("SF_AB_T", "6,7").split(",")]:
     for mode, (al, be) in (("pressure", (1.0, 4.0)), ("strict", (2683.2, 10733.8))):
         s = SF.StableFluids(G - 2, sweeps_per_launch=T, use_graph=False)
         x, x0 = s.new_field(), s.new_field(); x.uniform_(0, 1); x0.uniform_(0, 1)
@@ -19,6 +19,8 @@ for T in (6, 7):
 s = SF.StableFluids(G - 2)
 if os.environ.get("SF_STEAL"):
     s.set_option(SF.SF_OPT_WORK_STEALING, int(os.environ["SF_STEAL"]))
+if os.environ.get("SF_STEAL_SCOPE"):
+    s.set_option(SF.SF_OPT_STEAL_SCOPE, int(os.environ["SF_STEAL_SCOPE"]))
 f = [s.new_field() for _ in range(6)]
 s.init_synthetic(1, *f)
 for i in range(4):
