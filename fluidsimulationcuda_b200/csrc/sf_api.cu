@@ -64,10 +64,10 @@ int default_sweeps(const sf_context *c)
 
 // Split `iters` sweeps into launches of at most T sweeps.  The lin_solve ping-pongs between x and
 // the scratch field, so an EVEN number of launches leaves the result in x without a copy.
-std::vector<int> plan_launches(int iters, int T)
+std::vector<int> plan_launches(int iters, int T, bool odd_ok)
 {
     int L = (iters + T - 1) / T;
-    if ((L & 1) && L + 1 <= iters) ++L;
+    if (!odd_ok && (L & 1) && L + 1 <= iters) ++L;
     std::vector<int> plan(L, iters / L);
     for (int k = 0; k < iters % L; ++k) ++plan[k];
     return plan;
@@ -113,8 +113,15 @@ int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, floa
     int rc = ensure_scratch(c);
     if (rc) return rc;
     const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
-    const std::vector<int> plan = plan_launches(iters, stream_ok ? default_sweeps(c) : 1);
+    // A solve from the implicit zero guess (the pressure solves of project) never reads x in its first launch, so
+    // that launch may write x itself and the ping-pong may take an ODD number of launches: K = 20 runs as 3
+    // launches (7,7,6) instead of 4 (5,5,5,5), K = 200 as 29 instead of 30.  (K = 40 stays at 6 launches: 5 launches
+    // of 8 sweeps were measured SLOWER, 9.42 vs 8.87 ms per step at G=8192 -- at depth 8 the pressure kernel
+    // spills under its 128-register cap.)
+    const bool odd_ok = stream_ok && zero_guess && c->pressure_plan != 0;
+    const std::vector<int> plan = plan_launches(iters, stream_ok ? default_sweeps(c) : 1, odd_ok);
     float *cur = x, *nxt = c->scratch;
+    if (odd_ok && (plan.size() & 1)) { cur = c->scratch; nxt = x; }   // `cur` is not read by the first launch
     for (size_t k = 0; k < plan.size(); ++k) {
         rc = one_jacobi_launch(c, c->work, b, nxt, cur, x0, alpha, beta, plan[k], c->g.own_lo, c->g.own_hi, zero_guess && k == 0);
         if (rc) return rc;
@@ -235,7 +242,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.f[0] = f0; k.f[1] = f1; k.f[2] = f2;
     k.iters = iters;
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
-    k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope;
+    k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan;
     return k;
 }
 
@@ -338,6 +345,7 @@ int sf_set_option(sf_context *c, int option, int value)
             SF_CUDA(c, cudaStreamSynchronize(c->stream));
             break;
         }
+        case SF_OPT_PRESSURE_PLAN: c->pressure_plan = value ? 1 : 0; break;
         case SF_OPT_STEAL_SCOPE: SF_REQUIRE(c, value == 0 || value == 1, "steal scope: 0 scalar fields / 1 every strict solve"); c->steal_scope = value; break;
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }
@@ -356,6 +364,7 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_STAGING: *value = c->staging; break;
         case SF_OPT_WORK_STEALING: *value = c->steal_opt; break;
         case SF_OPT_STEAL_SCOPE: *value = c->steal_scope; break;
+        case SF_OPT_PRESSURE_PLAN: *value = c->pressure_plan; break;
         case SF_OPT_STEAL_COUNT: {   // diagnostics: row ranges taken over by another warp so far (synchronises)
             *value = 0;
             if (c->steal) {

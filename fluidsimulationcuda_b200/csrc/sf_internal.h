@@ -76,6 +76,7 @@ struct sf_context {
     int steal_capacity = 0;
     int steal_opt = 30;              // SF_OPT_WORK_STEALING (percent; 0 = off)
     int steal_scope = 0;             // SF_OPT_STEAL_SCOPE
+    int pressure_plan = 1;           // SF_OPT_PRESSURE_PLAN
     bool steal_now = false;          // set by the drivers around the solves that are worth it (see lin_solve)
     float *red_f = nullptr;          // reduction outputs
     double *red_d = nullptr;
@@ -127,7 +128,7 @@ inline bool stream_kernels_ok(const sf_context *c) { return jacobi_stream_suppor
 int ensure_scratch(sf_context *c);
 int arith_mode(const sf_context *c, float alpha, float beta);
 int default_sweeps(const sf_context *c);
-std::vector<int> plan_launches(int iters, int T);
+std::vector<int> plan_launches(int iters, int T, bool odd_ok = false);
 // strip_rows > 0 (peer-memory slabs): the launch exchanges boundary strips of that height with the
 // neighbours (fused into the kernel; see StripArgs in sf_common.cuh); xout must be an arena field
 int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const float *xin, const float *x0, float alpha,

@@ -329,7 +329,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
         __syncwarp();
     }
 
-    const int s_lo = max(a_lo - T, 0);
+    // `first`: the first output row that has not been produced yet.  It starts at a_lo and moves only when the
+    // pipeline is restarted (GROUP_VOTE below); the pipeline enters T rows above it.
+    int first = a_lo;
+    int s_lo = max(first - T, 0);
     const int s_hi = a_hi - 1 + T;                 // inclusive
     const int load_hi = min(s_hi, A.G - 1);
     const float *xsrc = A.xin + cc;
@@ -385,20 +388,19 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
     // so rows whose magnitudes stay below A.hi_in can never produce a numerator above SF_DIV_HI.
     // Every row is checked when it is fetched; one outlier switches the warp to the fully guarded
     // tick for the next rows (up to the next multiple of 64).
+    // (both lambdas below are only used inside a fast group, whose rows s..s+2 <= fast_hi <= load_hi)
+    auto xrow_in = [&](int row) -> float4 {
+        return zero_guess ? make_float4(0.f, 0.f, 0.f, 0.f) : xring[(row & (RING_X - 1)) * 32];
+    };
     auto row_is_big = [&](int row) -> bool {
-        if (MODE != MODE_STRICT || row > load_hi) return false;
-        const float4 a = xrow(row), b = rring[(row & (RING_R - 1)) * 32];
+        if (MODE != MODE_STRICT) return false;
+        const float4 a = xrow_in(row), b = rring[(row & (RING_R - 1)) * 32];
         const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
                               fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
         return !(m <= A.hi_in);   // NaN counts as big
     };
 
     float4 W[T][3];
-#pragma unroll
-    for (int t = 0; t < T; ++t) W[t][0] = W[t][1] = W[t][2] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-#pragma unroll
-    for (int k = 0; k < PREFETCH; ++k) issue(s_lo + k);
 
     float *orow = A.xout + cc;
     // peer-memory slabs: a boundary strip stores the rows its neighbour needs straight into the
@@ -409,10 +411,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
         if constexpr (STRIP) *reinterpret_cast<float4 *>(peer + cc + (size_t)a * pitch) = o;
     };
     auto emit_plain = [&](int a, const float4 &o) {
-        if (a >= a_lo && a < a_hi && st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
+        if (a >= first && a < a_hi && st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
     };
     auto emit_walls = [&](int a, const float4 &o) {
-        if (a < a_lo || a >= a_hi) return;
+        if (a < first || a >= a_hi) return;
         if (st_ok) {
             *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
             push(a, o);
@@ -436,10 +438,23 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
     const int fast_lo = T + 2;
     const int fast_hi = min(s_hi, A.N);
     [[maybe_unused]] int end_seen = a_hi;    // STEAL: the slot's end as of the previous poll
-    // an out-of-range numerator or an outlier row was seen: guarded ticks for the next rows.  Strip warps
-    // (peer slabs) only ever take the general tick (which carries the neighbour push): they live for ~3T
-    // ticks, and a strip copy with the fast tick was measured to cost the interior path registers.
-    bool slow = STRIP;
+    // MODE_STRICT: an out-of-range numerator or an outlier row was seen -- guarded ticks for rows below
+    // slow_until (the next multiple of 64: the numerators that need them, the decaying front of a density
+    // field, occupy a band of rows, not the rest of a chunk of thousands; a retry that fails wastes one
+    // optimistic group per 64 rows).  Strip warps (peer slabs) only ever take the general tick (which carries
+    // the neighbour push): they live for ~3T ticks, and a strip copy with the fast tick was measured to cost
+    // the interior path registers.
+    int slow_until = STRIP ? 0x7fffffff : 0;
+    [[maybe_unused]] int span = 64;
+    auto next64 = [](int row) { return (row + 63) & ~63; };
+    // GROUP_VOTE: the three ticks of a fast group run without a branch between them (one basic block: the
+    // ticks' dependency chains overlap, which is what the packed arithmetic needs to stay issue-bound) and
+    // the warp votes once per group.  A failed vote means rows s-T.. have been emitted with a division that
+    // was not proved exact and the windows hold such values: the pipeline is restarted T rows above the first
+    // of them with guarded ticks (level-0 rows are re-read from global memory, 2T rows of redundant work per
+    // failure; the rows are written again with the exact values by this same warp).  The bulk-copy staging
+    // variant keeps a vote per tick (its mbarrier phases are tied to the first row of the pipeline).
+    constexpr bool GROUP_VOTE = (MODE == MODE_STRICT) && !TMA && !STRIP;
 
     // general tick at phase 0 followed by the register rotation that restores phase 0
     auto general_tick = [&](int s_, const float4 &row_in) {
@@ -449,6 +464,13 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
 #pragma unroll
         for (int t = 0; t < T; ++t) { W[t][0] = W[t][1]; W[t][1] = W[t][2]; }
     };
+
+    for (;;) {   // (re)start of the pipeline at `first`
+    bool restart = false;
+#pragma unroll
+    for (int t = 0; t < T; ++t) W[t][0] = W[t][1] = W[t][2] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < PREFETCH; ++k) issue(s_lo + k);
 
     int s = s_lo;
     while (s <= s_hi) {
@@ -465,28 +487,45 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                 end_seen = ld_relaxed_gpu(&slot->end);
             }
         }
-        // The guarded mode is left again every 64 rows: the numerators that need it (the decaying front of
-        // a density field) occupy a band of rows, not the rest of a chunk of thousands of rows.  A retry
-        // that fails costs one wasted optimistic tick per 64 guarded ones.
-        if (MODE == MODE_STRICT && !STRIP && (s & 63) == 0) slow = false;
+        const bool slow = s < slow_until;
         if (!slow && s >= fast_lo && s + 2 <= fast_hi) {
             issue(s + PREFETCH); issue(s + PREFETCH + 1); issue(s + PREFETCH + 2);
             landed(s, 3);                    // rows <= s+2 have landed
-            if (MODE == MODE_STRICT) slow = __any_sync(0xffffffffu, row_is_big(s) | row_is_big(s + 1) | row_is_big(s + 2));
-            if (!slow) {
+            bool big = false;
+            if (MODE == MODE_STRICT) big = __any_sync(0xffffffffu, row_is_big(s) | row_is_big(s + 1) | row_is_big(s + 2));
+            if (!big) {
                 float4 o;
-                bool ok = pipeline_tick<T, MODE, 0, false>(A, s, xrow(s), W, rring, ownsL, ownsR, o);
+                if constexpr (GROUP_VOTE) {
+                    bool ok = pipeline_tick<T, MODE, 0, false>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                    emit_plain(s - T, o);
+                    ok &= pipeline_tick<T, MODE, 1, false>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                    emit_plain(s + 1 - T, o);
+                    ok &= pipeline_tick<T, MODE, 2, false>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                    emit_plain(s + 2 - T, o);
+                    if (!__all_sync(0xffffffffu, ok)) {
+                        first = max(first, s - T);     // rows below it were emitted by groups that passed
+                        // a retry that fails straight away doubles the guarded span (64 .. 512 rows): where the
+                        // front of a density field runs ALONG a band, every retry would cost a restart
+                        span = (s < slow_until + 6) ? min(2 * span, 512) : 64;
+                        slow_until = next64(s + 3) + span - 64;
+                        restart = true;
+                        break;
+                    }
+                    s += 3;
+                    continue;
+                } else {
+                bool ok = pipeline_tick<T, MODE, 0, false>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
                 if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
-                    slow = true;                       // windows are still at phase 0: redo guarded
+                    slow_until = next64(s + 3);        // windows are still at phase 0: redo guarded
                     general_tick(s, xrow(s)); s += 1;
                     general_tick(s, xrow(s)); s += 1;  // the two other rows of this group are in flight already
                     general_tick(s, xrow(s)); s += 1;
                     continue;
                 }
                 emit_plain(s - T, o);
-                ok = pipeline_tick<T, MODE, 1, false>(A, s + 1, xrow(s + 1), W, rring, ownsL, ownsR, o);
+                ok = pipeline_tick<T, MODE, 1, false>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
                 if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
-                    slow = true;                       // phase 1 -> phase 0: up = slot 1, mid = slot 2
+                    slow_until = next64(s + 3);        // phase 1 -> phase 0: up = slot 1, mid = slot 2
 #pragma unroll
                     for (int t = 0; t < T; ++t) { W[t][0] = W[t][1]; W[t][1] = W[t][2]; }
                     general_tick(s + 1, xrow(s + 1));
@@ -495,9 +534,9 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     continue;
                 }
                 emit_plain(s + 1 - T, o);
-                ok = pipeline_tick<T, MODE, 2, false>(A, s + 2, xrow(s + 2), W, rring, ownsL, ownsR, o);
+                ok = pipeline_tick<T, MODE, 2, false>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
                 if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
-                    slow = true;                       // phase 2 -> phase 0: up = slot 2, mid = slot 0
+                    slow_until = next64(s + 3);        // phase 2 -> phase 0: up = slot 2, mid = slot 0
 #pragma unroll
                     for (int t = 0; t < T; ++t) { const float4 m = W[t][0]; W[t][0] = W[t][2]; W[t][1] = m; }
                     general_tick(s + 2, xrow(s + 2));
@@ -507,8 +546,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                 emit_plain(s + 2 - T, o);
                 s += 3;
                 continue;
+                }
             }
             // outlier row: the three rows of this group are already in flight; run them guarded
+            slow_until = next64(s + 3);
             general_tick(s, xrow(s)); s += 1;
             general_tick(s, xrow(s)); s += 1;
             general_tick(s, xrow(s)); s += 1;
@@ -516,6 +557,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
         }
         general_tick(s, fetch(s));
         ++s;
+    }
+    if (!restart) break;
+    cp_async_wait<0>();        // rows in flight land before their ring slots are reused
+    s_lo = max(first - T, 0);
     }
     if (TMA) {   // drain: rows issued beyond the last one consumed must land before the CTA's smem is released
         for (int row = s_hi + 1; row <= min(s_hi + PREFETCH + 2, load_hi); ++row)

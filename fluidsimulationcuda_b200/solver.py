@@ -31,6 +31,7 @@ SF_OPT_STAGING = 6
 SF_OPT_WORK_STEALING = 7
 SF_OPT_STEAL_COUNT = 8
 SF_OPT_STEAL_SCOPE = 9
+SF_OPT_PRESSURE_PLAN = 10
 STRICT, FAST = 0, 1
 
 # every symbol include/stablefluids.h declares (tests/test_abi.py checks the library exports them)

@@ -77,7 +77,11 @@ enum {
     SF_OPT_STEAL_COUNT = 8,
     /* which STRICT solves use work stealing: 0 (default) = scalar fields only (see above), 1 = every
      * STRICT lin_solve (the velocity solves of vel_step too).  Results are unchanged. */
-    SF_OPT_STEAL_SCOPE = 9
+    SF_OPT_STEAL_SCOPE = 9,
+    /* 1 (default): a lin_solve that starts from the implicit zero guess (the pressure solves of
+     * sf_project) may take an odd number of launches (its first launch does not read x, so it may
+     * write x); 0 = the even-count plan of every other solve.  Results are unchanged. */
+    SF_OPT_PRESSURE_PLAN = 10
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 

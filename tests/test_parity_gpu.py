@@ -142,6 +142,29 @@ def test_diffuse_huge_values_take_the_guarded_path(SF, oracle):
         assert_same(host(dx), want, f"huge values at {spot}")
 
 
+@pytest.mark.parametrize("T", [3, 6, 7])
+@pytest.mark.parametrize("b,chunk", [(0, 0), (1, 0), (0, 400), (1, 300)])
+def test_diffuse_tiny_patches_restart_the_pipeline(SF, oracle, b, chunk, T):
+    """Numerators below the fast division's range in the MIDDLE of a chunk: the strict kernel votes once per
+    group of three ticks, and a failed vote restarts the warp's pipeline above the group with guarded ticks
+    (b = 0 runs the work-stealing variant, b = 1 the plain one).  Patches of 1e-33 .. 1e-44 (subnormals
+    included) and of zeros inside an O(1) field, several per band so that retries fail and back off."""
+    N = 1022; G = N + 2
+    rng = np.random.default_rng(77 + T)
+    s = SF.StableFluids(N, sweeps_per_launch=T)
+    s.set_option(SF.SF_OPT_CHUNK_ROWS, chunk)      # 0: chunks of 2T rows at this size; 300/400: long chunks, retries back off
+    x, x0 = rnd(rng, G), rnd(rng, G)
+    for (r0, r1, c0, c1, scale) in ((100, 140, 50, 400, 1e-33), (300, 700, 600, 640, 3e-38), (500, 520, 0, G, 1e-41),
+                                    (800, 1000, 900, 1000, 0.0), (130, 180, 380, 420, 1e-44)):
+        x[r0:r1, c0:c1] = (x[r0:r1, c0:c1] * scale).astype(np.float32)
+        x0[r0:r1, c0:c1] = (x0[r0:r1, c0:c1] * scale).astype(np.float32)
+    for alpha, beta, iters in ((6.15, 25.6, 2 * T), (2683.2, 10733.8, 3 * T + 1)):
+        want = x.copy(); oracle.diffuse(N, b, want, x0, alpha, beta, iters)
+        dx = dev(x); s.diffuse(b, dx, dev(x0), alpha, beta, iters)
+        assert np.any((want != 0) & (np.abs(want) < 1.17e-38)), "test must exercise subnormals"
+        assert_same(host(dx), want, f"tiny patches b={b} chunk={chunk} T={T} alpha={alpha}")
+
+
 # ---- steps ----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,K", [(30, 4), (62, 20), (126, 40), (254, 20), (130, 6)])
 def test_vel_and_dens_step(SF, oracle, N, K):

@@ -19,6 +19,8 @@ for T in [int(t) for t in os.environ.get("SF_AB_T", "6,7").split(",")]:
 s = SF.StableFluids(G - 2)
 if os.environ.get("SF_STEAL"):
     s.set_option(SF.SF_OPT_WORK_STEALING, int(os.environ["SF_STEAL"]))
+if os.environ.get("SF_PRESSURE_PLAN"):
+    s.set_option(SF.SF_OPT_PRESSURE_PLAN, int(os.environ["SF_PRESSURE_PLAN"]))
 if os.environ.get("SF_STEAL_SCOPE"):
     s.set_option(SF.SF_OPT_STEAL_SCOPE, int(os.environ["SF_STEAL_SCOPE"]))
 f = [s.new_field() for _ in range(6)]
