@@ -45,6 +45,21 @@ constexpr int STEAL_MIN_ROWS = 64;            // work stealing: smallest remaini
 #define SF_RING_R 16
 #define SF_PREFETCH 5
 #endif
+#ifndef SF_OFF32
+#define SF_OFF32 1        // 32-bit cell offsets inside a field (see stream_rows)
+#endif
+#ifndef SF_EDGE_SPLIT
+// 1 = separate fast-group instantiation for bands without a wall column (saves the two predicated wall
+// multiplies per level in 72 of 74 bands).  Measured SLOWER at G=8192, K=40 (pressure solve 1.12 vs 0.91 ms,
+// strict 1.68 vs 1.58 ms, step 9.15 vs 8.58 ms): the second copy of the group costs the pressure kernel
+// its spill-free allocation.  Kept as a build option, off.
+#define SF_EDGE_SPLIT 0
+#endif
+#if SF_OFF32
+typedef unsigned cell_t;
+#else
+typedef size_t cell_t;
+#endif
 constexpr int WPC = SF_WPC;            // warps per CTA (adjacent bands, same row chunk)
 constexpr int RING_X = SF_RING_X;      // x-row ring slots per warp (power of two, >= PREFETCH + 3)
 constexpr int RING_R = SF_RING_R;      // rhs-row ring slots per warp (power of two, >= T + PREFETCH + 3)
@@ -260,7 +275,9 @@ __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rg
 // the level below in this same tick.  PH is a compile-time constant, so after three ticks every
 // row is back in the register it started in and the hot loop contains no register moves.
 // WALLS adds the fused set_bnd handling.  Returns level T of row s-T in `out`.
-template <int T, int MODE, int PH, bool WALLS>
+// EDGE = false: the warp's band touches neither wall column (72 of the 74 bands at G = 8192): the two
+// predicated wall multiplies per level are not even issued.
+template <int T, int MODE, int PH, bool WALLS, bool EDGE = true>
 __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const float4 &row_in, float4 (&W)[T][3],
                                               const float4 *rring, bool ownsL, bool ownsR, float4 &out)
 {
@@ -277,8 +294,10 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
         float4 o = jacobi4<MODE, WALLS>(lft, mid, rgt, up, dn, r, A.alpha, A.div, ok);
         // wall columns: x[row][0] = sx * x[row][1], x[row][N+1] = sx * x[row][N]  (two predicated
         // multiplies; only the lanes holding columns 0 / N+1 of the two edge bands execute them)
-        if (ownsL) o.x = __fmul_rn(A.sx, o.y);
-        if (ownsR) o.w = __fmul_rn(A.sx, o.z);
+        if (EDGE) {
+            if (ownsL) o.x = __fmul_rn(A.sx, o.y);
+            if (ownsR) o.w = __fmul_rn(A.sx, o.z);
+        }
         if (WALLS) {
             if (t + 1 < T) {
                 // wall rows of level t+1 live in the NEXT level's window: its MID slot is row a-1
@@ -335,9 +354,12 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
     int s_lo = max(first - T, 0);
     const int s_hi = a_hi - 1 + T;                 // inclusive
     const int load_hi = min(s_hi, A.G - 1);
-    const float *xsrc = A.xin + cc;
-    const float *rsrc = A.rhs + cc;
     const size_t pitch = (size_t)A.G;
+    // Cell offsets inside a field are taken in unsigned 32-bit arithmetic (jacobi_stream_supported keeps
+    // rows * G below 2^32): one 32-bit multiply per row instead of a sign-extended 64-bit one, and the pointer
+    // is one widening multiply-add from the field base.
+    const cell_t Gu = (cell_t)A.G, ccu = (cell_t)cc;
+    auto cell = [&](int row) -> cell_t { return (cell_t)(row - A.row_base) * Gu + ccu; };
     const bool zero_guess = A.zero_guess != 0;
 
     auto issue = [&](int row) {
@@ -354,11 +376,25 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             return;
         }
         if (row <= load_hi) {
-            const size_t off = (size_t)(row - A.row_base) * pitch;
-            if (!zero_guess) cp_async16(xring + (row & (RING_X - 1)) * 32, xsrc + off, nbytes);
-            cp_async16(rring + (row & (RING_R - 1)) * 32, rsrc + off, nbytes);
+            const cell_t off = cell(row);
+            if (!zero_guess) cp_async16(xring + (row & (RING_X - 1)) * 32, A.xin + off, nbytes);
+            cp_async16(rring + (row & (RING_R - 1)) * 32, A.rhs + off, nbytes);
         }
         cp_async_commit();
+    };
+    // three consecutive rows (one fast group): one address computation when all of them exist
+    auto issue3 = [&](int row) {
+        if (!TMA && row + 2 <= load_hi) {
+            const cell_t off = cell(row);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (!zero_guess) cp_async16(xring + ((row + k) & (RING_X - 1)) * 32, A.xin + (off + (cell_t)k * Gu), nbytes);
+                cp_async16(rring + ((row + k) & (RING_R - 1)) * 32, A.rhs + (off + (cell_t)k * Gu), nbytes);
+                cp_async_commit();
+            }
+            return;
+        }
+        issue(row); issue(row + 1); issue(row + 2);
     };
     // rows [first, first + n) have been issued; block until they have landed
     auto landed = [&](int first, int n) {
@@ -402,7 +438,6 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
 
     float4 W[T][3];
 
-    float *orow = A.xout + cc;
     // peer-memory slabs: a boundary strip stores the rows its neighbour needs straight into the
     // neighbour's ghost rows over NVLink (plain peer stores; the exchange is part of the compute kernel)
     // peer-memory slabs: a strip warp stores every row it produces into the neighbour's ghost rows as well
@@ -411,25 +446,25 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
         if constexpr (STRIP) *reinterpret_cast<float4 *>(peer + cc + (size_t)a * pitch) = o;
     };
     auto emit_plain = [&](int a, const float4 &o) {
-        if (a >= first && a < a_hi && st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
+        if (a >= first && a < a_hi && st_ok) *reinterpret_cast<float4 *>(A.xout + cell(a)) = o;
     };
     auto emit_walls = [&](int a, const float4 &o) {
         if (a < first || a >= a_hi) return;
         if (st_ok) {
-            *reinterpret_cast<float4 *>(orow + (size_t)(a - A.row_base) * pitch) = o;
+            *reinterpret_cast<float4 *>(A.xout + cell(a)) = o;
             push(a, o);
         }
         if (a == 1 && A.write_top) {
             float4 w = scale4(o, A.sy);
             if (ownsL) w.x = __fmul_rn(0.5f, __fadd_rn(w.y, o.x));   // x[0][0] = .5*(x[0][1] + x[1][0])
             if (ownsR) w.w = __fmul_rn(0.5f, __fadd_rn(w.z, o.w));   // x[0][N+1] = .5*(x[0][N] + x[1][N+1])
-            if (st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(0 - A.row_base) * pitch) = w;
+            if (st_ok) *reinterpret_cast<float4 *>(A.xout + cell(0)) = w;
         }
         if (a == A.N && A.write_bot) {
             float4 w = scale4(o, A.sy);
             if (ownsL) w.x = __fmul_rn(0.5f, __fadd_rn(w.y, o.x));   // x[N+1][0] = .5*(x[N+1][1] + x[N][0])
             if (ownsR) w.w = __fmul_rn(0.5f, __fadd_rn(w.z, o.w));   // x[N+1][N+1] = .5*(x[N+1][N] + x[N][N+1])
-            if (st_ok) *reinterpret_cast<float4 *>(orow + (size_t)(A.N + 1 - A.row_base) * pitch) = w;
+            if (st_ok) *reinterpret_cast<float4 *>(A.xout + cell(A.N + 1)) = w;
         }
     };
     // The row-wall logic is needed when some level produces row 1 or row N+1 (s-t-1 in {1, N+1}, t < T)
@@ -455,6 +490,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
     // failure; the rows are written again with the exact values by this same warp).  The bulk-copy staging
     // variant keeps a vote per tick (its mbarrier phases are tied to the first row of the pipeline).
     constexpr bool GROUP_VOTE = (MODE == MODE_STRICT) && !TMA && !STRIP;
+    // the modes without a range check (pressure, fast, IEEE division) run the same branch-free group
+    constexpr bool BRANCH_FREE_GROUP = (MODE != MODE_STRICT);
+    // warp-uniform: does this band hold a wall column?  (selects the group instantiation, see pipeline_tick)
+    const bool edge_band = SF_EDGE_SPLIT ? __any_sync(0xffffffffu, ownsL || ownsR) : true;
 
     // general tick at phase 0 followed by the register rotation that restores phase 0
     auto general_tick = [&](int s_, const float4 &row_in) {
@@ -489,20 +528,35 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
         }
         const bool slow = s < slow_until;
         if (!slow && s >= fast_lo && s + 2 <= fast_hi) {
-            issue(s + PREFETCH); issue(s + PREFETCH + 1); issue(s + PREFETCH + 2);
+            issue3(s + PREFETCH);
             landed(s, 3);                    // rows <= s+2 have landed
             bool big = false;
             if (MODE == MODE_STRICT) big = __any_sync(0xffffffffu, row_is_big(s) | row_is_big(s + 1) | row_is_big(s + 2));
             if (!big) {
                 float4 o;
-                if constexpr (GROUP_VOTE) {
-                    bool ok = pipeline_tick<T, MODE, 0, false>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
-                    emit_plain(s - T, o);
-                    ok &= pipeline_tick<T, MODE, 1, false>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
-                    emit_plain(s + 1 - T, o);
-                    ok &= pipeline_tick<T, MODE, 2, false>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
-                    emit_plain(s + 2 - T, o);
-                    if (!__all_sync(0xffffffffu, ok)) {
+                if constexpr (GROUP_VOTE || BRANCH_FREE_GROUP) {
+                    bool ok;
+                    // the three rows this group emits: one offset, then +G, +2G
+                    const cell_t e0 = cell(s - T);
+                    auto emit_plain = [&](int a, const float4 &ov) {
+                        if (a >= first && a < a_hi && st_ok) *reinterpret_cast<float4 *>(A.xout + (e0 + (cell_t)(a - (s - T)) * Gu)) = ov;
+                    };
+                    if (edge_band) {
+                        ok = pipeline_tick<T, MODE, 0, false, true>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                        emit_plain(s - T, o);
+                        ok &= pipeline_tick<T, MODE, 1, false, true>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                        emit_plain(s + 1 - T, o);
+                        ok &= pipeline_tick<T, MODE, 2, false, true>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                        emit_plain(s + 2 - T, o);
+                    } else {
+                        ok = pipeline_tick<T, MODE, 0, false, false>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                        emit_plain(s - T, o);
+                        ok &= pipeline_tick<T, MODE, 1, false, false>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                        emit_plain(s + 1 - T, o);
+                        ok &= pipeline_tick<T, MODE, 2, false, false>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                        emit_plain(s + 2 - T, o);
+                    }
+                    if (GROUP_VOTE && !__all_sync(0xffffffffu, ok)) {
                         first = max(first, s - T);     // rows below it were emitted by groups that passed
                         // a retry that fails straight away doubles the guarded span (64 .. 512 rows): where the
                         // front of a density field runs ALONG a band, every retry would cost a restart
@@ -836,7 +890,12 @@ void preload_jacobi_kernels()
     (void)cudaGetLastError();
 }
 
-bool jacobi_stream_supported(const Geom &g) { return (g.G % 4) == 0 && g.G >= 4; }
+// widths that are a multiple of 4 (16-byte rows) and fields of fewer than 2^32 cells (32-bit cell offsets in the
+// streaming kernel: up to G = 65532 on one GPU, any BASELINE size); everything else runs the generic kernel
+bool jacobi_stream_supported(const Geom &g)
+{
+    return (g.G % 4) == 0 && g.G >= 4 && (!SF_OFF32 || (unsigned long long)g.rows * (unsigned long long)g.G < (1ull << 32));
+}
 
 bool division_validated(float beta, bool allow_run, cudaStream_t st)
 {
