@@ -13,4 +13,6 @@ for cfg in "strict 7 8192 1" "strict 7 8192 0" "pressure 7 8192 0"; do
   ncu -i gpurun_out/final_prof_$tag.ncu-rep --page raw --csv --metrics $M > gpurun_out/final_prof_$tag.csv 2>/dev/null
   [ "$tag" = "strict_7_8192_1" ] || rm -f gpurun_out/final_prof_$tag.ncu-rep     # gpurun brings back at most 64 MiB
 done
+# BASELINE config 3: lin_solve time and effective bandwidth against the temporal-blocking depth
+python tools/t_sweep.py 8192 40 1,2,3,4,5,6,7,8 > gpurun_out/final_t_sweep.log 2>&1; cat gpurun_out/final_t_sweep.log
 ls -la gpurun_out/final_*
