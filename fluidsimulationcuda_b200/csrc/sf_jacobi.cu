@@ -55,6 +55,20 @@ constexpr int STEAL_MIN_ROWS = 64;            // work stealing: smallest remaini
 // its spill-free allocation.  Kept as a build option, off.
 #define SF_EDGE_SPLIT 0
 #endif
+#ifndef SF_INNER_LOOP
+// 1 / 2 = consecutive fast groups run in their own inner loop (the general tick stays in the outer one).  With one
+// loop for both paths ptxas gives the windows a different register assignment at the loop latch than at the
+// loop head and pays for it with 8T register moves per group ON THE FAST PATH (56 MOVs of ~650 instructions
+// at T = 7: the general tick's explicit rotation, sunk into the common latch); see profiles/r01_sass_static.txt.
+// Off until it has been through the GPU parity suite and an A/B timing.
+#define SF_INNER_LOOP 0
+#endif
+#ifndef SF_PRESSURE_CTAS
+// CTAs per SM the pressure kernel (T >= 6) is register-bounded for: 4 (128 registers, 16 warps per SM) or 3 (168 registers,
+// 12 warps per SM).  With SF_INNER_LOOP the T = 7 pressure kernel spills 32 bytes under the 128-register cap, so the
+// pair (SF_INNER_LOOP=1, SF_PRESSURE_CTAS=3) is the other candidate of that A/B.
+#define SF_PRESSURE_CTAS 4
+#endif
 #if SF_OFF32
 typedef unsigned cell_t;
 #else
@@ -68,7 +82,7 @@ constexpr int PREFETCH = SF_PREFETCH;  // rows in flight ahead of the row being 
 // in flight: at T >= 6 it needs ~150 registers, so it runs 3 CTAs (12 warps) per SM instead of 4 --
 // measured faster than spilling at 128 registers (1.78 vs 2.18 ms per 40-sweep solve at G=8192).
 template <int T, int MODE>
-constexpr int min_ctas() { return ((MODE == MODE_STRICT || MODE == MODE_IEEE) && T >= 6) ? 3 : 4; }
+constexpr int min_ctas() { return ((MODE == MODE_STRICT || MODE == MODE_IEEE) && T >= 6) ? 3 : (MODE == MODE_PRESSURE && T >= 6) ? SF_PRESSURE_CTAS : 4; }
 
 struct StreamArgs {
     const float *xin, *rhs;
@@ -528,6 +542,22 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
         }
         const bool slow = s < slow_until;
         if (!slow && s >= fast_lo && s + 2 <= fast_hi) {
+#if SF_INNER_LOOP
+            // every path through the body below ends in `continue` (-> the inner condition) or, for a restart, `break`
+            // 1: the modes without a range check only (the strict group already gets a loop of its own from ptxas); 2: all
+            constexpr bool INNER_RUN = (SF_INNER_LOOP == 2) || (MODE != MODE_STRICT);
+            [[maybe_unused]] bool stolen = false;
+            [[maybe_unused]] const int s_run = s;
+            do {
+            if constexpr (STEAL) {   // the same poll as above, for the groups after the first of this run
+                if (s != s_run && ((s - a_lo) & 31) < 3) {
+                    if (end_seen <= s - T) { stolen = true; break; }
+                    StealSlot *slot = A.steal->slots + (blockIdx.x * WPC + (threadIdx.x >> 5));
+                    if (lane == 0) st_relaxed_gpu(&slot->pos, s);
+                    end_seen = ld_relaxed_gpu(&slot->end);
+                }
+            }
+#endif
             issue3(s + PREFETCH);
             landed(s, 3);                    // rows <= s+2 have landed
             bool big = false;
@@ -608,6 +638,11 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             general_tick(s, xrow(s)); s += 1;
             general_tick(s, xrow(s)); s += 1;
             continue;
+#if SF_INNER_LOOP
+            } while (INNER_RUN && s >= slow_until && s + 2 <= fast_hi);     // (s >= fast_lo holds for the whole run)
+            if (restart || stolen) break;
+            continue;
+#endif
         }
         general_tick(s, fetch(s));
         ++s;
@@ -959,7 +994,8 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
         // the same, so a single full wave has no tail.  Large grids get chunks of hundreds of rows (2T
         // redundant halo rows each: a few percent); small grids cannot fill the wave with such chunks and
         // are latency-bound, so there the chunks shrink (down to 2T rows) to put every SM to work.
-        const bool heavy = (L.mode == MODE_STRICT || L.mode == MODE_IEEE) && L.sweeps >= 6;   // min_ctas<T, MODE>()
+        const bool heavy = ((L.mode == MODE_STRICT || L.mode == MODE_IEEE) && L.sweeps >= 6) ||
+                           (L.mode == MODE_PRESSURE && L.sweeps >= 6 && SF_PRESSURE_CTAS == 3);   // min_ctas<T, MODE>()
         const int slots = sm_count * (heavy ? 3 : 4) * WPC;
         int want_chunks = slots / A.nbands;
         if (want_chunks < 1) want_chunks = 1;
