@@ -90,7 +90,8 @@ def test_odd_iteration_count_lands_in_x(oracle):
     assert same(b, c)
 
 
-REF_CASES = [(14, 40, 5), (30, 4, 5), (62, 20, 10), (126, 20, 30), (126, 40, 10), (254, 20, 4), (1022, 20, 2)]
+# the first four: the smallest grids (G = 3, 4, 5, 8), where every cell touches a wall
+REF_CASES = [(1, 2, 4), (2, 4, 4), (3, 2, 4), (6, 4, 6), (14, 40, 5), (30, 4, 5), (62, 20, 10), (126, 20, 30), (126, 40, 10), (254, 20, 4), (1022, 20, 2)]
 
 
 @pytest.mark.parametrize("N,K,steps", REF_CASES)
