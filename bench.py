@@ -348,6 +348,11 @@ def run_ours(args):
             "note": "algorithmic bytes = 12 B per cell per sweep (read x, read x0, write x'); one launch fuses "
                     f"{K}/{jl} sweeps, so achieved exceeds the DRAM peak by design; traffic = ncu dram bytes per launch",
         }
+        tr = out["roofline"]["traffic"]
+        if tr:   # the same launch seen from DRAM: profiled bytes per launch / event-timed launch duration
+            dram = tr / (out["roofline"]["avg_launch_ms"] * 1e-3) / 1e9
+            out["roofline"]["dram_gbs"] = dram
+            out["roofline"]["dram_frac"] = dram / peak
         sr.close()
         # ---- end to end through the host-buffer entry point (sf_step_host): pinned host fields,
         # H2D of all six fields and D2H of dens,u,v inside the timed region, every step
