@@ -11,7 +11,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libstablefluids_b200.so")
-SOURCES = ["sf_api.cu", "sf_jacobi.cu", "sf_stages.cu", "sf_slab.cu"]
+SOURCES = ["sf_api.cu", "sf_jacobi.cu", "sf_stages.cu", "sf_slab.cu", "sf_solvers.cu"]
 HEADERS = ["sf_common.cuh", "sf_internal.h", os.path.join("..", "..", "include", "stablefluids.h")]
 
 NVCC_FLAGS = [

@@ -106,9 +106,25 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
     return SF_OK;
 }
 
+// SF_SOLVER_RBGS (opt-in, sf_solvers.cu): in place on x, iters x { red half-sweep, black half-sweep, set_bnd(b) }
+int rbgs_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters)
+{
+    if (!is_full_grid(c)) return fail(c, SF_ERR_UNSUPPORTED, "SF_SOLVER_RBGS: full-grid contexts only (no slabs yet)");
+    const int mode = arith_mode(c, alpha, beta);
+    const float omega = (float)c->omega_milli / 1000.0f;
+    for (int k = 0; k < iters; ++k) {
+        SF_CUDA(c, launch_rbgs_half_sweep(c->g, x, x0, 0, mode, alpha, beta, omega, c->work));
+        SF_CUDA(c, launch_rbgs_half_sweep(c->g, x, x0, 1, mode, alpha, beta, omega, c->work));
+        SF_CUDA(c, launch_set_bnd(c->g, b, x, c->work));
+        c->launches += 3;
+    }
+    return SF_OK;
+}
+
 // lin_solve: result always ends in x.
 int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess)
 {
+    if (c->solver == SF_SOLVER_RBGS) return rbgs_solve(c, b, x, x0, alpha, beta, iters);   // (never called with zero_guess)
     if (is_linked_slab(c)) return slab_lin_solve(c, b, x, x0, alpha, beta, iters, zero_guess);
     int rc = ensure_scratch(c);
     if (rc) return rc;
@@ -133,6 +149,8 @@ int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, floa
 
 int check_multi_launch_ok(sf_context *c, int iters)
 {
+    if (c->solver == SF_SOLVER_RBGS && !is_full_grid(c))
+        return fail(c, SF_ERR_UNSUPPORTED, "SF_SOLVER_RBGS: full-grid contexts only (no slabs yet)");
     if (is_full_grid(c) || is_linked_slab(c)) return SF_OK;
     const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
     const int L = (int)plan_launches(iters, stream_ok ? default_sweeps(c) : 1).size();
@@ -172,7 +190,8 @@ int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int
 {
     if (is_linked_slab(c)) return slab_project(c, u, v, p, div, iters);
     // the streaming lin_solve can start from an implicit zero guess, so p need not be written here
-    const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic;
+    // (the in-place red-black solver reads its guess: p is zeroed like in the reference)
+    const bool stream_ok = jacobi_stream_supported(c->g) && !c->force_generic && c->solver == SF_SOLVER_JACOBI;
     SF_CUDA(c, launch_divergence(c->g, u, v, p, div, stream_ok ? 0 : 1, c->work));
     ++c->launches;
     int rc = lin_solve(c, 0, p, div, 1.0f, 4.0f, iters, stream_ok ? 1 : 0);
@@ -242,7 +261,8 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.f[0] = f0; k.f[1] = f1; k.f[2] = f2;
     k.iters = iters;
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
-    k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan;
+    k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan + 16 * c->solver +
+                32 * c->omega_milli;
     return k;
 }
 
@@ -346,6 +366,12 @@ int sf_set_option(sf_context *c, int option, int value)
             break;
         }
         case SF_OPT_PRESSURE_PLAN: c->pressure_plan = value ? 1 : 0; break;
+        case SF_OPT_SOLVER:
+            SF_REQUIRE(c, value == SF_SOLVER_JACOBI || value == SF_SOLVER_RBGS, "solver: 0 Jacobi (reference) / 1 red-black Gauss-Seidel");
+            if (value == SF_SOLVER_RBGS && !is_full_grid(c)) return fail(c, SF_ERR_UNSUPPORTED, "SF_SOLVER_RBGS: full-grid contexts only (no slabs yet)");
+            c->solver = value;
+            break;
+        case SF_OPT_SOR_OMEGA_MILLI: SF_REQUIRE(c, value >= 1 && value <= 1999, "SOR omega in 1/1000: 1..1999"); c->omega_milli = value; break;
         case SF_OPT_STEAL_SCOPE: SF_REQUIRE(c, value == 0 || value == 1, "steal scope: 0 scalar fields / 1 every strict solve"); c->steal_scope = value; break;
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }
@@ -365,6 +391,8 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_WORK_STEALING: *value = c->steal_opt; break;
         case SF_OPT_STEAL_SCOPE: *value = c->steal_scope; break;
         case SF_OPT_PRESSURE_PLAN: *value = c->pressure_plan; break;
+        case SF_OPT_SOLVER: *value = c->solver; break;
+        case SF_OPT_SOR_OMEGA_MILLI: *value = c->omega_milli; break;
         case SF_OPT_STEAL_COUNT: {   // diagnostics: row ranges taken over by another warp so far (synchronises)
             *value = 0;
             if (c->steal) {

@@ -267,6 +267,9 @@ struct JacobiLaunch {
 cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_count, cudaStream_t st);
 cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStream_t st);
 bool jacobi_stream_supported(const Geom &g);
+// opt-in red-black Gauss-Seidel / SOR (sf_solvers.cu): one in-place half-sweep over the cells of one colour
+cudaError_t launch_rbgs_half_sweep(const Geom &g, float *x, const float *rhs, int colour, int mode, float alpha, float beta,
+                                   float omega, cudaStream_t st);
 // Exhaustive device check of div_const against __fdiv_rn for this beta (cached per process).
 // Returns true when MODE_STRICT may be used.  Synchronises `st`; must not be called while `st`
 // is being captured (pass allow_run = false to only consult the cache).

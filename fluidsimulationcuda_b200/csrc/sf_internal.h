@@ -77,6 +77,8 @@ struct sf_context {
     int steal_opt = 30;              // SF_OPT_WORK_STEALING (percent; 0 = off)
     int steal_scope = 0;             // SF_OPT_STEAL_SCOPE
     int pressure_plan = 1;           // SF_OPT_PRESSURE_PLAN
+    int solver = SF_SOLVER_JACOBI;   // SF_OPT_SOLVER
+    int omega_milli = 1000;          // SF_OPT_SOR_OMEGA_MILLI
     bool steal_now = false;          // set by the drivers around the solves that are worth it (see lin_solve)
     float *red_f = nullptr;          // reduction outputs
     double *red_d = nullptr;

@@ -32,7 +32,10 @@ SF_OPT_WORK_STEALING = 7
 SF_OPT_STEAL_COUNT = 8
 SF_OPT_STEAL_SCOPE = 9
 SF_OPT_PRESSURE_PLAN = 10
+SF_OPT_SOLVER = 11
+SF_OPT_SOR_OMEGA_MILLI = 12
 STRICT, FAST = 0, 1
+SOLVER_JACOBI, SOLVER_RBGS = 0, 1    # SF_OPT_SOLVER: the reference's Jacobi (default) / opt-in red-black Gauss-Seidel (SOR)
 
 # every symbol include/stablefluids.h declares (tests/test_abi.py checks the library exports them)
 ABI_SYMBOLS = [

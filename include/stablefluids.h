@@ -81,9 +81,21 @@ enum {
     /* 1 (default): a lin_solve that starts from the implicit zero guess (the pressure solves of
      * sf_project) may take an odd number of launches (its first launch does not read x, so it may
      * write x); 0 = the even-count plan of every other solve.  Results are unchanged. */
-    SF_OPT_PRESSURE_PLAN = 10
+    SF_OPT_PRESSURE_PLAN = 10,
+    /* which scheme lin_solve (sf_diffuse, sf_project and the solves inside the step functions) runs.
+     * SF_SOLVER_JACOBI (default) = the reference's double-buffered Jacobi (seq:85-104): results
+     * bit-identical to the reference.  SF_SOLVER_RBGS = red-black Gauss-Seidel, in place: per iteration
+     * a half-sweep over the cells with (row + col) even, one over the odd cells, then set_bnd(b); same
+     * cell formula and operand order.  NOT the reference's scheme -- it converges about twice as fast per
+     * iteration, so results differ from the reference by design; they are bit-identical to a CPU build of
+     * the same scheme (oracle/rbgs_check.c, tests/test_zz_solvers_gpu.py).  Full-grid contexts only. */
+    SF_OPT_SOLVER = 11,
+    /* SF_SOLVER_RBGS only: over-relaxation factor omega in 1/1000 (1..1999; default 1000 = plain
+     * Gauss-Seidel).  omega != 1: x = x + omega*(gs - x), three separately rounded operations. */
+    SF_OPT_SOR_OMEGA_MILLI = 12
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
+enum { SF_SOLVER_JACOBI = 0, SF_SOLVER_RBGS = 1 };
 
 /* ---- context -------------------------------------------------------------------------------- */
 

@@ -4,6 +4,8 @@ Two things are bound here:
 
 * ``Oracle``      -- oracle/libstam_oracle[_omp].so, the parametrised restatement of
                      /root/reference/project/sequential/FluidSequential.c.
+* ``RedBlackCheck``-- oracle/librbgs_check.so, a CPU build of the product's opt-in red-black solver (ours, not
+                     the reference's; the restatement is compiled into it a second time for the step functions).
 * ``ReferenceSeq``-- oracle/_ref/libref_seq_N<N>_K<K>.so, the reference's own translation unit
                      compiled from where it lies (oracle/Makefile target ``ref``); N and the
                      iteration count are compile-time literals there, so one library per (N, K).
@@ -30,8 +32,7 @@ def _ptr(a: np.ndarray):
 
 def build(force: bool = False) -> None:
     """Compile the restatement (and, when /root/reference is present, the reference builds)."""
-    have = os.path.exists(os.path.join(HERE, "libstam_oracle.so")) and os.path.exists(
-        os.path.join(HERE, "libstam_oracle_omp.so"))
+    have = all(os.path.exists(os.path.join(HERE, n)) for n in ("libstam_oracle.so", "libstam_oracle_omp.so", "librbgs_check.so"))
     if force or not have:
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if os.path.isdir("/root/reference/project"):
@@ -41,8 +42,10 @@ def build(force: bool = False) -> None:
 class Oracle:
     """Parametrised restatement.  ``threads=True`` loads the OpenMP build (identical results)."""
 
+    LIBNAME = None    # subclasses load another build of the same entry points
+
     def __init__(self, threads: bool = False):
-        name = "libstam_oracle_omp.so" if threads else "libstam_oracle.so"
+        name = self.LIBNAME or ("libstam_oracle_omp.so" if threads else "libstam_oracle.so")
         path = os.path.join(HERE, name)
         if not os.path.exists(path):
             build()
@@ -94,6 +97,30 @@ class Oracle:
     def run_steps(self, N, steps, s, visc, diff, dt, iters, first_step=0):
         self.L.so_run_steps(N, steps, first_step, _ptr(s["dens"]), _ptr(s["dens_prev"]), _ptr(s["u"]),
                             _ptr(s["u_prev"]), _ptr(s["v"]), _ptr(s["v_prev"]), visc, diff, dt, iters)
+
+
+class RedBlackCheck(Oracle):
+    """CPU build of the product's OPT-IN red-black Gauss-Seidel / SOR solver (oracle/rbgs_check.c) -- not a
+    reference path.  Same entry points as ``Oracle``; ``set_solver(1, omega)`` routes the solves inside
+    dens_step / vel_step / run_steps through the red-black scheme, ``set_solver(0)`` back to the reference's Jacobi."""
+
+    LIBNAME = "librbgs_check.so"
+
+    def __init__(self):
+        super().__init__(threads=True)
+        i, f = C.c_int, C.c_float
+        self.L.rb_set_solver.argtypes = [i, f]
+        self.L.rb_set_solver.restype = None
+        self.L.rb_lin_solve.argtypes = [i, i, FP, FP, f, f, i, f]
+        self.L.rb_lin_solve.restype = None
+        self.L.rb_residual_sumsq.argtypes = [i, FP, FP, f, f]
+        self.L.rb_residual_sumsq.restype = C.c_double
+
+    def set_solver(self, solver: int, omega: float = 1.0): self.L.rb_set_solver(solver, omega)
+    def rb_diffuse(self, N, b, x, x0, alpha, beta, iters, omega=1.0):
+        self.L.rb_lin_solve(N, b, _ptr(x), _ptr(x0), alpha, beta, iters, omega)
+    def residual_sumsq(self, N, x, x0, alpha, beta) -> float:
+        return float(self.L.rb_residual_sumsq(N, _ptr(x), _ptr(x0), alpha, beta))
 
 
 class ReferenceSeq:

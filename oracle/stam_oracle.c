@@ -26,6 +26,12 @@
 #include <string.h>
 
 #define AT(row, col) ((size_t)(row) * (size_t)G + (size_t)(col))
+/* The solver the step functions call.  Always so_lin_solve (the reference's Jacobi) in the oracle itself;
+ * oracle/rbgs_check.c re-compiles this file with its own dispatcher to check the product's OPT-IN red-black
+ * solver against a CPU build of the same scheme. */
+#ifndef SO_SOLVE
+#define SO_SOLVE so_lin_solve
+#endif
 
 /* FluidSequential.c:62-75 -- wall cells mirror the adjacent interior cell (negated on the
  * left/right walls for b==1, on the top/bottom walls for b==2); corners average their two
@@ -173,7 +179,7 @@ void so_dens_step(int N, float *x, float *x0, const float *u, const float *v, fl
     so_add_source(N, x, x0, dt);
     float alpha = dt * diff * (float)N * (float)N; /* :179 left-to-right */
     float beta = 1.0f + 4.0f * alpha;               /* :180 */
-    so_lin_solve(N, 0, x0, x, alpha, beta, iters);
+    SO_SOLVE(N, 0, x0, x, alpha, beta, iters);
     so_advect(N, 0, x, x0, u, v, dt);
 }
 
@@ -184,18 +190,18 @@ void so_vel_step(int N, float *u, float *v, float *u0, float *v0, float visc, fl
     so_add_source(N, v, v0, dt);
     float alpha = dt * visc * (float)N * (float)N; /* :199 */
     float beta = 1.0f + 4.0f * alpha;               /* :200 */
-    so_lin_solve(N, 1, u0, u, alpha, beta, iters);  /* :201-204 */
-    so_lin_solve(N, 2, v0, v, alpha, beta, iters);  /* :209-210 */
+    SO_SOLVE(N, 1, u0, u, alpha, beta, iters);  /* :201-204 */
+    SO_SOLVE(N, 2, v0, v, alpha, beta, iters);  /* :209-210 */
     /* project #1 on (u0, v0); u holds p, v holds div  (:213-223) */
     so_compute_divergence_and_pressure(N, u0, v0, u, v);
-    so_lin_solve(N, 0, u, v, 1.0f, 4.0f, iters);
+    SO_SOLVE(N, 0, u, v, 1.0f, 4.0f, iters);
     so_last_project(N, u0, v0, u, v);
     /* :228-237 advect both components with the projected field */
     so_advect(N, 1, u, u0, u0, v0, dt);
     so_advect(N, 2, v, v0, u0, v0, dt);
     /* project #2 on (u, v); u0 holds p, v0 holds div (:238-240) */
     so_compute_divergence_and_pressure(N, u, v, u0, v0);
-    so_lin_solve(N, 0, u0, v0, 1.0f, 4.0f, iters);
+    SO_SOLVE(N, 0, u0, v0, 1.0f, 4.0f, iters);
     so_last_project(N, u, v, u0, v0);
 }
 
