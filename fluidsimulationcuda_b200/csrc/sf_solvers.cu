@@ -11,7 +11,7 @@
 //                x  = x + omega*(gs - x)       (omega != 1: SOR, three separately rounded operations)
 //
 // Cells of one colour only read cells of the other colour, so a half-sweep is order-independent and the
-// GPU result is BIT-IDENTICAL to a CPU build of the same scheme (oracle/rbgs_check.c; the north star asks
+// GPU result is BIT-IDENTICAL to a CPU build of the same scheme (kept with the tests; the north star asks
 // exactly that of a red-black variant).  It is NOT the reference's scheme: results differ from the Jacobi
 // path by design, which is why it is opt-in.
 //
