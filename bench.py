@@ -353,6 +353,7 @@ def run_ours(args):
             dram = tr / (out["roofline"]["avg_launch_ms"] * 1e-3) / 1e9
             out["roofline"]["dram_gbs"] = dram
             out["roofline"]["dram_frac"] = dram / peak
+            out["roofline"]["dram_bytes_per_cell_update"] = tr / (cells * (K / jl))     # 12 without temporal blocking
         sr.close()
         # ---- end to end through the host-buffer entry point (sf_step_host): pinned host fields,
         # H2D of all six fields and D2H of dens,u,v inside the timed region, every step
