@@ -60,3 +60,17 @@ def test_product_does_not_touch_oracle():
                     if re.search(r"(^|\W)(import oracle|from oracle|oracle/|stam_oracle|pyoracle)", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_option_constants_match_the_header():
+    """solver.py mirrors the SF_OPT_* / SF_SOLVER_* / SF_ARITH_* enumerators of stablefluids.h by value."""
+    from fluidsimulationcuda_b200 import solver
+    hdr = open(os.path.join(ROOT, "include", "stablefluids.h")).read()
+    enums = {k: int(v) for k, v in re.findall(r"\b(SF_[A-Z_]+)\s*=\s*(-?\d+)", hdr)}
+    opts = {k: v for k, v in enums.items() if k.startswith("SF_OPT_")}
+    assert len(opts) >= 12 and len(set(opts.values())) == len(opts), "option numbers must be unique"
+    for name, value in opts.items():
+        assert getattr(solver, name) == value, name
+    assert (solver.STRICT, solver.FAST) == (enums["SF_ARITH_STRICT"], enums["SF_ARITH_FAST"])
+    assert (solver.SOLVER_JACOBI, solver.SOLVER_RBGS) == (enums["SF_SOLVER_JACOBI"], enums["SF_SOLVER_RBGS"])
+    assert (solver.SF_SLAB_ERR_TIMEOUT, solver.SF_SLAB_ERR_REACH) == (enums["SF_SLAB_ERR_TIMEOUT"], enums["SF_SLAB_ERR_REACH"])
