@@ -1,0 +1,17 @@
+"""Host-side model checks of kernel control flow (no GPU): see tools/models/."""
+import importlib.util
+import os
+
+from conftest import ROOT
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", "models", name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_inner_loop_restructuring_visits_the_same_ticks():
+    """SF_INNER_LOOP (build option of csrc/sf_jacobi.cu) must not change which rows run which tick."""
+    _load("loop_equivalence").main(trials=3000, seed=7)
