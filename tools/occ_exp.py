@@ -1,3 +1,4 @@
+"""Developer probe: lin_solve time at depth 3 on a small and a large grid (occupancy experiments; honours SF_LIBRARY)."""
 import sys; sys.path.insert(0, ".")
 import torch
 from fluidsimulationcuda_b200 import solver as SF

@@ -1,3 +1,4 @@
+"""Developer probe: step time on small grids (G = 128 .. 4096), where launches, not bandwidth, bound the step."""
 import sys; sys.path.insert(0, ".")
 import torch
 from fluidsimulationcuda_b200 import solver as SF

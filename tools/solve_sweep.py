@@ -1,3 +1,4 @@
+"""Developer probe: lin_solve time at depths 5 and 7 per arithmetic mode; argv[1] = staging (0 cp.async, 1 bulk copy)."""
 import sys; sys.path.insert(0, ".")
 import torch, os
 from fluidsimulationcuda_b200 import solver as SF
