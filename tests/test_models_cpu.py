@@ -15,3 +15,9 @@ def _load(name):
 def test_inner_loop_restructuring_visits_the_same_ticks():
     """SF_INNER_LOOP (build option of csrc/sf_jacobi.cu) must not change which rows run which tick."""
     _load("loop_equivalence").main(trials=3000, seed=7)
+
+
+def test_stream_kernel_model_matches_the_oracle_on_the_smallest_grids():
+    """The numpy transcription of jacobi_stream_kernel (pipeline, fused set_bnd, fast groups, chunking, launch plan, implicit
+    zero guess; unloaded data = NaN) is bit-identical to the oracle at G = 4, 8, 12, 32 and at a two-band width."""
+    _load("stream_model").main(sizes=(2, 6, 10, 30, 114))
