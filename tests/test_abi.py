@@ -74,3 +74,23 @@ def test_option_constants_match_the_header():
     assert (solver.STRICT, solver.FAST) == (enums["SF_ARITH_STRICT"], enums["SF_ARITH_FAST"])
     assert (solver.SOLVER_JACOBI, solver.SOLVER_RBGS) == (enums["SF_SOLVER_JACOBI"], enums["SF_SOLVER_RBGS"])
     assert (solver.SF_SLAB_ERR_TIMEOUT, solver.SF_SLAB_ERR_REACH) == (enums["SF_SLAB_ERR_TIMEOUT"], enums["SF_SLAB_ERR_REACH"])
+
+
+def test_c_example_compiles_and_links_as_c(tmp_path):
+    """The header pair (stablefluids.h + stablefluids_compat.h, the reference's own function names) is plain C and the
+    example links against the library -- and, with no CUDA device here, the program reports the error instead of
+    computing anything (the GPU suite runs it for real)."""
+    import shutil, subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else (shutil.which("gcc") or shutil.which("cc"))
+    if cc is None:
+        pytest.skip("no C compiler")
+    _lib()
+    exe = str(tmp_path / "fluid_main")
+    lib = os.path.join(ROOT, "fluidsimulationcuda_b200")
+    subprocess.check_call([cc, "-std=c11", "-Wall", "-Werror", "-O1", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "fluid_main.c"), "-L" + lib, "-lstablefluids_b200",
+                           "-Wl,-rpath," + lib, "-o", exe])
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "14", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode != 0 and "sum(dens)" not in r.stdout, (r.returncode, r.stdout, r.stderr)
