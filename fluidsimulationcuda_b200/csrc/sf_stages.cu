@@ -67,8 +67,11 @@ __global__ void set_bnd_kernel(float *x, Geom g, float sx, float sy)
     if (bot) x[(size_t)(N + 1 - g.row_base) * G + k] = __fmul_rn(sy, x[(size_t)(N - g.row_base) * G + k]);
     // corners: computed from the interior values that define the adjacent wall cells, so no
     // ordering between threads is needed (x[0][1] = sy*x[1][1], x[1][0] = sx*x[1][1], ...)
-    if (k == 1 || k == N) {
-        const int col = k, wc = (k == 1) ? 0 : N + 1;
+    // (two separate tests: at N == 1 the one thread owns the left AND the right corners)
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        if (k != (side == 0 ? 1 : N)) continue;
+        const int col = k, wc = (side == 0) ? 0 : N + 1;
         if (top) {
             const float a = x[(size_t)(1 - g.row_base) * G + col];
             x[(size_t)(0 - g.row_base) * G + wc] = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(sy, a), __fmul_rn(sx, a)));
