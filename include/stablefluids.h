@@ -88,7 +88,7 @@ enum {
      * a half-sweep over the cells with (row + col) even, one over the odd cells, then set_bnd(b); same
      * cell formula and operand order.  NOT the reference's scheme -- it converges about twice as fast per
      * iteration, so results differ from the reference by design; they are bit-identical to a CPU build of
-     * the same scheme (tests/test_zz_solvers_gpu.py).  Full-grid contexts only. */
+     * the same scheme (tests/test_zzz_solvers_gpu.py).  Full-grid contexts only. */
     SF_OPT_SOLVER = 11,
     /* SF_SOLVER_RBGS only: over-relaxation factor omega in 1/1000 (1..1999; default 1000 = plain
      * Gauss-Seidel).  omega != 1: x = x + omega*(gs - x), three separately rounded operations. */

@@ -7,7 +7,7 @@
  * (fluidsimulationcuda_b200/csrc/sf_solvers.cu); BASELINE.json's north star asks
  * that a red-black variant be "validated against a CPU red-black build" -- this file is that build.
  * A half-sweep only reads cells of the other colour, so the scheme is order-independent and the GPU must
- * match it BITWISE (tests/test_zz_solvers_gpu.py).
+ * match it BITWISE (tests/test_zzz_solvers_gpu.py).
  *
  * Scheme (one iteration): red half-sweep ((row + col) even), black half-sweep ((row + col) odd), set_bnd(b);
  * cell update gs = (x0 + alpha*(((l + r) + up) + dn)) / beta with the reference's operand order

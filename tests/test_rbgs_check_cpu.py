@@ -1,5 +1,5 @@
 """CPU checks of oracle/rbgs_check.c, the CPU build the product's opt-in red-black Gauss-Seidel / SOR solver
-(SF_OPT_SOLVER = SF_SOLVER_RBGS) is validated against on the GPU (tests/test_zz_solvers_gpu.py).  Not a
+(SF_OPT_SOLVER = SF_SOLVER_RBGS) is validated against on the GPU (tests/test_zzz_solvers_gpu.py).  Not a
 reference path: the reference solves with Jacobi only."""
 import numpy as np
 import pytest
