@@ -21,3 +21,9 @@ def test_stream_kernel_model_matches_the_oracle_on_the_smallest_grids():
     """The numpy transcription of jacobi_stream_kernel (pipeline, fused set_bnd, fast groups, chunking, launch plan, implicit
     zero guess; unloaded data = NaN) is bit-identical to the oracle at G = 4, 8, 12, 32 and at a two-band width."""
     _load("stream_model").main(sizes=(2, 6, 10, 30, 114))
+
+
+def test_temporally_blocked_red_black_design_matches_the_in_place_scheme():
+    """Design check for the next step of the opt-in solver: red-black Gauss-Seidel / SOR on the streaming pipeline
+    (one iteration = two levels, colour-masked updates, set_bnd on black levels) is bit-identical to the in-place scheme."""
+    _load("rbgs_blocked_model").main(sizes=(2, 6, 14, 114))
