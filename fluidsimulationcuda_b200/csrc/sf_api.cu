@@ -112,6 +112,28 @@ int rbgs_solve(sf_context *c, int b, float *x, const float *x0, float alpha, flo
     if (!is_full_grid(c)) return fail(c, SF_ERR_UNSUPPORTED, "SF_SOLVER_RBGS: full-grid contexts only (no slabs yet)");
     const int mode = arith_mode(c, alpha, beta);
     const float omega = (float)c->omega_milli / 1000.0f;
+    if (c->rbgs_blocked && stream_kernels_ok(c) && mode != MODE_FAST) {
+        // SF_OPT_RBGS_BLOCKED: the same scheme on the streaming pipeline, three iterations (six levels) per launch,
+        // ping-pong between x and the scratch field like the Jacobi path
+        int rc = ensure_scratch(c);
+        if (rc) return rc;
+        float *cur = x, *nxt = c->scratch;
+        for (int done = 0; done < iters;) {
+            const int k = iters - done < 3 ? iters - done : 3;
+            JacobiLaunch L;
+            L.xin = cur; L.rhs = x0; L.xout = nxt;
+            L.alpha = alpha; L.beta = beta; L.b = b; L.sweeps = 2 * k; L.mode = mode;
+            L.out_lo = c->g.own_lo; L.out_hi = c->g.own_hi;
+            L.chunk_rows = c->chunk_rows; L.zero_guess = 0; L.staging = 0;
+            L.rb = 1; L.omega = omega;
+            SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, c->work));
+            ++c->launches;
+            float *t = cur; cur = nxt; nxt = t;
+            done += k;
+        }
+        if (cur != x) SF_CUDA(c, cudaMemcpyAsync(x, cur, field_cells(c) * sizeof(float), cudaMemcpyDeviceToDevice, c->work));
+        return SF_OK;
+    }
     for (int k = 0; k < iters; ++k) {
         SF_CUDA(c, launch_rbgs_half_sweep(c->g, x, x0, 0, mode, alpha, beta, omega, c->work));
         SF_CUDA(c, launch_rbgs_half_sweep(c->g, x, x0, 1, mode, alpha, beta, omega, c->work));
@@ -262,7 +284,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.iters = iters;
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
     k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan + 16 * c->solver +
-                32 * c->omega_milli;
+                32 * c->omega_milli + 65536 * c->rbgs_blocked;
     return k;
 }
 
@@ -372,6 +394,7 @@ int sf_set_option(sf_context *c, int option, int value)
             c->solver = value;
             break;
         case SF_OPT_SOR_OMEGA_MILLI: SF_REQUIRE(c, value >= 1 && value <= 1999, "SOR omega in 1/1000: 1..1999"); c->omega_milli = value; break;
+        case SF_OPT_RBGS_BLOCKED: c->rbgs_blocked = value ? 1 : 0; break;
         case SF_OPT_STEAL_SCOPE: SF_REQUIRE(c, value == 0 || value == 1, "steal scope: 0 scalar fields / 1 every strict solve"); c->steal_scope = value; break;
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }
@@ -393,6 +416,7 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_PRESSURE_PLAN: *value = c->pressure_plan; break;
         case SF_OPT_SOLVER: *value = c->solver; break;
         case SF_OPT_SOR_OMEGA_MILLI: *value = c->omega_milli; break;
+        case SF_OPT_RBGS_BLOCKED: *value = c->rbgs_blocked; break;
         case SF_OPT_STEAL_COUNT: {   // diagnostics: row ranges taken over by another warp so far (synchronises)
             *value = 0;
             if (c->steal) {

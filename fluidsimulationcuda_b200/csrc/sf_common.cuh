@@ -263,6 +263,9 @@ struct JacobiLaunch {
     // row-level work stealing (nullptr = off): device control block with room for steal_capacity items
     StealCtl *steal = nullptr;
     int steal_capacity = 0;
+    // opt-in red-black Gauss-Seidel / SOR on the streaming pipeline: `sweeps` LEVELS (even: two per iteration)
+    int rb = 0;
+    float omega = 1.0f;
 };
 cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_count, cudaStream_t st);
 cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStream_t st);

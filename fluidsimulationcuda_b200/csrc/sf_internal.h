@@ -79,6 +79,7 @@ struct sf_context {
     int pressure_plan = 1;           // SF_OPT_PRESSURE_PLAN
     int solver = SF_SOLVER_JACOBI;   // SF_OPT_SOLVER
     int omega_milli = 1000;          // SF_OPT_SOR_OMEGA_MILLI
+    int rbgs_blocked = 0;            // SF_OPT_RBGS_BLOCKED
     bool steal_now = false;          // set by the drivers around the solves that are worth it (see lin_solve)
     float *red_f = nullptr;          // reduction outputs
     double *red_d = nullptr;

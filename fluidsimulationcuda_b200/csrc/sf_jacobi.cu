@@ -291,7 +291,12 @@ __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rg
 // WALLS adds the fused set_bnd handling.  Returns level T of row s-T in `out`.
 // EDGE = false: the warp's band touches neither wall column (72 of the 74 bands at G = 8192): the two
 // predicated wall multiplies per level are not even issued.
-template <int T, int MODE, int PH, bool WALLS, bool EDGE = true>
+// RB = true (opt-in red-black Gauss-Seidel / SOR, SF_OPT_RBGS_BLOCKED; design checked in tools/models/rbgs_blocked_model.py):
+// one red-black ITERATION is two LEVELS -- level t+1 with t even is the state after the red half-sweep ((row + col) even),
+// with t odd after the black one -- a level updates the cells of its colour and copies the others through, and set_bnd acts
+// on black levels only (wall columns and wall rows copy through on red levels).  A lane's first column is a multiple of 4,
+// so which two of its four cells a level updates is warp-uniform.  omega travels in A.div.pad (1.0f = plain Gauss-Seidel).
+template <int T, int MODE, int PH, bool WALLS, bool EDGE = true, bool RB = false>
 __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const float4 &row_in, float4 (&W)[T][3],
                                               const float4 *rring, bool ownsL, bool ownsR, float4 &out)
 {
@@ -306,6 +311,35 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
         const float lft = __shfl_up_sync(0xffffffffu, mid.w, 1);
         const float rgt = __shfl_down_sync(0xffffffffu, mid.x, 1);
         float4 o = jacobi4<MODE, WALLS>(lft, mid, rgt, up, dn, r, A.alpha, A.div, ok);
+        if constexpr (RB) {
+            const bool black = (t & 1) != 0;                 // compile-time: t is an unrolled index
+            const float om = A.div.pad;
+            if (om != 1.0f) {                                // SOR: x + omega*(gs - x), three roundings (warp-uniform branch)
+                o.x = __fadd_rn(mid.x, __fmul_rn(om, __fsub_rn(o.x, mid.x)));
+                o.y = __fadd_rn(mid.y, __fmul_rn(om, __fsub_rn(o.y, mid.y)));
+                o.z = __fadd_rn(mid.z, __fmul_rn(om, __fsub_rn(o.z, mid.z)));
+                o.w = __fadd_rn(mid.w, __fmul_rn(om, __fsub_rn(o.w, mid.w)));
+            }
+            // cell (a, c + k) belongs to this level iff ((a + k) & 1) == colour, colour = black ? 1 : 0 (c is even)
+            const bool even_upd = (((a & 1) != 0) == black);
+            o.x = even_upd ? o.x : mid.x;
+            o.z = even_upd ? o.z : mid.z;
+            o.y = even_upd ? mid.y : o.y;
+            o.w = even_upd ? mid.w : o.w;
+            if (black) {
+                if (ownsL) o.x = __fmul_rn(A.sx, o.y);
+                if (ownsR) o.w = __fmul_rn(A.sx, o.z);
+            } else {
+                if (ownsL) o.x = mid.x;
+                if (ownsR) o.w = mid.w;
+            }
+            if (WALLS) {
+                if (t + 1 < T) {
+                    if (a == A.N + 1) o = black ? scale4(W[t + 1][MID], A.sy) : mid;     // row N+1 of level t+1
+                    if (a == 1) W[t + 1][MID] = black ? scale4(o, A.sy) : up;            // row 0 of level t+1
+                }
+            }
+        } else {
         // wall columns: x[row][0] = sx * x[row][1], x[row][N+1] = sx * x[row][N]  (two predicated
         // multiplies; only the lanes holding columns 0 / N+1 of the two edge bands execute them)
         if (EDGE) {
@@ -318,6 +352,7 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
                 if (a == A.N + 1) o = scale4(W[t + 1][MID], A.sy);     // row N+1 = sy * row N
                 if (a == 1) W[t + 1][MID] = scale4(o, A.sy);           // row 0   = sy * row 1
             }
+        }
         }
         if (t + 1 < T) W[t + 1][DN] = o; else out = o;
     }
@@ -332,7 +367,7 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
 // peer + row * pitch, the neighbour GPU's copy of the field (pre-offset so that global row numbers index it).
 // STEAL = true: the warp's slot (A.steal->slots[global warp]) holds its published range; the end may be
 // lowered by another warp at any time.
-template <int T, int MODE, bool TMA, bool STRIP, bool STEAL>
+template <int T, int MODE, bool TMA, bool STRIP, bool STEAL, bool RB = false>
 __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, const int lane, const int warp, const int band,
                                             const int a_lo, const int a_hi, float *peer)
 {
@@ -512,7 +547,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
     // general tick at phase 0 followed by the register rotation that restores phase 0
     auto general_tick = [&](int s_, const float4 &row_in) {
         float4 o;
-        pipeline_tick<T, MODE, 0, true>(A, s_, row_in, W, rring, ownsL, ownsR, o);
+        pipeline_tick<T, MODE, 0, true, true, RB>(A, s_, row_in, W, rring, ownsL, ownsR, o);
         emit_walls(s_ - T, o);
 #pragma unroll
         for (int t = 0; t < T; ++t) { W[t][0] = W[t][1]; W[t][1] = W[t][2]; }
@@ -572,18 +607,18 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                         if (a >= first && a < a_hi && st_ok) *reinterpret_cast<float4 *>(A.xout + (e0 + (cell_t)(a - (s - T)) * Gu)) = ov;
                     };
                     if (edge_band) {
-                        ok = pipeline_tick<T, MODE, 0, false, true>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                        ok = pipeline_tick<T, MODE, 0, false, true, RB>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
                         emit_plain(s - T, o);
-                        ok &= pipeline_tick<T, MODE, 1, false, true>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                        ok &= pipeline_tick<T, MODE, 1, false, true, RB>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
                         emit_plain(s + 1 - T, o);
-                        ok &= pipeline_tick<T, MODE, 2, false, true>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                        ok &= pipeline_tick<T, MODE, 2, false, true, RB>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
                         emit_plain(s + 2 - T, o);
                     } else {
-                        ok = pipeline_tick<T, MODE, 0, false, false>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                        ok = pipeline_tick<T, MODE, 0, false, false, RB>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
                         emit_plain(s - T, o);
-                        ok &= pipeline_tick<T, MODE, 1, false, false>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                        ok &= pipeline_tick<T, MODE, 1, false, false, RB>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
                         emit_plain(s + 1 - T, o);
-                        ok &= pipeline_tick<T, MODE, 2, false, false>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                        ok &= pipeline_tick<T, MODE, 2, false, false, RB>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
                         emit_plain(s + 2 - T, o);
                     }
                     if (GROUP_VOTE && !__all_sync(0xffffffffu, ok)) {
@@ -598,7 +633,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     s += 3;
                     continue;
                 } else {
-                bool ok = pipeline_tick<T, MODE, 0, false>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                bool ok = pipeline_tick<T, MODE, 0, false, true, RB>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
                 if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
                     slow_until = next64(s + 3);        // windows are still at phase 0: redo guarded
                     general_tick(s, xrow(s)); s += 1;
@@ -607,7 +642,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     continue;
                 }
                 emit_plain(s - T, o);
-                ok = pipeline_tick<T, MODE, 1, false>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                ok = pipeline_tick<T, MODE, 1, false, true, RB>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
                 if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
                     slow_until = next64(s + 3);        // phase 1 -> phase 0: up = slot 1, mid = slot 2
 #pragma unroll
@@ -618,7 +653,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     continue;
                 }
                 emit_plain(s + 1 - T, o);
-                ok = pipeline_tick<T, MODE, 2, false>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                ok = pipeline_tick<T, MODE, 2, false, true, RB>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
                 if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
                     slow_until = next64(s + 3);        // phase 2 -> phase 0: up = slot 2, mid = slot 0
 #pragma unroll
@@ -751,7 +786,7 @@ __device__ __noinline__ void strip_warp(const StreamArgs A, float4 *ring, const 
 template <int T, int MODE, int VAR>
 __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
 {
-    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2 || VAR == 4), STEALS = (VAR == 3 || VAR == 4);
+    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2 || VAR == 4), STEALS = (VAR == 3 || VAR == 4), RB = (VAR == 5);
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.
@@ -770,7 +805,7 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     const int a_hi = min(a_lo + A.chunk_rows, A.a_hi);
     if constexpr (!STEALS) {
         if (a_lo >= a_hi) return;
-        stream_rows<T, MODE, TMA, false, false>(A, ring, lane, warp, band, a_lo, a_hi, nullptr);
+        stream_rows<T, MODE, TMA, false, false, RB>(A, ring, lane, warp, band, a_lo, a_hi, nullptr);
     } else {
         int b = band, lo = a_lo, hi = a_hi;
         steal_publish(A.steal, b, lo, hi);
@@ -867,6 +902,19 @@ cudaError_t launch_stream_T(const StreamArgs &A, dim3 grid, size_t smem, bool tm
         return cudaGetLastError();
     }
     jacobi_stream_kernel<T, MODE, 0><<<grid, WPC * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+// red-black levels (VAR = 5): an even number of levels per launch (whole iterations), built for depths 2, 4 and 6
+template <int MODE>
+cudaError_t launch_stream_rb(int T, const StreamArgs &A, dim3 grid, size_t smem, cudaStream_t st)
+{
+    switch (T) {
+        case 2: jacobi_stream_kernel<2, MODE, 5><<<grid, WPC * 32, smem, st>>>(A); break;
+        case 4: jacobi_stream_kernel<4, MODE, 5><<<grid, WPC * 32, smem, st>>>(A); break;
+        case 6: jacobi_stream_kernel<6, MODE, 5><<<grid, WPC * 32, smem, st>>>(A); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
@@ -1011,6 +1059,25 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
                A.nbands * A.nchunks > 1) ? L.steal : nullptr;
     dim3 grid((items + WPC - 1) / WPC);
     const size_t smem = (size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4);
+    if (L.rb) {
+        // red-black levels: omega rides in the divisor block's spare word; the magnitude bound that keeps every numerator
+        // in the exact division's range grows per level by |1 - omega| + omega * F / beta instead of F / beta
+        if (A.strips != nullptr || L.staging == 1 || L.zero_guess) return cudaErrorNotSupported;
+        A.steal = nullptr;
+        A.div.pad = L.omega;
+        const double F = 1.0 + 4.0 * fabs((double)L.alpha), om = (double)L.omega;
+        double gl = (fabs(1.0 - om) + om * F / fabs((double)L.beta)) * 1.000001;
+        if (gl < 1.0) gl = 1.0;
+        double hi = (double)SF_DIV_HI / (F * 1.01) / (1.0 + om);    // (1 + omega): the relaxation step's own intermediate
+        for (int t = 0; t < L.sweeps; ++t) hi /= gl;
+        A.hi_in = (float)hi;
+        switch (L.mode) {
+            case MODE_PRESSURE: return launch_stream_rb<MODE_PRESSURE>(L.sweeps, A, grid, smem, st);
+            case MODE_STRICT: return launch_stream_rb<MODE_STRICT>(L.sweeps, A, grid, smem, st);
+            case MODE_IEEE: return launch_stream_rb<MODE_IEEE>(L.sweeps, A, grid, smem, st);
+            default: return cudaErrorNotSupported;
+        }
+    }
     switch (L.mode) {
         case MODE_PRESSURE: return launch_stream_mode<MODE_PRESSURE>(L.sweeps, A, grid, smem, L.staging == 1, st);
         case MODE_FAST: return launch_stream_mode<MODE_FAST>(L.sweeps, A, grid, smem, L.staging == 1, st);

@@ -34,6 +34,7 @@ SF_OPT_STEAL_SCOPE = 9
 SF_OPT_PRESSURE_PLAN = 10
 SF_OPT_SOLVER = 11
 SF_OPT_SOR_OMEGA_MILLI = 12
+SF_OPT_RBGS_BLOCKED = 13
 STRICT, FAST = 0, 1
 SOLVER_JACOBI, SOLVER_RBGS = 0, 1    # SF_OPT_SOLVER: the reference's Jacobi (default) / opt-in red-black Gauss-Seidel (SOR)
 

@@ -92,7 +92,11 @@ enum {
     SF_OPT_SOLVER = 11,
     /* SF_SOLVER_RBGS only: over-relaxation factor omega in 1/1000 (1..1999; default 1000 = plain
      * Gauss-Seidel).  omega != 1: x = x + omega*(gs - x), three separately rounded operations. */
-    SF_OPT_SOR_OMEGA_MILLI = 12
+    SF_OPT_SOR_OMEGA_MILLI = 12,
+    /* SF_SOLVER_RBGS only: 0 (default) = one kernel launch per half-sweep; 1 = the red-black sweeps run on the
+     * temporally blocked streaming pipeline of the Jacobi kernels (three iterations per launch; grid widths with
+     * (N+2) % 4 == 0, other widths keep the one-launch-per-half-sweep path).  Results are unchanged. */
+    SF_OPT_RBGS_BLOCKED = 13
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 enum { SF_SOLVER_JACOBI = 0, SF_SOLVER_RBGS = 1 };
