@@ -1,0 +1,103 @@
+"""The Jacobi kernels' OWN SOURCE, compiled for the host and run warp by warp with 32 threads per warp (tools/emu/):
+stream_rows, pipeline_tick, the exact division with its votes, guarded ticks and pipeline restarts, fused set_bnd, the
+red-black levels -- everything except the inline-PTX helpers, which get host equivalents.  Checked bitwise against the
+oracle (Jacobi) and against the in-place red-black scheme (SF_OPT_RBGS_BLOCKED), for the default build and for the
+compile-time variants that have not been on a GPU yet.  No GPU needed; the GPU suite remains the final word on the SASS."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+FP = C.POINTER(C.c_float)
+VARIANTS = {"default": (), "il2_edge": ("-DSF_INNER_LOOP=2", "-DSF_EDGE_SPLIT=1"), "il1": ("-DSF_INNER_LOOP=1",)}
+_libs = {}
+
+
+def emu(variant):
+    if variant not in _libs:
+        sys.path.insert(0, os.path.join(ROOT, "tools", "emu"))
+        import build_emu
+        L = C.CDLL(build_emu.build("" if variant == "default" else variant, VARIANTS[variant]))
+        L.emu_lin_solve.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.emu_lin_solve.restype = C.c_int
+        _libs[variant] = L
+    return _libs[variant]
+
+
+def p(a):
+    return a.ctypes.data_as(FP)
+
+
+def same(a, b):
+    return np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.fixture(scope="module")
+def rb():
+    from oracle.pyoracle import RedBlackCheck
+    return RedBlackCheck()
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_kernel_source_on_the_smallest_grids(oracle, variant):
+    L = emu(variant)
+    rng = np.random.default_rng(0)
+    for N in (2, 6, 10, 30):
+        G = N + 2
+        for T in ((1, 2, 3, 7, 8) if variant == "default" else (3, 7)):
+            for b, (al, be), K, zg in ((0, (1.0, 4.0), 5, 0), (1, (0.635, 3.54), 2 * T, 0), (2, (2683.2, 10733.8), T + 2, 0),
+                                       (0, (1.0, 4.0), 7, 1)):
+                x = rng.uniform(-1, 1, (G, G)).astype(np.float32); x0 = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+                if zg:
+                    x[...] = 0
+                want = x.copy(); oracle.diffuse(N, b, want, x0, al, be, K)
+                got = x.copy()
+                if zg:
+                    got[...] = np.nan          # an implicit zero guess is never read
+                assert L.emu_lin_solve(N, b, p(got), p(x0), al, be, K, T, zg, 0, 0, 1.0) == 0
+                assert same(got, want), (variant, N, T, b, K, zg)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_kernel_source_two_bands_chunks_and_a_decaying_front(oracle, variant):
+    """G = 128 (two bands), small chunks, and a compactly supported field whose front decays through the low end of the exact
+    division's range: outlier votes, guarded binary64 ticks and pipeline restarts of the strict kernel."""
+    L = emu(variant)
+    rng = np.random.default_rng(1)
+    N = 126; G = N + 2
+    x = rng.uniform(-1, 1, (G, G)).astype(np.float32); x0 = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+    for T, chunk, (al, be), K in ((7, 0, (0.635, 3.54), 14), (3, 24, (1.0, 4.0), 6)):
+        want = x.copy(); oracle.diffuse(N, 1, want, x0, al, be, K)
+        got = x.copy()
+        assert L.emu_lin_solve(N, 1, p(got), p(x0), al, be, K, T, 0, chunk, 0, 1.0) == 0
+        assert same(got, want), (variant, T, chunk)
+    src = np.zeros((G, G), np.float32)
+    src[50:70, 40:90] = rng.uniform(0, 1, (G, G)).astype(np.float32)[50:70, 40:90] * np.float32(1e-24)
+    al, be = 107322.0, 429289.0
+    want = np.zeros((G, G), np.float32); oracle.diffuse(N, 0, want, src, al, be, 14)
+    assert np.any((want != 0) & (np.abs(want) < 1e-30)), "the case must reach below the fast division's range"
+    got = np.zeros((G, G), np.float32)
+    assert L.emu_lin_solve(N, 0, p(got), p(src), al, be, 14, 7, 0, 0, 0, 1.0) == 0
+    assert same(got, want), (variant, "front")
+
+
+@pytest.mark.parametrize("variant", ["default", "il2_edge"])
+def test_red_black_levels_in_the_kernel_source(rb, variant):
+    """SF_OPT_RBGS_BLOCKED: jacobi_stream_kernel<T, MODE, 5> against the in-place red-black scheme."""
+    L = emu(variant)
+    rng = np.random.default_rng(2)
+    for N in (2, 6, 10, 30, 126):
+        G = N + 2
+        for om in (1.0, 1.5):
+            for b, (al, be), K in ((0, (1.0, 4.0), 7), (1, (0.635, 3.54), 5), (2, (2683.2, 10733.8), 4), (1, (0.635, 3.54), 1)):
+                if N == 126 and K > 5:
+                    continue
+                x = rng.uniform(-1, 1, (G, G)).astype(np.float32); x0 = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+                want = x.copy(); rb.rb_diffuse(N, b, want, x0, al, be, K, om)
+                got = x.copy()
+                assert L.emu_lin_solve(N, b, p(got), p(x0), al, be, K, 6, 0, 0, 1, om) == 0
+                assert same(got, want), (variant, N, om, b, K)

@@ -1,0 +1,138 @@
+// Host harness around the generated build of the Jacobi kernels' source (tools/emu/gen_emu.py): restates the launch
+// geometry of launch_jacobi_stream and the launch plan of lin_solve (csrc/sf_jacobi.cu, csrc/sf_api.cu), and runs
+// jacobi_stream_kernel<T, MODE, VAR> warp by warp with 32 host threads per warp.  Exposed to Python through ctypes
+// (tests/test_emu_cpu.py).  Test infrastructure: nothing in the product uses it.
+#include "emu_prelude.h"
+
+#include <thread>
+#include <vector>
+
+#include "_gen/emu_jacobi.inc"
+
+namespace sf {
+namespace {
+float4 ring[WPC * (RING_X + RING_R) * 32 + 256];     // the kernel's `extern __shared__ float4 ring[]` (+ mbarrier words)
+
+template <int T, int MODE, int VAR>
+void run_grid(const StreamArgs &A, int ctas)
+{
+    std::barrier<> bar(32);
+    emu::warp_barrier = &bar;
+    emu::g_dim = {(unsigned)ctas, 1, 1};
+    emu::b_dim = {(unsigned)(WPC * 32), 1, 1};
+    for (int cta = 0; cta < ctas; ++cta)
+        for (int warp = 0; warp < WPC; ++warp) {       // warps never synchronise with each other: one at a time
+            for (auto &v : ring) v = make_float4(NAN, NAN, NAN, NAN);    // stale shared memory is poison
+            std::vector<std::thread> lanes;
+            for (int l = 0; l < 32; ++l)
+                lanes.emplace_back([&, l] {
+                    emu::t_idx = {(unsigned)(warp * 32 + l), 0, 0};
+                    emu::b_idx = {(unsigned)cta, 0, 0};
+                    jacobi_stream_kernel<T, MODE, VAR>(A);
+                });
+            for (auto &t : lanes) t.join();
+        }
+}
+
+template <int MODE, int VAR>
+int run_T(int T, const StreamArgs &A, int ctas)
+{
+    switch (T) {
+        case 1: if constexpr (VAR != 5) { run_grid<1, MODE, VAR>(A, ctas); return 0; } break;
+        case 2: run_grid<2, MODE, VAR>(A, ctas); return 0;
+        case 3: if constexpr (VAR != 5) { run_grid<3, MODE, VAR>(A, ctas); return 0; } break;
+        case 4: run_grid<4, MODE, VAR>(A, ctas); return 0;
+        case 5: if constexpr (VAR != 5) { run_grid<5, MODE, VAR>(A, ctas); return 0; } break;
+        case 6: run_grid<6, MODE, VAR>(A, ctas); return 0;
+        case 7: if constexpr (VAR != 5) { run_grid<7, MODE, VAR>(A, ctas); return 0; } break;
+        case 8: if constexpr (VAR != 5) { run_grid<8, MODE, VAR>(A, ctas); return 0; } break;
+    }
+    return -1;
+}
+
+// launch_jacobi_stream (csrc/sf_jacobi.cu) for a full-grid context: same geometry, same StreamArgs
+int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mode, float alpha, float beta, int sweeps,
+           int zero_guess, int chunk_rows, int rb, float omega)
+{
+    StreamArgs A;
+    std::memset(&A, 0, sizeof(A));
+    const int G = N + 2;
+    A.xin = xin; A.rhs = rhs; A.xout = xout;
+    A.G = G; A.N = N; A.row_base = 0;
+    A.a_lo = 1; A.a_hi = N + 1;
+    A.write_top = 1; A.write_bot = 1;
+    A.nbands = (G + VALID_W - 1) / VALID_W;
+    A.zero_guess = zero_guess;
+    A.alpha = alpha; A.div = make_div_const(beta);
+    const double F = 1.0 + 4.0 * fabs((double)alpha);
+    if (!rb) {
+        double g = F / fabs((double)beta) * 1.000001;
+        if (g < 1.0) g = 1.0;
+        double hi = (double)SF_DIV_HI / (F * 1.01);
+        for (int t = 0; t < sweeps; ++t) hi /= g;
+        A.hi_in = (float)hi;
+    } else {
+        A.div.pad = omega;
+        const double om = (double)omega;
+        double gl = (fabs(1.0 - om) + om * F / fabs((double)beta)) * 1.000001;
+        if (gl < 1.0) gl = 1.0;
+        double hi = (double)SF_DIV_HI / (F * 1.01) / (1.0 + om);
+        for (int t = 0; t < sweeps; ++t) hi /= gl;
+        A.hi_in = (float)hi;
+    }
+    A.sx = (b == 1) ? -1.0f : 1.0f;
+    A.sy = (b == 2) ? -1.0f : 1.0f;
+    const int rows = A.a_hi - A.a_lo;
+    int chunk = chunk_rows;
+    if (chunk <= 0) {
+        const bool heavy = (mode == MODE_STRICT || mode == MODE_IEEE) && sweeps >= 6;
+        const int slots = 148 * (heavy ? 3 : 4) * WPC;
+        int want = slots / A.nbands;
+        if (want < 1) want = 1;
+        chunk = (std::max(rows, 1) + want - 1) / want;
+        const int min_chunk = 2 * sweeps > 8 ? 2 * sweeps : 8;
+        if (chunk < min_chunk) chunk = min_chunk;
+    }
+    if (chunk > rows) chunk = std::max(rows, 1);
+    A.chunk_rows = chunk;
+    A.nchunks = rows > 0 ? (rows + chunk - 1) / chunk : 0;
+    const int items = A.nbands * A.nchunks;
+    const int ctas = (items + WPC - 1) / WPC;
+    if (rb) {
+        if (mode == MODE_PRESSURE) return run_T<MODE_PRESSURE, 5>(sweeps, A, ctas);
+        return run_T<MODE_STRICT, 5>(sweeps, A, ctas);
+    }
+    if (mode == MODE_PRESSURE) return run_T<MODE_PRESSURE, 0>(sweeps, A, ctas);
+    return run_T<MODE_STRICT, 0>(sweeps, A, ctas);
+}
+}  // namespace
+}  // namespace sf
+
+extern "C" {
+// lin_solve of csrc/sf_api.cu (Jacobi: plan_launches; red-black: three iterations per launch); result ends in x
+int emu_lin_solve(int N, int b, float *x, const float *x0, float alpha, float beta, int iters, int T, int zero_guess,
+                  int chunk_rows, int rb, float omega)
+{
+    using namespace sf;
+    const size_t cells = (size_t)(N + 2) * (N + 2);
+    std::vector<float> scratch(cells, NAN);
+    const int mode = (alpha == 1.0f && beta == 4.0f) ? MODE_PRESSURE : MODE_STRICT;
+    std::vector<int> plan;
+    if (rb) {
+        for (int done = 0; done < iters;) { const int k = std::min(3, iters - done); plan.push_back(2 * k); done += k; }
+    } else {
+        int L = (iters + T - 1) / T;
+        if (!zero_guess && (L & 1) && L + 1 <= iters) ++L;
+        plan.assign(L, iters / L);
+        for (int k = 0; k < iters % L; ++k) ++plan[k];
+    }
+    float *cur = x, *nxt = scratch.data();
+    if (!rb && zero_guess && (plan.size() & 1)) { cur = scratch.data(); nxt = x; }
+    for (size_t k = 0; k < plan.size(); ++k) {
+        if (launch(nxt, cur, x0, N, b, mode, alpha, beta, plan[k], zero_guess && k == 0, chunk_rows, rb, omega)) return -1;
+        std::swap(cur, nxt);
+    }
+    if (cur != x) std::memcpy(x, cur, cells * sizeof(float));
+    return 0;
+}
+}
