@@ -101,3 +101,43 @@ def test_red_black_levels_in_the_kernel_source(rb, variant):
                 got = x.copy()
                 assert L.emu_lin_solve(N, b, p(got), p(x0), al, be, K, 6, 0, 0, 1, om) == 0
                 assert same(got, want), (variant, N, om, b, K)
+
+
+def test_stage_kernels_source_on_the_smallest_grids(oracle):
+    """csrc/sf_stages.cu as written (set_bnd, add_source, advect, divergence, gradient subtract; the float4 row kernels with
+    their shuffles at G % 4 == 0, the per-cell kernels otherwise) against the oracle at G = 3 .. 32.  This is the check that
+    reproduces the N = 1 corner bug of the old set_bnd kernel."""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "emu"))
+    import build_emu
+    L = C.CDLL(build_emu.build_stages())
+    i, f = C.c_int, C.c_float
+    L.emu_set_bnd.argtypes = [i, i, FP]; L.emu_add_source.argtypes = [i, FP, FP, f]; L.emu_advect.argtypes = [i, i, FP, FP, FP, FP, f]
+    L.emu_advect_uv.argtypes = [i, FP, FP, FP, FP, f]; L.emu_divergence.argtypes = [i, FP, FP, FP, FP, i]
+    L.emu_last_project.argtypes = [i, FP, FP, FP]
+    for fn in ("emu_set_bnd", "emu_add_source", "emu_advect", "emu_advect_uv", "emu_divergence", "emu_last_project"):
+        getattr(L, fn).restype = None
+    rng = np.random.default_rng(0)
+    DT = 0.016
+    rnd = lambda G, lo=-1, hi=1: rng.uniform(lo, hi, (G, G)).astype(np.float32)
+    zeros = lambda G: np.zeros((G, G), np.float32)
+    for N in (1, 2, 3, 4, 5, 6, 10, 13, 14, 30):
+        G = N + 2
+        for b in (0, 1, 2):
+            x = rnd(G); w = x.copy(); oracle.set_bnd(N, b, w); L.emu_set_bnd(N, b, p(x))
+            assert same(x, w), ("set_bnd", N, b)
+        x, s_ = rnd(G), rnd(G); w = x.copy(); oracle.add_source(N, w, s_, DT); L.emu_add_source(N, p(x), p(s_), DT)
+        assert same(x, w), ("add_source", N)
+        u, v = rnd(G, -.3, .3), rnd(G, -.3, .3)
+        for b in (0, 1, 2):
+            d0 = rnd(G); w = zeros(G); oracle.advect(N, b, w, d0, u, v, DT)
+            d = zeros(G); L.emu_advect(N, b, p(d), p(d0), p(u), p(v), DT)
+            assert same(d, w), ("advect", N, b)
+        wu, wv = zeros(G), zeros(G); oracle.advect(N, 1, wu, u, u, v, DT); oracle.advect(N, 2, wv, v, u, v, DT)
+        du, dv = zeros(G), zeros(G); L.emu_advect_uv(N, p(du), p(dv), p(u), p(v), DT)
+        assert same(du, wu) and same(dv, wv), ("advect_uv", N)
+        wp, wd = zeros(G), zeros(G); oracle.computeDivergenceAndPressure(N, u, v, wp, wd)
+        gp, gd = rnd(G), rnd(G); L.emu_divergence(N, p(u), p(v), p(gp), p(gd), 1)
+        assert same(gp, wp) and same(gd, wd), ("divergence", N)
+        pr = rnd(G); wu, wv = u.copy(), v.copy(); oracle.lastProject(N, wu, wv, pr, wd)
+        gu, gv = u.copy(), v.copy(); L.emu_last_project(N, p(gu), p(gv), p(pr))
+        assert same(gu, wu) and same(gv, wv), ("last_project", N)

@@ -20,6 +20,16 @@ def build(tag="", defs=()):
     return out
 
 
+def build_stages():
+    gen_emu.gen_stages()
+    out = os.path.join(HERE, "_gen", "libemu_stages.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.check_call([cxx, "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + cuda_inc,
+                           "-I" + HERE, os.path.join(HERE, "emu_stages.cpp"), "-o", out])
+    return out
+
+
 if __name__ == "__main__":
     args = sys.argv[1:]
     tag = args[0] if args and not args[0].startswith("-D") else ""

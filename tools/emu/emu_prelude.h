@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #undef __device__
@@ -104,5 +105,9 @@ inline int atomicCAS(int *p, int cmp, int val) { __atomic_compare_exchange_n(p, 
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline double atomicAdd(double *p, double v) { double o = *p; *p = o + v; return o; }       // (reductions are not emulated)
+inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
+inline int __float_as_int(float a) { int i; std::memcpy(&i, &a, 4); return i; }
+inline void __syncthreads() { std::abort(); }                                               // CTA-wide barriers: not emulated
 using std::max;
 using std::min;
