@@ -141,3 +141,22 @@ def test_stage_kernels_source_on_the_smallest_grids(oracle):
         pr = rnd(G); wu, wv = u.copy(), v.copy(); oracle.lastProject(N, wu, wv, pr, wd)
         gu, gv = u.copy(), v.copy(); L.emu_last_project(N, p(gu), p(gv), p(pr))
         assert same(gu, wu) and same(gv, wv), ("last_project", N)
+
+
+def test_red_black_half_sweep_kernel_source(rb):
+    """csrc/sf_solvers.cu as written (the default, launch-per-half-sweep form of SF_SOLVER_RBGS) against the in-place scheme."""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "emu"))
+    import build_emu
+    L = C.CDLL(build_emu.build_stages())
+    L.emu_rbgs.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_int, C.c_float]
+    L.emu_rbgs.restype = None
+    rng = np.random.default_rng(3)
+    for N in (1, 2, 5, 13, 14, 30):
+        G = N + 2
+        for om in (1.0, 1.5, 0.8):
+            for b, (al, be), K in ((0, (1.0, 4.0), 4), (1, (0.635, 3.54), 3), (2, (2683.2, 10733.8), 2)):
+                x = rng.uniform(-1, 1, (G, G)).astype(np.float32); x0 = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+                om32 = float(np.float32(om))
+                want = x.copy(); rb.rb_diffuse(N, b, want, x0, al, be, K, om32)
+                got = x.copy(); L.emu_rbgs(N, b, p(got), p(x0), al, be, K, om32)
+                assert same(got, want), (N, om, b, K)

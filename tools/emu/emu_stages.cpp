@@ -112,4 +112,20 @@ void emu_last_project(int N, float *u, float *v, const float *p)
         run_kernel(cell_grid(g, block, rows), block, [&] { last_project_kernel(u, v, p, g, h); });
     }
 }
+// rbgs_solve of csrc/sf_api.cu with launch_rbgs_half_sweep of csrc/sf_solvers.cu: iters x { red, black, set_bnd(b) }, in place
+void emu_rbgs(int N, int b, float *x, const float *x0, float alpha, float beta, int iters, float omega)
+{
+    const Geom g = full(N);
+    const DivConst dc = make_div_const(beta);
+    const int relax = (omega != 1.0f) ? 1 : 0;
+    const bool pressure = (alpha == 1.0f && beta == 4.0f);
+    const dim3 block(64, 4), grid(((g.N + 1) / 2 + 63) / 64, (g.N + 3) / 4);
+    for (int k = 0; k < iters; ++k) {
+        for (int colour = 0; colour < 2; ++colour) {
+            if (pressure) run_kernel(grid, block, [&] { rbgs_half_sweep_kernel<MODE_PRESSURE>(x, x0, g, colour, alpha, dc, omega, relax); });
+            else run_kernel(grid, block, [&] { rbgs_half_sweep_kernel<MODE_STRICT>(x, x0, g, colour, alpha, dc, omega, relax); });
+        }
+        run_kernel(dim3((N + 255) / 256), dim3(256), [&] { set_bnd_kernel(x, g, b == 1 ? -1.0f : 1.0f, b == 2 ? -1.0f : 1.0f); });
+    }
+}
 }
