@@ -83,6 +83,14 @@ def test_kernel_source_two_bands_chunks_and_a_decaying_front(oracle, variant):
     got = np.zeros((G, G), np.float32)
     assert L.emu_lin_solve(N, 0, p(got), p(src), al, be, 14, 7, 0, 0, 0, 1.0) == 0
     assert same(got, want), (variant, "front")
+    # rows beyond the HIGH end of the validated range: detected when the row is fetched (row_is_big), the group runs guarded
+    x = rng.uniform(-1, 1, (G, G)).astype(np.float32); x0 = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+    x[40:43, 10:20] = np.float32(3e31); x0[90, 60:64] = np.float32(-2e33)
+    al, be = 0.635, 3.54
+    want = x.copy(); oracle.diffuse(N, 2, want, x0, al, be, 14)
+    got = x.copy()
+    assert L.emu_lin_solve(N, 2, p(got), p(x0), al, be, 14, 7, 0, 0, 0, 1.0) == 0
+    assert same(got, want), (variant, "huge values")
 
 
 @pytest.mark.parametrize("variant", ["default", "il2_edge"])
