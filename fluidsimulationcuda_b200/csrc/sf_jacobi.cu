@@ -63,6 +63,12 @@ constexpr int STEAL_MIN_ROWS = 64;            // work stealing: smallest remaini
 // Off until it has been through the GPU parity suite and an A/B timing.
 #define SF_INNER_LOOP 0
 #endif
+#ifndef SF_GUARDED_GROUP
+// 1 = rows inside a guarded span (the decaying front of a density field) run in wall-free groups of three ticks with the
+// binary64 division instead of one general tick per row (which carries the wall logic and 8T register moves per tick).
+// Source checked on the host (tools/emu); off until its register allocation and timing have been seen on a GPU.
+#define SF_GUARDED_GROUP 0
+#endif
 #ifndef SF_PRESSURE_CTAS
 // CTAs per SM the pressure kernel (T >= 6) is register-bounded for: 4 (128 registers, 16 warps per SM) or 3 (168 registers,
 // 12 warps per SM).  With SF_INNER_LOOP the T = 7 pressure kernel spills 32 bytes under the 128-register cap, so the
@@ -296,7 +302,8 @@ __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rg
 // with t odd after the black one -- a level updates the cells of its colour and copies the others through, and set_bnd acts
 // on black levels only (wall columns and wall rows copy through on red levels).  A lane's first column is a multiple of 4,
 // so which two of its four cells a level updates is warp-uniform.  omega travels in A.div.pad (1.0f = plain Gauss-Seidel).
-template <int T, int MODE, int PH, bool WALLS, bool EDGE = true, bool RB = false>
+// GUARD = true: the wall-free tick with the binary64 division for every cell (SF_GUARDED_GROUP).
+template <int T, int MODE, int PH, bool WALLS, bool EDGE = true, bool RB = false, bool GUARD = false>
 __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const float4 &row_in, float4 (&W)[T][3],
                                               const float4 *rring, bool ownsL, bool ownsR, float4 &out)
 {
@@ -310,7 +317,7 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
         const float4 r = rring[(a & (RING_R - 1)) * 32];
         const float lft = __shfl_up_sync(0xffffffffu, mid.w, 1);
         const float rgt = __shfl_down_sync(0xffffffffu, mid.x, 1);
-        float4 o = jacobi4<MODE, WALLS>(lft, mid, rgt, up, dn, r, A.alpha, A.div, ok);
+        float4 o = jacobi4<MODE, WALLS || GUARD>(lft, mid, rgt, up, dn, r, A.alpha, A.div, ok);
         if constexpr (RB) {
             const bool black = (t & 1) != 0;                 // compile-time: t is an unrolled index
             const float om = A.div.pad;
@@ -679,6 +686,23 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             continue;
 #endif
         }
+#if SF_GUARDED_GROUP
+        if constexpr (MODE == MODE_STRICT && !TMA && !STRIP) {
+            if (slow && s >= fast_lo && s + 2 <= fast_hi && s + 2 < slow_until) {
+                issue3(s + PREFETCH);
+                landed(s, 3);
+                float4 o;
+                pipeline_tick<T, MODE, 0, false, true, RB, true>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                emit_plain(s - T, o);
+                pipeline_tick<T, MODE, 1, false, true, RB, true>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                emit_plain(s + 1 - T, o);
+                pipeline_tick<T, MODE, 2, false, true, RB, true>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                emit_plain(s + 2 - T, o);
+                s += 3;
+                continue;
+            }
+        }
+#endif
         general_tick(s, fetch(s));
         ++s;
     }

@@ -13,7 +13,8 @@ import pytest
 from conftest import ROOT
 
 FP = C.POINTER(C.c_float)
-VARIANTS = {"default": (), "il2_edge": ("-DSF_INNER_LOOP=2", "-DSF_EDGE_SPLIT=1"), "il1": ("-DSF_INNER_LOOP=1",)}
+VARIANTS = {"default": (), "il2_edge": ("-DSF_INNER_LOOP=2", "-DSF_EDGE_SPLIT=1"), "il1": ("-DSF_INNER_LOOP=1",),
+            "gg": ("-DSF_GUARDED_GROUP=1",)}
 _libs = {}
 
 
@@ -42,7 +43,7 @@ def rb():
     return RedBlackCheck()
 
 
-@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("variant", ["default", "il2_edge", "il1"])
 def test_kernel_source_on_the_smallest_grids(oracle, variant):
     L = emu(variant)
     rng = np.random.default_rng(0)

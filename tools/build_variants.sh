@@ -9,4 +9,6 @@ b il1c3  -DSF_INNER_LOOP=1 -DSF_PRESSURE_CTAS=3
 b il2    -DSF_INNER_LOOP=2
 b il2c3  -DSF_INNER_LOOP=2 -DSF_PRESSURE_CTAS=3
 b il2c3e -DSF_INNER_LOOP=2 -DSF_PRESSURE_CTAS=3 -DSF_EDGE_SPLIT=1
+b gg     -DSF_GUARDED_GROUP=1
+b ggil2  -DSF_GUARDED_GROUP=1 -DSF_INNER_LOOP=2
 ls -la build/

@@ -5,7 +5,7 @@ import ctypes as C, numpy as np, sys, time, os
 HERE=os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0,os.path.join(HERE,'..','..')); sys.path.insert(0,HERE)
 import build_emu
 from oracle.pyoracle import Oracle, RedBlackCheck
-variant=sys.argv[1]; defs={"default":(),"il2_edge":("-DSF_INNER_LOOP=2","-DSF_EDGE_SPLIT=1")}[variant]
+variant=sys.argv[1]; defs={"default":(),"il2_edge":("-DSF_INNER_LOOP=2","-DSF_EDGE_SPLIT=1"),"gg":("-DSF_GUARDED_GROUP=1",),"all":("-DSF_GUARDED_GROUP=1","-DSF_INNER_LOOP=2","-DSF_EDGE_SPLIT=1")}[variant]
 L=C.CDLL(build_emu.build("fz_"+variant, defs)); FP=C.POINTER(C.c_float)
 L.emu_lin_solve.argtypes=[C.c_int,C.c_int,FP,FP,C.c_float,C.c_float,C.c_int,C.c_int,C.c_int,C.c_int,C.c_int,C.c_float]; L.emu_lin_solve.restype=C.c_int
 p=lambda a:a.ctypes.data_as(FP)
