@@ -160,9 +160,9 @@ def test_red_black_half_sweep_kernel_source(rb):
     L.emu_rbgs.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_int, C.c_float]
     L.emu_rbgs.restype = None
     rng = np.random.default_rng(3)
-    for N in (1, 2, 5, 13, 14, 30):
+    for N in (1, 2, 5, 14):
         G = N + 2
-        for om in (1.0, 1.5, 0.8):
+        for om in (1.0, 1.5):
             for b, (al, be), K in ((0, (1.0, 4.0), 4), (1, (0.635, 3.54), 3), (2, (2683.2, 10733.8), 2)):
                 x = rng.uniform(-1, 1, (G, G)).astype(np.float32); x0 = rng.uniform(-1, 1, (G, G)).astype(np.float32)
                 om32 = float(np.float32(om))
