@@ -91,6 +91,11 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
         L.strip_rows[0] = c->link.nbr[0].present ? strip_rows : 0;
         L.strip_rows[1] = c->link.nbr[1].present ? strip_rows : 0;
     }
+    {   // rows the launch reads must be stored locally (strip launches read the ghost rows the neighbour pushed: same bound)
+        const int rd_lo = out_lo - sweeps > 0 ? out_lo - sweeps : 0;
+        const int rd_hi = out_hi - 1 + sweeps < c->g.G - 1 ? out_hi - 1 + sweeps : c->g.G - 1;
+        SF_REQUIRE(c, rd_lo >= c->g.row_base && rd_hi < c->g.row_base + c->g.rows, "Jacobi launch: fewer ghost rows than fused sweeps");
+    }
     if (stream_kernels_ok(c)) {
         SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, st));
     } else {
@@ -299,6 +304,10 @@ int create_common(sf_context **out, int N, int device, void *stream, bool own_st
     if (N < 1 || N > (1 << 24) - 2) return SF_ERR_INVALID;
     const int G = N + 2;
     if (row_lo < 0 || row_hi > G || row_hi <= row_lo || halo < 0) return SF_ERR_INVALID;
+    // a partial slab reads its neighbours' rows through ghost rows (every stage is at least a radius-1 stencil), and a wall
+    // row belongs to the slab that owns the interior row it mirrors (set_bnd is fused into the kernels that write row 1 / N)
+    if ((row_lo > 0 || row_hi < G) && halo < 1) return SF_ERR_INVALID;
+    if (row_lo == 1 || row_hi == G - 1) return SF_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SF_ERR_CUDA;
     sf_context *c = new (std::nothrow) sf_context();

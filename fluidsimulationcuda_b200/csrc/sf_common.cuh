@@ -1,6 +1,7 @@
 // Shared device/host definitions for the stable-fluids kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace sf {
@@ -232,10 +233,14 @@ struct StripArgs {
 // Double coverage is harmless: both warps would write bit-identical values.
 struct StealSlot {
     int pos;    // input row the owner has reached (published every few ticks)
+    int tag;    // launch the slot belongs to (StealCtl::epoch + 1): stale slots are ignored
+    // (end, band) form ONE aligned 64-bit word: a thief lowers `end` with a 64-bit compare-and-swap on the pair, so a
+    // range republished with the same end but another band in between (chunk ends are aligned across bands) cannot be
+    // mistaken for the range the thief sampled
     int end;    // one past the last output row the owner will produce; lowered by a thief
     int band;
-    int tag;    // launch the slot belongs to (StealCtl::epoch + 1): stale slots are ignored
 };
+static_assert(sizeof(StealSlot) == 16 && offsetof(StealSlot, end) == 8, "StealSlot: (end, band) is an aligned 64-bit word");
 struct StealCtl {
     int epoch;      // launches completed
     int done;       // warps of the current launch that have finished

@@ -48,33 +48,15 @@ constexpr int STEAL_MIN_ROWS = 64;            // work stealing: smallest remaini
 #ifndef SF_OFF32
 #define SF_OFF32 1        // 32-bit cell offsets inside a field (see stream_rows)
 #endif
-#ifndef SF_EDGE_SPLIT
-// 1 = separate fast-group instantiation for bands without a wall column (saves the two predicated wall
-// multiplies per level in 72 of 74 bands).  Measured SLOWER at G=8192, K=40 (pressure solve 1.12 vs 0.91 ms,
-// strict 1.68 vs 1.58 ms, step 9.15 vs 8.58 ms): the second copy of the group costs the pressure kernel
-// its spill-free allocation.  Kept as a build option, off.
-#define SF_EDGE_SPLIT 0
-#endif
-#ifndef SF_INNER_LOOP
-// 1 / 2 = consecutive fast groups run in their own inner loop (the general tick stays in the outer one).  With one
-// loop for both paths ptxas gives the windows a different register assignment at the loop latch than at the
-// loop head and pays for it with 8T register moves per group ON THE FAST PATH (56 MOVs of ~650 instructions
-// at T = 7: the general tick's explicit rotation, sunk into the common latch); see profiles/r01_sass_static.txt.
-// Off until it has been through the GPU parity suite and an A/B timing.
-#define SF_INNER_LOOP 0
-#endif
-#ifndef SF_GUARDED_GROUP
-// 1 = rows inside a guarded span (the decaying front of a density field) run in wall-free groups of three ticks with the
-// binary64 division instead of one general tick per row (which carries the wall logic and 8T register moves per tick).
-// Source checked on the host (tools/emu); off until its register allocation and timing have been seen on a GPU.
-#define SF_GUARDED_GROUP 0
-#endif
-#ifndef SF_PRESSURE_CTAS
-// CTAs per SM the pressure kernel (T >= 6) is register-bounded for: 4 (128 registers, 16 warps per SM) or 3 (168 registers,
-// 12 warps per SM).  With SF_INNER_LOOP the T = 7 pressure kernel spills 32 bytes under the 128-register cap, so the
-// pair (SF_INNER_LOOP=1, SF_PRESSURE_CTAS=3) is the other candidate of that A/B.
-#define SF_PRESSURE_CTAS 4
-#endif
+// Adopted after the A/B of round 2 (profiles/r02/s1_86a0b52_ab_variants.txt, G = 8192, K = 40, one B200):
+//  * consecutive wall-free groups of the modes WITHOUT a range check (pressure, fast, IEEE) run in an inner loop of their own,
+//    and the pressure kernel (T >= 6) is register-bounded for 3 CTAs per SM: with one loop for both paths ptxas sank the
+//    general tick's window rotation (8T register moves) into the common latch, 56 MOVs per group on the fast path; the
+//    inner loop needs 142 registers, hence 12 instead of 16 warps per SM.  Pressure solve 0.916 -> 0.872 ms.
+//  * rows inside a guarded span (the decaying front of a density field) run in wall-free groups of three ticks with the
+//    binary64 division instead of one general tick per row.  Density solve 1.92 -> 1.67 ms, step 8.58 -> 8.33 ms.
+// Measured and removed: an inner loop for the strict groups too (no change: ptxas already gives them their own loop), a
+// separate group instantiation for bands without a wall column (no change at best, spills at worst).
 #if SF_OFF32
 typedef unsigned cell_t;
 #else
@@ -88,7 +70,7 @@ constexpr int PREFETCH = SF_PREFETCH;  // rows in flight ahead of the row being 
 // in flight: at T >= 6 it needs ~150 registers, so it runs 3 CTAs (12 warps) per SM instead of 4 --
 // measured faster than spilling at 128 registers (1.78 vs 2.18 ms per 40-sweep solve at G=8192).
 template <int T, int MODE>
-constexpr int min_ctas() { return ((MODE == MODE_STRICT || MODE == MODE_IEEE) && T >= 6) ? 3 : (MODE == MODE_PRESSURE && T >= 6) ? SF_PRESSURE_CTAS : 4; }
+constexpr int min_ctas() { return ((MODE == MODE_STRICT || MODE == MODE_IEEE || MODE == MODE_PRESSURE) && T >= 6) ? 3 : 4; }
 
 struct StreamArgs {
     const float *xin, *rhs;
@@ -295,15 +277,13 @@ __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rg
 // the level below in this same tick.  PH is a compile-time constant, so after three ticks every
 // row is back in the register it started in and the hot loop contains no register moves.
 // WALLS adds the fused set_bnd handling.  Returns level T of row s-T in `out`.
-// EDGE = false: the warp's band touches neither wall column (72 of the 74 bands at G = 8192): the two
-// predicated wall multiplies per level are not even issued.
 // RB = true (opt-in red-black Gauss-Seidel / SOR, SF_OPT_RBGS_BLOCKED; design checked in tools/models/rbgs_blocked_model.py):
 // one red-black ITERATION is two LEVELS -- level t+1 with t even is the state after the red half-sweep ((row + col) even),
 // with t odd after the black one -- a level updates the cells of its colour and copies the others through, and set_bnd acts
 // on black levels only (wall columns and wall rows copy through on red levels).  A lane's first column is a multiple of 4,
 // so which two of its four cells a level updates is warp-uniform.  omega travels in A.div.pad (1.0f = plain Gauss-Seidel).
-// GUARD = true: the wall-free tick with the binary64 division for every cell (SF_GUARDED_GROUP).
-template <int T, int MODE, int PH, bool WALLS, bool EDGE = true, bool RB = false, bool GUARD = false>
+// GUARD = true: the wall-free tick with the binary64 division for every cell (groups inside a guarded span).
+template <int T, int MODE, int PH, bool WALLS, bool RB = false, bool GUARD = false>
 __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const float4 &row_in, float4 (&W)[T][3],
                                               const float4 *rring, bool ownsL, bool ownsR, float4 &out)
 {
@@ -349,10 +329,8 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
         } else {
         // wall columns: x[row][0] = sx * x[row][1], x[row][N+1] = sx * x[row][N]  (two predicated
         // multiplies; only the lanes holding columns 0 / N+1 of the two edge bands execute them)
-        if (EDGE) {
-            if (ownsL) o.x = __fmul_rn(A.sx, o.y);
-            if (ownsR) o.w = __fmul_rn(A.sx, o.z);
-        }
+        if (ownsL) o.x = __fmul_rn(A.sx, o.y);
+        if (ownsR) o.w = __fmul_rn(A.sx, o.z);
         if (WALLS) {
             if (t + 1 < T) {
                 // wall rows of level t+1 live in the NEXT level's window: its MID slot is row a-1
@@ -548,13 +526,11 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
     constexpr bool GROUP_VOTE = (MODE == MODE_STRICT) && !TMA && !STRIP;
     // the modes without a range check (pressure, fast, IEEE division) run the same branch-free group
     constexpr bool BRANCH_FREE_GROUP = (MODE != MODE_STRICT);
-    // warp-uniform: does this band hold a wall column?  (selects the group instantiation, see pipeline_tick)
-    const bool edge_band = SF_EDGE_SPLIT ? __any_sync(0xffffffffu, ownsL || ownsR) : true;
 
     // general tick at phase 0 followed by the register rotation that restores phase 0
     auto general_tick = [&](int s_, const float4 &row_in) {
         float4 o;
-        pipeline_tick<T, MODE, 0, true, true, RB>(A, s_, row_in, W, rring, ownsL, ownsR, o);
+        pipeline_tick<T, MODE, 0, true, RB>(A, s_, row_in, W, rring, ownsL, ownsR, o);
         emit_walls(s_ - T, o);
 #pragma unroll
         for (int t = 0; t < T; ++t) { W[t][0] = W[t][1]; W[t][1] = W[t][2]; }
@@ -584,10 +560,9 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
         }
         const bool slow = s < slow_until;
         if (!slow && s >= fast_lo && s + 2 <= fast_hi) {
-#if SF_INNER_LOOP
-            // every path through the body below ends in `continue` (-> the inner condition) or, for a restart, `break`
-            // 1: the modes without a range check only (the strict group already gets a loop of its own from ptxas); 2: all
-            constexpr bool INNER_RUN = (SF_INNER_LOOP == 2) || (MODE != MODE_STRICT);
+            // consecutive groups of the modes without a range check run in this inner loop (the strict group already gets a
+            // loop of its own from ptxas): every path through the body ends in `continue` (-> the inner condition) or `break`
+            constexpr bool INNER_RUN = (MODE != MODE_STRICT);
             [[maybe_unused]] bool stolen = false;
             [[maybe_unused]] const int s_run = s;
             do {
@@ -599,7 +574,6 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     end_seen = ld_relaxed_gpu(&slot->end);
                 }
             }
-#endif
             issue3(s + PREFETCH);
             landed(s, 3);                    // rows <= s+2 have landed
             bool big = false;
@@ -613,21 +587,12 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     auto emit_plain = [&](int a, const float4 &ov) {
                         if (a >= first && a < a_hi && st_ok) *reinterpret_cast<float4 *>(A.xout + (e0 + (cell_t)(a - (s - T)) * Gu)) = ov;
                     };
-                    if (edge_band) {
-                        ok = pipeline_tick<T, MODE, 0, false, true, RB>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
-                        emit_plain(s - T, o);
-                        ok &= pipeline_tick<T, MODE, 1, false, true, RB>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
-                        emit_plain(s + 1 - T, o);
-                        ok &= pipeline_tick<T, MODE, 2, false, true, RB>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
-                        emit_plain(s + 2 - T, o);
-                    } else {
-                        ok = pipeline_tick<T, MODE, 0, false, false, RB>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
-                        emit_plain(s - T, o);
-                        ok &= pipeline_tick<T, MODE, 1, false, false, RB>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
-                        emit_plain(s + 1 - T, o);
-                        ok &= pipeline_tick<T, MODE, 2, false, false, RB>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
-                        emit_plain(s + 2 - T, o);
-                    }
+                    ok = pipeline_tick<T, MODE, 0, false, RB>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                    emit_plain(s - T, o);
+                    ok &= pipeline_tick<T, MODE, 1, false, RB>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                    emit_plain(s + 1 - T, o);
+                    ok &= pipeline_tick<T, MODE, 2, false, RB>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                    emit_plain(s + 2 - T, o);
                     if (GROUP_VOTE && !__all_sync(0xffffffffu, ok)) {
                         first = max(first, s - T);     // rows below it were emitted by groups that passed
                         // a retry that fails straight away doubles the guarded span (64 .. 512 rows): where the
@@ -640,7 +605,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     s += 3;
                     continue;
                 } else {
-                bool ok = pipeline_tick<T, MODE, 0, false, true, RB>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                bool ok = pipeline_tick<T, MODE, 0, false, RB>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
                 if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
                     slow_until = next64(s + 3);        // windows are still at phase 0: redo guarded
                     general_tick(s, xrow(s)); s += 1;
@@ -649,7 +614,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     continue;
                 }
                 emit_plain(s - T, o);
-                ok = pipeline_tick<T, MODE, 1, false, true, RB>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                ok = pipeline_tick<T, MODE, 1, false, RB>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
                 if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
                     slow_until = next64(s + 3);        // phase 1 -> phase 0: up = slot 1, mid = slot 2
 #pragma unroll
@@ -660,7 +625,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     continue;
                 }
                 emit_plain(s + 1 - T, o);
-                ok = pipeline_tick<T, MODE, 2, false, true, RB>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                ok = pipeline_tick<T, MODE, 2, false, RB>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
                 if (MODE == MODE_STRICT && !__all_sync(0xffffffffu, ok)) {
                     slow_until = next64(s + 3);        // phase 2 -> phase 0: up = slot 2, mid = slot 0
 #pragma unroll
@@ -680,29 +645,26 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             general_tick(s, xrow(s)); s += 1;
             general_tick(s, xrow(s)); s += 1;
             continue;
-#if SF_INNER_LOOP
             } while (INNER_RUN && s >= slow_until && s + 2 <= fast_hi);     // (s >= fast_lo holds for the whole run)
             if (restart || stolen) break;
             continue;
-#endif
         }
-#if SF_GUARDED_GROUP
+        // guarded span: wall-free groups of three ticks with the binary64 division (same windows, no register rotation)
         if constexpr (MODE == MODE_STRICT && !TMA && !STRIP) {
             if (slow && s >= fast_lo && s + 2 <= fast_hi && s + 2 < slow_until) {
                 issue3(s + PREFETCH);
                 landed(s, 3);
                 float4 o;
-                pipeline_tick<T, MODE, 0, false, true, RB, true>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                pipeline_tick<T, MODE, 0, false, RB, true>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
                 emit_plain(s - T, o);
-                pipeline_tick<T, MODE, 1, false, true, RB, true>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                pipeline_tick<T, MODE, 1, false, RB, true>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
                 emit_plain(s + 1 - T, o);
-                pipeline_tick<T, MODE, 2, false, true, RB, true>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                pipeline_tick<T, MODE, 2, false, RB, true>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
                 emit_plain(s + 2 - T, o);
                 s += 3;
                 continue;
             }
         }
-#endif
         general_tick(s, fetch(s));
         ++s;
     }
@@ -750,7 +712,7 @@ __device__ __noinline__ bool steal_next(StealCtl *ctl, int nitems, int chunk_row
         const StealSlot *S = ctl->slots + cand;
         // pos is written last by its owner (after a fence) and read first here: a valid pos vouches for the rest
         const int cpos = ld_acquire_gpu(&S->pos);
-        const int ctag = ld_relaxed_gpu(&S->tag), cend = ld_relaxed_gpu(&S->end);
+        const int ctag = ld_relaxed_gpu(&S->tag), cend = ld_relaxed_gpu(&S->end), cband = ld_relaxed_gpu(&S->band);
         const bool valid = ctag == tag && cand != item && cpos >= seg_lo - HALO_X && cend <= seg_hi && cend > cpos;
         const int rem = valid ? cend - cpos : 0;    // rows the owner has not reached yet
         int best = rem, who = lane;
@@ -763,14 +725,17 @@ __device__ __noinline__ bool steal_next(StealCtl *ctl, int nitems, int chunk_row
         int mid = 0, ok = 0;
         if (lane == who) {
             mid = cend - rem / 2;                       // the thief takes the upper half [mid, cend)
-            ok = (atomicCAS(&ctl->slots[cand].end, cend, mid) == cend) ? 1 : 0;
+            // 64-bit compare-and-swap on (end, band): succeeds only against the very range that was sampled
+            const unsigned long long hi32 = (unsigned long long)(unsigned)cband << 32;
+            const unsigned long long want = hi32 | (unsigned)cend, put = hi32 | (unsigned)mid;
+            ok = (atomicCAS(reinterpret_cast<unsigned long long *>(&ctl->slots[cand].end), want, put) == want) ? 1 : 0;
             if (ok) atomicAdd(&ctl->taken, 1);
         }
         ok = __shfl_sync(0xffffffffu, ok, who);
         if (ok) {
             lo = __shfl_sync(0xffffffffu, mid, who);
             hi = __shfl_sync(0xffffffffu, cend, who);
-            band = __shfl_sync(0xffffffffu, ld_relaxed_gpu(&S->band), who);
+            band = __shfl_sync(0xffffffffu, cband, who);
             if (lane == 0) {     // the taken range is this warp's published range now
                 st_relaxed_gpu(&slot->end, hi); st_relaxed_gpu(&slot->band, band);
                 __threadfence();
@@ -893,15 +858,14 @@ cudaError_t launch_stream_T(const StreamArgs &A, dim3 grid, size_t smem, bool tm
     static_assert((size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4) <= 48 * 1024,
                   "ring fits the default 48 KB dynamic shared memory limit (no attribute call needed)");
     // the bulk-copy variant is built for the depths the default launch plans use (5, 6, 7)
-    if (tma && (T == 5 || T == 6 || T == 7) && (MODE == MODE_STRICT || MODE == MODE_PRESSURE)) {
+    // (the bulk-copy variant has no strip warps: a peer-slab launch with strips takes the cp.async kernels below)
+    if (tma && A.strips == nullptr && (T == 5 || T == 6 || T == 7) && (MODE == MODE_STRICT || MODE == MODE_PRESSURE)) {
         constexpr int TT = (T == 5 || T == 6 || T == 7) ? T : 7;
         constexpr int MM = (MODE == MODE_STRICT || MODE == MODE_PRESSURE) ? MODE : MODE_PRESSURE;
         const size_t smem_tma = smem + (size_t)WPC * RING_X * sizeof(uint64_t);
-        static bool configured = false;
-        if (!configured) {
+        {   // above the 48 KB default; the attribute is per device, so it is set on every launch (a cheap host-side call)
             cudaError_t e = cudaFuncSetAttribute(jacobi_stream_kernel<TT, MM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
             if (e != cudaSuccess) return e;
-            configured = true;
         }
         jacobi_stream_kernel<TT, MM, 1><<<grid, WPC * 32, smem_tma, st>>>(A);
         return cudaGetLastError();
@@ -1066,8 +1030,7 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
         // the same, so a single full wave has no tail.  Large grids get chunks of hundreds of rows (2T
         // redundant halo rows each: a few percent); small grids cannot fill the wave with such chunks and
         // are latency-bound, so there the chunks shrink (down to 2T rows) to put every SM to work.
-        const bool heavy = ((L.mode == MODE_STRICT || L.mode == MODE_IEEE) && L.sweeps >= 6) ||
-                           (L.mode == MODE_PRESSURE && L.sweeps >= 6 && SF_PRESSURE_CTAS == 3);   // min_ctas<T, MODE>()
+        const bool heavy = (L.mode == MODE_STRICT || L.mode == MODE_IEEE || L.mode == MODE_PRESSURE) && L.sweeps >= 6;   // min_ctas<T, MODE>()
         const int slots = sm_count * (heavy ? 3 : 4) * WPC;
         int want_chunks = slots / A.nbands;
         if (want_chunks < 1) want_chunks = 1;

@@ -144,7 +144,8 @@ __global__ void advect_kernel(float *__restrict__ dA, float *__restrict__ dB, co
     const int c0 = (int)px, r0 = (int)py;
     const float wx1 = __fsub_rn(px, (float)c0), wx0 = __fsub_rn(1.0f, wx1);
     const float wy1 = __fsub_rn(py, (float)r0), wy0 = __fsub_rn(1.0f, wy1);
-    const size_t j = (size_t)(r0 - g.row_base) * G + c0;
+    const int rs = min(max(r0, g.row_base), g.row_base + g.rows - 2);   // see advect_cell
+    const size_t j = (size_t)(rs - g.row_base) * G + c0;
     const Wall w = wall_of(g, row, col);
     {
         const float a00 = __ldg(srcA + j), a10 = __ldg(srcA + j + G), a01 = __ldg(srcA + j + 1), a11 = __ldg(srcA + j + G + 1);
@@ -252,20 +253,26 @@ __global__ void __launch_bounds__(256) init4_kernel(float *dens, float *dens_pre
 // ---- reductions (warp shuffle, then one atomic per block) ------------------------------------
 __global__ void max_abs_kernel(const float *__restrict__ x, size_t first, size_t count, float *out)
 {
-    float m = 0.0f;
+    // integer order of |v|'s bit pattern == magnitude order, and every NaN pattern sorts above +inf: a NaN anywhere in the
+    // field comes out as NaN (fmaxf would drop it, and a caller sizing an advection halo from the result would see 0)
+    int m = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(x[first + i]));
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    __shared__ float part[32];
+        m = max(m, __float_as_int(fabsf(x[first + i])));
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ int part[32];
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x < 32) {
-        m = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0f;
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (threadIdx.x == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));  // m >= 0: int order == float order
+        m = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0;
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) atomicMax(reinterpret_cast<int *>(out), m);
     }
 }
 
+// sum over the owned interior cells of r^2, r = x0 - (beta*x - alpha*(x_l + x_r + x_u + x_d)): the residual of the system the
+// lin_solve relaxes (FluidSequential.c:95-96 solved for x0).  A diagnostic, not part of the reference's arithmetic: every
+// operation is binary64 (products of binary32 values are exact there), so the result does not depend on contraction or on
+// the association of the neighbour sum beyond 1e-15 relative.
 __global__ void residual_kernel(const float *__restrict__ x, const float *__restrict__ x0, Geom g, float alpha,
                                 float beta, double *out)
 {
@@ -273,12 +280,13 @@ __global__ void residual_kernel(const float *__restrict__ x, const float *__rest
     interior_rows(g, lo, hi);
     double acc = 0.0;
     const size_t G = (size_t)g.G;
+    const double al = (double)alpha, be = (double)beta;
     for (int row = lo + blockIdx.y; row < hi; row += gridDim.y)
         for (int col = 1 + blockIdx.x * blockDim.x + threadIdx.x; col <= g.N; col += gridDim.x * blockDim.x) {
             const size_t i = (size_t)(row - g.row_base) * G + col;
-            const float nb = x[i - 1] + x[i + 1] + x[i - G] + x[i + G];
-            const float r = x0[i] - (beta * x[i] - alpha * nb);
-            acc += (double)r * (double)r;
+            const double nb = __dadd_rn(__dadd_rn((double)x[i - 1], (double)x[i + 1]), __dadd_rn((double)x[i - G], (double)x[i + G]));
+            const double r = __dsub_rn((double)x0[i], __dsub_rn(__dmul_rn(be, (double)x[i]), __dmul_rn(al, nb)));
+            acc = __fma_rn(r, r, acc);
         }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     __shared__ double part[32];
@@ -399,7 +407,10 @@ __device__ __forceinline__ void advect_cell(const float *__restrict__ srcA, cons
     const float wx1 = __fsub_rn(px, (float)c0), wx0 = __fsub_rn(1.0f, wx1);
     const float wy1 = __fsub_rn(py, (float)r0), wy0 = __fsub_rn(1.0f, wy1);
     const size_t G = (size_t)g.G;
-    const size_t j = (size_t)(r0 - g.row_base) * G + c0;
+    // a slab context stores rows [row_base, row_base + rows): a back-trace that leaves them (the caller's ghost rows were
+    // too few -- slab.SlabSolver verifies the reach afterwards and raises) reads the nearest stored rows, never outside the array
+    const int rs = min(max(r0, g.row_base), g.row_base + g.rows - 2);
+    const size_t j = (size_t)(rs - g.row_base) * G + c0;
     {
         const float a00 = __ldg(srcA + j), a10 = __ldg(srcA + j + G), a01 = __ldg(srcA + j + 1), a11 = __ldg(srcA + j + G + 1);
         oA = __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),

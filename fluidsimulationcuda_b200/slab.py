@@ -266,6 +266,8 @@ class SlabSolver(SlabLayout):
 
     def _reach_rows(self, max_vel: float, dt: float) -> int:
         dt0 = float(np.float32(dt) * np.float32(self.N))
+        if not math.isfinite(max_vel):      # sf_reduce_max_abs propagates NaN / inf velocities
+            raise SF.StableFluidsError(f"advection reach: max|velocity| is {max_vel}; the fields are corrupt")
         W = int(math.ceil(dt0 * max_vel)) + 2
         if W > self.halo:
             raise SF.StableFluidsError(

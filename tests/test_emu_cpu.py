@@ -2,7 +2,7 @@
 stream_rows, pipeline_tick, the exact division with its votes, guarded ticks and pipeline restarts, fused set_bnd, the
 red-black levels -- everything except the inline-PTX helpers, which get host equivalents.  Checked bitwise against the
 oracle (Jacobi) and against the in-place red-black scheme (SF_OPT_RBGS_BLOCKED), for the default build and for the
-compile-time variants that have not been on a GPU yet.  No GPU needed; the GPU suite remains the final word on the SASS."""
+inner-loop / guarded-group paths it contains.  No GPU needed; the GPU suite remains the final word on the SASS."""
 import ctypes as C
 import os
 import sys
@@ -13,8 +13,9 @@ import pytest
 from conftest import ROOT
 
 FP = C.POINTER(C.c_float)
-VARIANTS = {"default": (), "il2_edge": ("-DSF_INNER_LOOP=2", "-DSF_EDGE_SPLIT=1"), "il1": ("-DSF_INNER_LOOP=1",),
-            "gg": ("-DSF_GUARDED_GROUP=1",)}
+# the build options of round 1 (inner-loop groups, guarded groups) were adopted or removed after their A/B on the GPU
+# (profiles/r02/): the shipped source is the only variant left
+VARIANTS = {"default": ()}
 _libs = {}
 
 
@@ -43,7 +44,7 @@ def rb():
     return RedBlackCheck()
 
 
-@pytest.mark.parametrize("variant", ["default", "il2_edge", "il1"])
+@pytest.mark.parametrize("variant", ["default"])
 def test_kernel_source_on_the_smallest_grids(oracle, variant):
     L = emu(variant)
     rng = np.random.default_rng(0)
@@ -94,7 +95,7 @@ def test_kernel_source_two_bands_chunks_and_a_decaying_front(oracle, variant):
     assert same(got, want), (variant, "huge values")
 
 
-@pytest.mark.parametrize("variant", ["default", "il2_edge"])
+@pytest.mark.parametrize("variant", ["default"])
 def test_red_black_levels_in_the_kernel_source(rb, variant):
     """SF_OPT_RBGS_BLOCKED: jacobi_stream_kernel<T, MODE, 5> against the in-place red-black scheme."""
     L = emu(variant)

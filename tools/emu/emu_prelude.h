@@ -95,6 +95,8 @@ inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 inline float __double2float_rn(double a) { return (float)a; }
@@ -102,6 +104,7 @@ inline unsigned __float_as_uint(float a) { unsigned u; std::memcpy(&u, &a, 4); r
 inline float __uint_as_float(unsigned u) { float a; std::memcpy(&a, &u, 4); return a; }
 template <class V> inline V __ldg(const V *p) { return *p; }
 inline int atomicCAS(int *p, int cmp, int val) { __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long val) { __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
