@@ -20,6 +20,8 @@ namespace sf {
 int ensure_scratch(sf_context *c)
 {
     if (!c->scratch) SF_CUDA(c, cudaMalloc(&c->scratch, field_cells(c) * sizeof(float)));
+    // (allocated here, on the first direct run of a step, never inside a stream capture)
+    if (!c->scratch2 && is_full_grid(c)) SF_CUDA(c, cudaMalloc(&c->scratch2, field_cells(c) * sizeof(float)));
     if (!c->steal) {
         c->steal_capacity = 16384;
         const size_t bytes = sizeof(StealCtl) + (size_t)c->steal_capacity * sizeof(StealSlot);
@@ -74,10 +76,11 @@ std::vector<int> plan_launches(int iters, int T, bool odd_ok)
 }
 
 int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const float *xin, const float *x0, float alpha,
-                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, int strip_rows)
+                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, int strip_rows, float *rhs_out, float src_dt)
 {
     JacobiLaunch L;
     L.xin = xin; L.rhs = x0; L.xout = xout;
+    L.rhs_out = rhs_out; L.src_dt = src_dt;
     L.alpha = alpha; L.beta = beta; L.b = b; L.sweeps = sweeps;
     L.mode = arith_mode(c, alpha, beta);
     L.out_lo = out_lo; L.out_hi = out_hi;
@@ -100,6 +103,7 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
         SF_CUDA(c, launch_jacobi_stream(c->g, L, c->sm_count, st));
     } else {
         SF_REQUIRE(c, sweeps == 1, "generic Jacobi kernel does one sweep per launch");
+        SF_REQUIRE(c, rhs_out == nullptr, "generic Jacobi kernel has no fused add_source");
         SF_REQUIRE(c, strip_rows == 0, "generic Jacobi kernel has no fused strip exchange");
         if (zero_guess) {
             // generic kernel always reads xin
@@ -174,6 +178,39 @@ int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, floa
     return SF_OK;
 }
 
+// add_source followed by the lin_solve that consumes it, as dens_step / vel_step run them (FluidSequential.c:177-182,
+// :193-204, :197-210): x0 += dt * x; SWAP; solve with right-hand side x0 from the initial guess x, result in x.
+// Fused form (SF_OPT_FUSE_SOURCES): the first launch forms x0 + dt * x itself while the rows stream in and stores it to the
+// context's second scratch field, which the later launches read as their right-hand side; x0 is left as it was -- every
+// caller below overwrites it before anything reads it again (vel_step: p / div of the projection; dens_step: advect's output).
+int source_lin_solve(sf_context *c, int b, float *x, float *x0, float dt, float alpha, float beta, int iters)
+{
+    bool fuse = c->fuse_sources && is_full_grid(c) && c->solver == SF_SOLVER_JACOBI && stream_kernels_ok(c) && c->staging == 0;
+    std::vector<int> plan;
+    if (fuse) {
+        plan = plan_launches(iters, default_sweeps(c), false);
+        fuse = jacobi_src_fusion_built(plan[0], arith_mode(c, alpha, beta));
+    }
+    if (!fuse) {
+        float *xs[1] = {x0};
+        const float *ss[1] = {x};
+        SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->work));
+        ++c->launches;
+        return lin_solve(c, b, x, x0, alpha, beta, iters, 0);
+    }
+    int rc = ensure_scratch(c);
+    if (rc) return rc;
+    float *cur = x, *nxt = c->scratch;
+    for (size_t k = 0; k < plan.size(); ++k) {
+        rc = one_jacobi_launch(c, c->work, b, nxt, cur, k == 0 ? x0 : c->scratch2, alpha, beta, plan[k], c->g.own_lo, c->g.own_hi, 0, 0,
+                               k == 0 ? c->scratch2 : nullptr, dt);
+        if (rc) return rc;
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    if (cur != x) SF_CUDA(c, cudaMemcpyAsync(x, cur, field_cells(c) * sizeof(float), cudaMemcpyDeviceToDevice, c->work));
+    return SF_OK;
+}
+
 int check_multi_launch_ok(sf_context *c, int iters)
 {
     if (c->solver == SF_SOLVER_RBGS && !is_full_grid(c))
@@ -192,10 +229,6 @@ int check_multi_launch_ok(sf_context *c, int iters)
 int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters)
 {
     if (is_linked_slab(c)) return slab_dens_step(c, x, x0, u, v, diff, dt, iters);
-    float *xs[1] = {x};
-    const float *ss[1] = {x0};
-    SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->work));
-    ++c->launches;
     const float fN = (float)c->g.N;
     float alpha = dt * diff;      // FluidSequential.c:179, left to right in binary32
     alpha = alpha * fN;
@@ -205,7 +238,7 @@ int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const 
     // Density fields have compact support with a decaying front, where the exact division needs its
     // guarded ticks: the one solve of a step whose warps are worth balancing (velocity fields are dense).
     c->steal_now = true;
-    int rc = lin_solve(c, 0, x0, x, alpha, beta, iters, 0);   // SWAP; diffuse(0, x, x0): solves into the old x0
+    int rc = source_lin_solve(c, 0, x0, x, dt, alpha, beta, iters);   // add_source(x, x0); SWAP; diffuse(0, x, x0): solves into the old x0
     c->steal_now = false;
     if (rc) return rc;
     SF_CUDA(c, launch_advect(c->g, 0, x, x0, u, v, dt, c->work));   // SWAP; advect(0, x, x0, u, v)
@@ -232,17 +265,13 @@ int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int
 // solve while v is still in flight: viscosity solve of one component (add_source + lin_solve, :193-210) ...
 int enqueue_vel_diffuse(sf_context *c, int b, float *x, float *x0, float visc, float dt, int iters)
 {
-    float *xs[1] = {x};
-    const float *ss[1] = {x0};
-    SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->work));
-    ++c->launches;
     const float fN = (float)c->g.N;
     float alpha = dt * visc;      // :199
     alpha = alpha * fN;
     alpha = alpha * fN;
     float beta = 4.0f * alpha;    // :200
     beta = 1.0f + beta;
-    return lin_solve(c, b, x0, x, alpha, beta, iters, 0);
+    return source_lin_solve(c, b, x0, x, dt, alpha, beta, iters);
 }
 // ... and everything after the two solves (:213-240)
 int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, float dt, int iters)
@@ -257,19 +286,15 @@ int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, fl
 int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
 {
     if (is_linked_slab(c)) return slab_vel_step(c, u, v, u0, v0, visc, dt, iters);
-    float *xs[2] = {u, v};
-    const float *ss[2] = {u0, v0};
-    SF_CUDA(c, launch_add_source(c->g, 2, xs, ss, dt, c->work));
-    ++c->launches;
     const float fN = (float)c->g.N;
     float alpha = dt * visc;      // :199
     alpha = alpha * fN;
     alpha = alpha * fN;
     float beta = 4.0f * alpha;    // :200
     beta = 1.0f + beta;
-    int rc = lin_solve(c, 1, u0, u, alpha, beta, iters, 0);            // :201-204
+    int rc = source_lin_solve(c, 1, u0, u, dt, alpha, beta, iters);    // :193, :201-204
     if (rc) return rc;
-    rc = lin_solve(c, 2, v0, v, alpha, beta, iters, 0);                // :209-210
+    rc = source_lin_solve(c, 2, v0, v, dt, alpha, beta, iters);        // :197, :209-210
     if (rc) return rc;
     rc = enqueue_project(c, u0, v0, u, v, iters);                      // :213-223 (p in u, div in v)
     if (rc) return rc;
@@ -289,7 +314,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.iters = iters;
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
     k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan + 16 * c->solver +
-                32 * c->omega_milli + 65536 * c->rbgs_blocked;
+                32 * c->omega_milli + 65536 * c->rbgs_blocked + 131072 * c->fuse_sources;
     return k;
 }
 
@@ -360,6 +385,7 @@ int sf_destroy(sf_context *c)
     cudaStreamSynchronize(c->stream);
     for (auto &e : c->graphs) if (e.exec) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
     if (c->scratch && !c->scratch_in_arena) cudaFree(c->scratch);
+    if (c->scratch2) cudaFree(c->scratch2);
     slab_release(c);
     if (c->steal) cudaFree(c->steal);
     if (c->red_f) cudaFree(c->red_f);
@@ -404,6 +430,7 @@ int sf_set_option(sf_context *c, int option, int value)
             break;
         case SF_OPT_SOR_OMEGA_MILLI: SF_REQUIRE(c, value >= 1 && value <= 1999, "SOR omega in 1/1000: 1..1999"); c->omega_milli = value; break;
         case SF_OPT_RBGS_BLOCKED: c->rbgs_blocked = value ? 1 : 0; break;
+        case SF_OPT_FUSE_SOURCES: c->fuse_sources = value ? 1 : 0; break;
         case SF_OPT_STEAL_SCOPE: SF_REQUIRE(c, value == 0 || value == 1, "steal scope: 0 scalar fields / 1 every strict solve"); c->steal_scope = value; break;
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }
@@ -426,6 +453,7 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_SOLVER: *value = c->solver; break;
         case SF_OPT_SOR_OMEGA_MILLI: *value = c->omega_milli; break;
         case SF_OPT_RBGS_BLOCKED: *value = c->rbgs_blocked; break;
+        case SF_OPT_FUSE_SOURCES: *value = c->fuse_sources; break;
         case SF_OPT_STEAL_COUNT: {   // diagnostics: row ranges taken over by another warp so far (synchronises)
             *value = 0;
             if (c->steal) {

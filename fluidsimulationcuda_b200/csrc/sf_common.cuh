@@ -271,7 +271,13 @@ struct JacobiLaunch {
     // opt-in red-black Gauss-Seidel / SOR on the streaming pipeline: `sweeps` LEVELS (even: two per iteration)
     int rb = 0;
     float omega = 1.0f;
+    // fused add_source (first launch of a solve in the step drivers): rhs = raw field, xin = source field = initial guess;
+    // the launch forms raw + src_dt * xin on the fly and stores it to rhs_out (nullptr = off)
+    float *rhs_out = nullptr;
+    float src_dt = 0.0f;
 };
+// can launch_jacobi_stream fuse add_source into a launch of this depth and mode?  (the instantiations that exist)
+inline bool jacobi_src_fusion_built(int sweeps, int mode) { return sweeps >= 5 && sweeps <= 7 && (mode == MODE_STRICT || mode == MODE_IEEE); }
 cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_count, cudaStream_t st);
 cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStream_t st);
 bool jacobi_stream_supported(const Geom &g);

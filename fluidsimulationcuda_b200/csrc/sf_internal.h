@@ -70,6 +70,8 @@ struct sf_context {
     int force_generic = 0;
     int chunk_rows = 0;
     int staging = 0;
+    float *scratch2 = nullptr;       // right-hand side of a solve whose add_source is fused into its first launch
+    int fuse_sources = 1;            // SF_OPT_FUSE_SOURCES
     float *scratch = nullptr;        // lin_solve ping-pong partner (inside the arena for peer slabs)
     bool scratch_in_arena = false;
     sf::StealCtl *steal = nullptr;   // row-level work stealing between the warps of a Jacobi launch
@@ -135,7 +137,8 @@ std::vector<int> plan_launches(int iters, int T, bool odd_ok = false);
 // strip_rows > 0 (peer-memory slabs): the launch exchanges boundary strips of that height with the
 // neighbours (fused into the kernel; see StripArgs in sf_common.cuh); xout must be an arena field
 int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const float *xin, const float *x0, float alpha,
-                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, int strip_rows = 0);
+                      float beta, int sweeps, int out_lo, int out_hi, int zero_guess, int strip_rows = 0, float *rhs_out = nullptr,
+                      float src_dt = 0.0f);
 int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess);
 int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters);
 int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters);

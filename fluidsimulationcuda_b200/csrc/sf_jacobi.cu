@@ -85,6 +85,10 @@ struct StreamArgs {
     DivConst div;        // beta and its reciprocals
     const StripArgs *strips;   // peer-memory slabs: the fused exchange of the top / bottom strip (device memory)
     StealCtl *steal;           // row-level work stealing (VAR 3 / 4), device memory
+    // fused add_source (VAR 6 / 7, first launch of a solve inside the step drivers): rhs = raw + src_dt * xin is formed
+    // as the rows land and stored to rhs_out for the later launches of the solve; `rhs` points at the raw field
+    float *rhs_out;
+    float src_dt;
 };
 
 // GPU-scope relaxed accesses for the stealing words (plain `volatile` would be system-scope strong accesses)
@@ -352,7 +356,14 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
 // peer + row * pitch, the neighbour GPU's copy of the field (pre-offset so that global row numbers index it).
 // STEAL = true: the warp's slot (A.steal->slots[global warp]) holds its published range; the end may be
 // lowered by another warp at any time.
-template <int T, int MODE, bool TMA, bool STRIP, bool STEAL, bool RB = false>
+// SRC = true: add_source fused into the first launch of a lin_solve (FluidSequential.c:78-82 + :85-104).  A.rhs is the RAW
+// field x, A.xin the source field s -- which is also the solve's initial guess in dens_step / vel_step (the local SWAP at
+// :181 / :201) -- and every level-0 row becomes rhs = x + dt * s in the warp's own ring slot as soon as it has landed
+// (each lane reads and writes only its own 16 bytes of a slot: no synchronisation).  The rows of the warp's output range
+// are also stored to A.rhs_out, a separate field: the later launches of the solve read their right-hand side there, and
+// x itself stays untouched (in place, a neighbouring warp could read a halo row after it was updated and add the source
+// twice).  One pass over x and s less per solve: 8 B per cell.
+template <int T, int MODE, bool TMA, bool STRIP, bool STEAL, bool RB = false, bool SRC = false>
 __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, const int lane, const int warp, const int band,
                                             const int a_lo, const int a_hi, float *peer)
 {
@@ -441,9 +452,24 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             cp_async_wait<PREFETCH>();
         }
     };
+    [[maybe_unused]] auto fuse_src = [&](int row) {      // exactly once per landed row
+        if constexpr (SRC) {
+            if (row <= load_hi) {
+                float4 *slot = rring + (row & (RING_R - 1)) * 32;
+                const float4 raw = *slot, sv = xring[(row & (RING_X - 1)) * 32];
+                const float2 r01 = add2_rn(make_float2(raw.x, raw.y), mul2_exact(dup2(A.src_dt), make_float2(sv.x, sv.y), A.div.nz));
+                const float2 r23 = add2_rn(make_float2(raw.z, raw.w), mul2_exact(dup2(A.src_dt), make_float2(sv.z, sv.w), A.div.nz));
+                const float4 r = make_float4(r01.x, r01.y, r23.x, r23.y);
+                *slot = r;
+                if (row >= a_lo && row < a_hi && st_ok) *reinterpret_cast<float4 *>(A.rhs_out + cell(row)) = r;
+            }
+        }
+    };
+
     auto fetch = [&](int row) -> float4 {   // level-0 row `row` (after it landed)
         issue(row + PREFETCH);
         landed(row, 1);
+        fuse_src(row);
         float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!zero_guess && row <= load_hi) in = xring[(row & (RING_X - 1)) * 32];
         return in;
@@ -576,6 +602,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             }
             issue3(s + PREFETCH);
             landed(s, 3);                    // rows <= s+2 have landed
+            fuse_src(s); fuse_src(s + 1); fuse_src(s + 2);
             bool big = false;
             if (MODE == MODE_STRICT) big = __any_sync(0xffffffffu, row_is_big(s) | row_is_big(s + 1) | row_is_big(s + 2));
             if (!big) {
@@ -654,6 +681,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             if (slow && s >= fast_lo && s + 2 <= fast_hi && s + 2 < slow_until) {
                 issue3(s + PREFETCH);
                 landed(s, 3);
+                fuse_src(s); fuse_src(s + 1); fuse_src(s + 2);
                 float4 o;
                 pipeline_tick<T, MODE, 0, false, RB, true>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
                 emit_plain(s - T, o);
@@ -775,7 +803,8 @@ __device__ __noinline__ void strip_warp(const StreamArgs A, float4 *ring, const 
 template <int T, int MODE, int VAR>
 __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
 {
-    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2 || VAR == 4), STEALS = (VAR == 3 || VAR == 4), RB = (VAR == 5);
+    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2 || VAR == 4), STEALS = (VAR == 3 || VAR == 4 || VAR == 7), RB = (VAR == 5);
+    constexpr bool SRC = (VAR == 6 || VAR == 7);       // fused add_source (first launch of a solve), without / with work stealing
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.
@@ -794,12 +823,12 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     const int a_hi = min(a_lo + A.chunk_rows, A.a_hi);
     if constexpr (!STEALS) {
         if (a_lo >= a_hi) return;
-        stream_rows<T, MODE, TMA, false, false, RB>(A, ring, lane, warp, band, a_lo, a_hi, nullptr);
+        stream_rows<T, MODE, TMA, false, false, RB, SRC>(A, ring, lane, warp, band, a_lo, a_hi, nullptr);
     } else {
         int b = band, lo = a_lo, hi = a_hi;
         steal_publish(A.steal, b, lo, hi);
         for (;;) {
-            if (lo < hi) stream_rows<T, MODE, false, false, true>(A, ring, lane, warp, b, lo, hi, nullptr);
+            if (lo < hi) stream_rows<T, MODE, false, false, true, false, SRC>(A, ring, lane, warp, b, lo, hi, nullptr);
             if (!steal_next(A.steal, nitems, A.chunk_rows, A.a_lo, A.a_hi, b, lo, hi)) break;
         }
     }
@@ -858,6 +887,22 @@ cudaError_t launch_stream_T(const StreamArgs &A, dim3 grid, size_t smem, bool tm
     static_assert((size_t)WPC * (RING_X + RING_R) * 32 * sizeof(float4) <= 48 * 1024,
                   "ring fits the default 48 KB dynamic shared memory limit (no attribute call needed)");
     // the bulk-copy variant is built for the depths the default launch plans use (5, 6, 7)
+    if (A.rhs_out != nullptr) {
+        // fused add_source: built for the depths a default launch plan starts with and the two bit-exact divisions
+        if constexpr ((T == 5 || T == 6 || T == 7) && (MODE == MODE_STRICT || MODE == MODE_IEEE)) {
+            if (A.strips != nullptr || tma) return cudaErrorNotSupported;
+            if constexpr (MODE == MODE_STRICT) {
+                if (A.steal != nullptr) {
+                    jacobi_stream_kernel<T, MODE_STRICT, 7><<<grid, WPC * 32, smem, st>>>(A);
+                    return cudaGetLastError();
+                }
+            }
+            jacobi_stream_kernel<T, MODE, 6><<<grid, WPC * 32, smem, st>>>(A);
+            return cudaGetLastError();
+        } else {
+            return cudaErrorNotSupported;
+        }
+    }
     // (the bulk-copy variant has no strip warps: a peer-slab launch with strips takes the cp.async kernels below)
     if (tma && A.strips == nullptr && (T == 5 || T == 6 || T == 7) && (MODE == MODE_STRICT || MODE == MODE_PRESSURE)) {
         constexpr int TT = (T == 5 || T == 6 || T == 7) ? T : 7;
@@ -940,6 +985,10 @@ void preload_T(cudaFuncAttributes &a)
         cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE_STRICT, 3>);
         cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE_STRICT, 4>);
     }
+    if constexpr ((T == 5 || T == 6 || T == 7) && (MODE == MODE_STRICT || MODE == MODE_IEEE)) {
+        cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE, 6>);
+        if constexpr (MODE == MODE_STRICT) cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE_STRICT, 7>);
+    }
 }
 template <int MODE>
 void preload_mode()
@@ -1010,6 +1059,8 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     A.write_bot = (L.out_hi == g.G);
     A.nbands = (g.G + VALID_W - 1) / VALID_W;
     A.zero_guess = L.zero_guess;
+    A.rhs_out = L.rhs_out; A.src_dt = L.src_dt;
+    if (L.rhs_out != nullptr && (L.zero_guess || L.rb)) return cudaErrorInvalidValue;
     A.alpha = L.alpha; A.div = make_div_const(L.beta);
     {   // see row_is_big: bound on level-0 magnitudes that keeps all numerators of T sweeps in range
         const double F = 1.0 + 4.0 * fabs((double)L.alpha);

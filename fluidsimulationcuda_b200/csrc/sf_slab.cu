@@ -12,7 +12,7 @@
 //     take an interior work item like every other warp; interior items never touch a ghost row and
 //     never wait;
 //   * advect: no halo exchange at all -- a back-trace that leaves the slab reads the neighbour's rows
-//     through the peer mapping (advect4_peer_kernel);
+//     through the peer mapping (advect_lanes_kernel<NF, true>);
 //   * the few remaining exchanges (right-hand sides, one row of u, v) are a push kernel between two
 //     NEIGHBOUR BARRIER kernels (one warp: bump a local epoch, store it into both neighbours' inboxes,
 //     spin until both neighbours' epochs have arrived).  All counters live in device memory and only

@@ -423,29 +423,6 @@ __device__ __forceinline__ void advect_cell(const float *__restrict__ srcA, cons
     }
 }
 
-template <int NF>
-__global__ void __launch_bounds__(256) advect4_kernel(float *__restrict__ dA, float *__restrict__ dB,
-                                                      const float *__restrict__ srcA, const float *__restrict__ srcB,
-                                                      const float *__restrict__ u, const float *__restrict__ v, Geom g,
-                                                      float dt0, int bA)
-{
-    SF_ROW4_PROLOGUE
-    (void)lane; (void)cs;
-    if (!active) return;
-    const float4 uu = __ldg(reinterpret_cast<const float4 *>(u + rowoff + c));
-    const float4 vv = __ldg(reinterpret_cast<const float4 *>(v + rowoff + c));
-    const float hiC = (float)g.N + 0.5f;
-    float4 oA = make_float4(0.f, 0.f, 0.f, 0.f), oB = oA;
-    // columns 0 and N+1 are wall cells: their lanes are overwritten by store_row4_walls, but the
-    // trace still has to stay inside the array, which the clamp to [0.5, N+0.5] guarantees
-    advect_cell<NF>(srcA, srcB, g, row, c + 0, uu.x, vv.x, dt0, hiC, oA.x, oB.x);
-    advect_cell<NF>(srcA, srcB, g, row, c + 1, uu.y, vv.y, dt0, hiC, oA.y, oB.y);
-    advect_cell<NF>(srcA, srcB, g, row, c + 2, uu.z, vv.z, dt0, hiC, oA.z, oB.z);
-    advect_cell<NF>(srcA, srcB, g, row, c + 3, uu.w, vv.w, dt0, hiC, oA.w, oB.w);
-    store_row4_walls(dA, g, row, c, oA, bA == 1 ? -1.0f : 1.0f, bA == 2 ? -1.0f : 1.0f);
-    if (NF == 2) store_row4_walls(dB, g, row, c, oB, 1.0f, -1.0f);   // b = 2
-}
-
 // ---- advect on a peer-memory slab ---------------------------------------------------------------
 // Same arithmetic; the gather's two source rows are resolved per cell: a row outside this slab's
 // owned range is read straight from the neighbour GPU that owns it (peer loads over NVLink), so the
@@ -505,24 +482,73 @@ __device__ __forceinline__ void advect_cell_peer(const PeerView &sA, const PeerV
     if (NF == 2) oB = bilinear(peer_base(sB, w0) + off0 + c0, peer_base(sB, w1) + off1 + c0, wx0, wx1, wy0, wy1);
 }
 
-template <int NF>
-__global__ void __launch_bounds__(256) advect4_peer_kernel(float *__restrict__ dA, float *__restrict__ dB, PeerView sA,
-                                                           PeerView sB, const float *__restrict__ u,
-                                                           const float *__restrict__ v, Geom g, PeerGeom pg, float dt0, int bA)
+// ---- advect, lane-strided mapping (the product path for G % 4 == 0) ---------------------------------
+// A warp owns 128 consecutive columns of one row and lane l handles the four columns seg + 32 k + l (k = 0..3), NOT four
+// adjacent ones: every load, gather and store instruction of the warp then touches 32 CONSECUTIVE cells -- or their
+// back-traced sources, which are consecutive up to the (smooth) variation of the velocity field.  With four adjacent cells
+// per thread (advect4_kernel, round 1) each gather request was strided by 16 bytes and touched 16-27 sectors: ncu showed the
+// L1 tag stage at 76 % and DRAM at 38 % (profiles/r02/s1_86a0b52_stage_ncu.csv); one cell per thread coalesces as well but
+// keeps too few loads in flight per thread to cover two dependent DRAM round trips.  Same arithmetic per cell, same bits.
+// set_bnd is fused as before: the lane that holds wall column 0 / N+1 takes the adjacent interior value from lane 1 / lane-1
+// by shuffle; the warp of row 1 / row N also writes the wall row and its corners.
+// PEER = true: the two source rows of a back-trace may lie in a neighbour GPU's slab (see advect_cell_peer).
+template <int NF, bool PEER>
+__global__ void __launch_bounds__(256) advect_lanes_kernel(float *__restrict__ dA, float *__restrict__ dB, PeerView sA, PeerView sB,
+                                                           const float *__restrict__ u, const float *__restrict__ v, Geom g,
+                                                           PeerGeom pg, float dt0, int bA)
 {
-    SF_ROW4_PROLOGUE
-    (void)lane; (void)cs;
-    if (!active) return;
-    const float4 uu = __ldg(reinterpret_cast<const float4 *>(u + rowoff + c));
-    const float4 vv = __ldg(reinterpret_cast<const float4 *>(v + rowoff + c));
+    int lo, hi;
+    interior_rows(g, lo, hi);
+    const int lane = threadIdx.x;                                   // blockDim.x == 32: one warp per row segment
+    const int seg = blockIdx.x * 128;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y + lo;
+    if (row >= hi) return;                                          // uniform per warp
+    const size_t G = (size_t)g.G;
+    const size_t rowoff = (size_t)(row - g.row_base) * G;
     const float hiC = (float)g.N + 0.5f;
-    float4 oA = make_float4(0.f, 0.f, 0.f, 0.f), oB = oA;
-    advect_cell_peer<NF>(sA, sB, g, pg, row, c + 0, uu.x, vv.x, dt0, hiC, oA.x, oB.x);
-    advect_cell_peer<NF>(sA, sB, g, pg, row, c + 1, uu.y, vv.y, dt0, hiC, oA.y, oB.y);
-    advect_cell_peer<NF>(sA, sB, g, pg, row, c + 2, uu.z, vv.z, dt0, hiC, oA.z, oB.z);
-    advect_cell_peer<NF>(sA, sB, g, pg, row, c + 3, uu.w, vv.w, dt0, hiC, oA.w, oB.w);
-    store_row4_walls(dA, g, row, c, oA, bA == 1 ? -1.0f : 1.0f, bA == 2 ? -1.0f : 1.0f);
-    if (NF == 2) store_row4_walls(dB, g, row, c, oB, 1.0f, -1.0f);   // b = 2
+    float uu[4], vv[4], oA[4], oB[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                   // idle lanes (col >= G) mirror the last column: loads stay legal
+        const int cl = min(seg + 32 * k + lane, g.G - 1);
+        uu[k] = __ldg(u + rowoff + cl);
+        vv[k] = __ldg(v + rowoff + cl);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // columns 0 and N+1 are wall cells: their values are replaced below, but the trace still has to stay inside the
+        // array, which the clamp to [0.5, N+0.5] guarantees
+        const int cl = min(seg + 32 * k + lane, g.G - 1);
+        oA[k] = 0.0f; oB[k] = 0.0f;
+        if (PEER) advect_cell_peer<NF>(sA, sB, g, pg, row, cl, uu[k], vv[k], dt0, hiC, oA[k], oB[k]);
+        else advect_cell<NF>(sA.loc, sB.loc, g, row, cl, uu[k], vv[k], dt0, hiC, oA[k], oB[k]);
+    }
+    const bool top = (row == 1) && (g.own_lo == 0), bot = (row == g.N) && (g.own_hi == g.G);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        float *o = f == 0 ? oA : oB;
+        float *dst = (f == 0 ? dA : dB) + rowoff;
+        const float sx = (f == 0 ? bA == 1 : false) ? -1.0f : 1.0f;     // field B of the pair is v: b = 2
+        const float sy = (f == 0 ? bA == 2 : true) ? -1.0f : 1.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = seg + 32 * k + lane;
+            const float nxt = __shfl_down_sync(0xffffffffu, o[k], 1), prv = __shfl_up_sync(0xffffffffu, o[k], 1);
+            const bool wallL = (col == 0), wallR = (col == g.G - 1);
+            float val = o[k];
+            if (wallL) val = __fmul_rn(sx, nxt);                       // x[row][0]   = sx * x[row][1]
+            if (wallR) val = __fmul_rn(sx, prv);                       // x[row][N+1] = sx * x[row][N]
+            if (col < g.G) {
+                dst[col] = val;
+                if (top | bot) {
+                    float w = __fmul_rn(sy, val);                      // wall row = sy * adjacent interior row
+                    if (wallL) w = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(sy, nxt), val));   // corner = .5 * (wall-row nbr + wall-col nbr)
+                    if (wallR) w = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(sy, prv), val));
+                    if (top) (dst - G)[col] = w;
+                    if (bot) (dst + G)[col] = w;
+                }
+            }
+        }
+    }
 }
 
 inline bool row4_ok(const Geom &g, std::initializer_list<const void *> ptrs)
@@ -538,6 +564,8 @@ inline dim3 row4_grid(const Geom &g, dim3 block, int rows)
     return dim3((g.G + per_block - 1) / per_block, (rows + block.y - 1) / block.y);
 }
 
+// advect_lanes_kernel: block (32, 8) = eight rows of one 128-column segment
+inline dim3 lanes_grid(const Geom &g, int rows) { return dim3((g.G + 127) / 128, (rows + 7) / 8); }
 inline dim3 cell_grid(const Geom &g, dim3 block, int rows) { return dim3((g.N + block.x - 1) / block.x, (rows + block.y - 1) / block.y); }
 inline int interior_row_count(const Geom &g)
 {
@@ -552,8 +580,8 @@ void preload_stage_kernels()
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, set_bnd_kernel); cudaFuncGetAttributes(&a, add_source_kernel);
     cudaFuncGetAttributes(&a, advect_kernel<1>); cudaFuncGetAttributes(&a, advect_kernel<2>);
-    cudaFuncGetAttributes(&a, advect4_kernel<1>); cudaFuncGetAttributes(&a, advect4_kernel<2>);
-    cudaFuncGetAttributes(&a, advect4_peer_kernel<1>); cudaFuncGetAttributes(&a, advect4_peer_kernel<2>);
+    cudaFuncGetAttributes(&a, advect_lanes_kernel<1, false>); cudaFuncGetAttributes(&a, advect_lanes_kernel<2, false>);
+    cudaFuncGetAttributes(&a, advect_lanes_kernel<1, true>); cudaFuncGetAttributes(&a, advect_lanes_kernel<2, true>);
     cudaFuncGetAttributes(&a, divergence_kernel); cudaFuncGetAttributes(&a, divergence4_kernel);
     cudaFuncGetAttributes(&a, last_project_kernel); cudaFuncGetAttributes(&a, last_project4_kernel);
     cudaFuncGetAttributes(&a, init_kernel); cudaFuncGetAttributes(&a, init4_kernel);
@@ -592,9 +620,9 @@ cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const
     if (rows == 0) return cudaSuccess;
     const dim3 block(64, 4);
     const float dt0 = dt * (float)g.N;   // FluidSequential.c:111, rounded once in binary32
-    if (row4_ok(g, {d, d0, u, v})) {
-        const dim3 b4(32, 8);
-        advect4_kernel<1><<<row4_grid(g, b4, rows), b4, 0, st>>>(d, nullptr, d0, nullptr, u, v, g, dt0, b);
+    if (g.G % 4 == 0) {
+        const PeerView sA{d0, nullptr, nullptr};
+        advect_lanes_kernel<1, false><<<lanes_grid(g, rows), dim3(32, 8), 0, st>>>(d, nullptr, sA, sA, u, v, g, PeerGeom(), dt0, b);
         return cudaGetLastError();
     }
     advect_kernel<1><<<cell_grid(g, block, rows), block, 0, st>>>(d, nullptr, d0, nullptr, u, v, g, dt0, b);
@@ -607,9 +635,9 @@ cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u
     if (rows == 0) return cudaSuccess;
     const dim3 block(64, 4);
     const float dt0 = dt * (float)g.N;
-    if (row4_ok(g, {du, dv, u0, v0})) {
-        const dim3 b4(32, 8);
-        advect4_kernel<2><<<row4_grid(g, b4, rows), b4, 0, st>>>(du, dv, u0, v0, u0, v0, g, dt0, 1);
+    if (g.G % 4 == 0) {
+        const PeerView sA{u0, nullptr, nullptr}, sB{v0, nullptr, nullptr};
+        advect_lanes_kernel<2, false><<<lanes_grid(g, rows), dim3(32, 8), 0, st>>>(du, dv, sA, sB, u0, v0, g, PeerGeom(), dt0, 1);
         return cudaGetLastError();
     }
     advect_kernel<2><<<cell_grid(g, block, rows), block, 0, st>>>(du, dv, u0, v0, u0, v0, g, dt0, 1);
@@ -621,11 +649,10 @@ cudaError_t launch_advect_peer(const Geom &g, int b, float *d, const float *d0, 
 {
     const int rows = interior_row_count(g);
     if (rows == 0) return cudaSuccess;
-    if (!row4_ok(g, {d, d0, u, v, d0p.up, d0p.dn})) return cudaErrorInvalidValue;
+    if (g.G % 4 != 0) return cudaErrorInvalidValue;
     const float dt0 = dt * (float)g.N;   // FluidSequential.c:111
-    const dim3 b4(32, 8);
     const PeerView sA{d0, d0p.up, d0p.dn};
-    advect4_peer_kernel<1><<<row4_grid(g, b4, rows), b4, 0, st>>>(d, nullptr, sA, sA, u, v, g, pg, dt0, b);
+    advect_lanes_kernel<1, true><<<lanes_grid(g, rows), dim3(32, 8), 0, st>>>(d, nullptr, sA, sA, u, v, g, pg, dt0, b);
     return cudaGetLastError();
 }
 
@@ -634,11 +661,10 @@ cudaError_t launch_advect_uv_peer(const Geom &g, float *du, float *dv, const flo
 {
     const int rows = interior_row_count(g);
     if (rows == 0) return cudaSuccess;
-    if (!row4_ok(g, {du, dv, u0, v0, u0p.up, u0p.dn, v0p.up, v0p.dn})) return cudaErrorInvalidValue;
+    if (g.G % 4 != 0) return cudaErrorInvalidValue;
     const float dt0 = dt * (float)g.N;
-    const dim3 b4(32, 8);
     const PeerView sA{u0, u0p.up, u0p.dn}, sB{v0, v0p.up, v0p.dn};
-    advect4_peer_kernel<2><<<row4_grid(g, b4, rows), b4, 0, st>>>(du, dv, sA, sB, u0, v0, g, pg, dt0, 1);
+    advect_lanes_kernel<2, true><<<lanes_grid(g, rows), dim3(32, 8), 0, st>>>(du, dv, sA, sB, u0, v0, g, pg, dt0, 1);
     return cudaGetLastError();
 }
 

@@ -35,6 +35,7 @@ SF_OPT_PRESSURE_PLAN = 10
 SF_OPT_SOLVER = 11
 SF_OPT_SOR_OMEGA_MILLI = 12
 SF_OPT_RBGS_BLOCKED = 13
+SF_OPT_FUSE_SOURCES = 14
 STRICT, FAST = 0, 1
 SOLVER_JACOBI, SOLVER_RBGS = 0, 1    # SF_OPT_SOLVER: the reference's Jacobi (default) / opt-in red-black Gauss-Seidel (SOR)
 

@@ -96,7 +96,13 @@ enum {
     /* SF_SOLVER_RBGS only: 0 (default) = one kernel launch per half-sweep; 1 = the red-black sweeps run on the
      * temporally blocked streaming pipeline of the Jacobi kernels (three iterations per launch; grid widths with
      * (N+2) % 4 == 0, other widths keep the one-launch-per-half-sweep path).  Results are unchanged. */
-    SF_OPT_RBGS_BLOCKED = 13
+    SF_OPT_RBGS_BLOCKED = 13,
+    /* 1 (default) = inside dens_step / vel_step / step the add_source pass (seq:78-82) is fused into the first temporally
+     * blocked launch of the lin_solve that follows it (seq:177-182, :193-210): the right-hand side x + dt*s is formed as
+     * the rows stream in and kept in a context-owned field, one pass over x and s less per solve.  The fields the
+     * reference's step functions leave behind (u, v, dens and the clobbered *_prev buffers) are unchanged, bit for bit.
+     * 0 = a separate add_source kernel, as sf_add_source + sf_diffuse would run it.  Full-grid contexts. */
+    SF_OPT_FUSE_SOURCES = 14
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 enum { SF_SOLVER_JACOBI = 0, SF_SOLVER_RBGS = 1 };

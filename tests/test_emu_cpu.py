@@ -26,6 +26,8 @@ def emu(variant):
         L = C.CDLL(build_emu.build("" if variant == "default" else variant, VARIANTS[variant]))
         L.emu_lin_solve.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
         L.emu_lin_solve.restype = C.c_int
+        L.emu_source_lin_solve.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.emu_source_lin_solve.restype = C.c_int
         _libs[variant] = L
     return _libs[variant]
 
@@ -62,6 +64,31 @@ def test_kernel_source_on_the_smallest_grids(oracle, variant):
                     got[...] = np.nan          # an implicit zero guess is never read
                 assert L.emu_lin_solve(N, b, p(got), p(x0), al, be, K, T, zg, 0, 0, 1.0) == 0
                 assert same(got, want), (variant, N, T, b, K, zg)
+
+
+def test_fused_add_source_in_the_kernel_source(oracle):
+    """jacobi_stream_kernel<T, STRICT, 6> (SF_OPT_FUSE_SOURCES): the first launch of a solve forms x0 + dt * s itself.  Against
+    add_source + diffuse of the oracle; the raw field must come back untouched; small grids, two bands, chunked, a front that
+    decays through the division's low range (guarded groups and pipeline restarts re-form the right-hand side)."""
+    L = emu("default")
+    rng = np.random.default_rng(5)
+    dt = 0.016
+    cases = [(N, T, K, 0) for N in (2, 6, 30) for T, K in ((5, 10), (6, 12), (7, 14))] + [(126, 7, 14, 0), (126, 7, 40, 24), (126, 5, 20, 16)]
+    for N, T, K, chunk in cases:
+        G = N + 2
+        for b, (al, be) in ((0, (2683.2, 10733.8)), (1, (0.635, 3.54)), (2, (2683.2, 10733.8))):
+            src = rng.uniform(0, 1, (G, G)).astype(np.float32); raw = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+            if N == 126 and b == 0:      # density-like: compact support, a front running through 1e-30 .. 1e-45 .. 0
+                yy, xx = np.mgrid[0:G, 0:G]
+                r = np.hypot(yy - G / 2, xx - G / 2)
+                raw = (np.float32(0.05) * np.exp(-np.maximum(r - 10, 0) * 3.0)).astype(np.float32)
+                src = (raw * np.float32(0.5)).astype(np.float32)
+            rhs = raw.copy(); oracle.add_source(N, rhs, src, dt)
+            want = src.copy(); oracle.diffuse(N, b, want, rhs, al, be, K)
+            got, raw_in = src.copy(), raw.copy()
+            assert L.emu_source_lin_solve(N, b, p(got), p(raw_in), dt, al, be, K, T, chunk) == 0
+            assert same(got, want), (N, T, K, chunk, b)
+            assert same(raw_in, raw)
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))

@@ -166,11 +166,16 @@ def test_diffuse_tiny_patches_restart_the_pipeline(SF, oracle, b, chunk, T):
 
 
 # ---- steps ----------------------------------------------------------------------------------------
-@pytest.mark.parametrize("N,K", [(30, 4), (62, 20), (126, 40), (254, 20), (130, 6)])
-def test_vel_and_dens_step(SF, oracle, N, K):
+@pytest.mark.parametrize("fuse", [1, 0])
+@pytest.mark.parametrize("N,K", [(30, 4), (62, 20), (126, 40), (254, 20), (130, 6), (254, 12), (510, 33)])
+def test_vel_and_dens_step(SF, oracle, N, K, fuse):
+    """fuse = 1 (default): add_source is formed inside the first launch of each viscosity / diffusion solve when that launch
+    fuses 5-7 sweeps (K = 20: 5, K = 12: 6, K = 40 and 33: 7; K = 4 and 6 take the separate add_source kernel either way)."""
     G = N + 2
     rng = np.random.default_rng(N + K)
     s = SF.StableFluids(N)
+    s.set_option(SF.SF_OPT_FUSE_SOURCES, fuse)
+    assert s.get_option(SF.SF_OPT_FUSE_SOURCES) == fuse
     u, v, u0, v0 = rnd(rng, G, -.1, .1), rnd(rng, G, -.1, .1), rnd(rng, G, 0, 1), rnd(rng, G, 0, 1)
     wu, wv, wu0, wv0 = (a.copy() for a in (u, v, u0, v0))
     oracle.vel_step(N, wu, wv, wu0, wv0, VIS, DT, K)

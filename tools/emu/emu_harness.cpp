@@ -52,7 +52,7 @@ int run_T(int T, const StreamArgs &A, int ctas)
 
 // launch_jacobi_stream (csrc/sf_jacobi.cu) for a full-grid context: same geometry, same StreamArgs
 int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mode, float alpha, float beta, int sweeps,
-           int zero_guess, int chunk_rows, int rb, float omega)
+           int zero_guess, int chunk_rows, int rb, float omega, float *rhs_out = nullptr, float src_dt = 0.0f)
 {
     StreamArgs A;
     std::memset(&A, 0, sizeof(A));
@@ -63,6 +63,7 @@ int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mo
     A.write_top = 1; A.write_bot = 1;
     A.nbands = (G + VALID_W - 1) / VALID_W;
     A.zero_guess = zero_guess;
+    A.rhs_out = rhs_out; A.src_dt = src_dt;
     A.alpha = alpha; A.div = make_div_const(beta);
     const double F = 1.0 + 4.0 * fabs((double)alpha);
     if (!rb) {
@@ -85,7 +86,7 @@ int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mo
     const int rows = A.a_hi - A.a_lo;
     int chunk = chunk_rows;
     if (chunk <= 0) {
-        const bool heavy = (mode == MODE_STRICT || mode == MODE_IEEE) && sweeps >= 6;
+        const bool heavy = (mode == MODE_STRICT || mode == MODE_IEEE || mode == MODE_PRESSURE) && sweeps >= 6;
         const int slots = 148 * (heavy ? 3 : 4) * WPC;
         int want = slots / A.nbands;
         if (want < 1) want = 1;
@@ -101,6 +102,14 @@ int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mo
     if (rb) {
         if (mode == MODE_PRESSURE) return run_T<MODE_PRESSURE, 5>(sweeps, A, ctas);
         return run_T<MODE_STRICT, 5>(sweeps, A, ctas);
+    }
+    if (rhs_out != nullptr) {      // fused add_source: the depths launch_stream_T builds (5, 6, 7), strict arithmetic
+        switch (sweeps) {
+            case 5: run_grid<5, MODE_STRICT, 6>(A, ctas); return 0;
+            case 6: run_grid<6, MODE_STRICT, 6>(A, ctas); return 0;
+            case 7: run_grid<7, MODE_STRICT, 6>(A, ctas); return 0;
+        }
+        return -1;
     }
     if (mode == MODE_PRESSURE) return run_T<MODE_PRESSURE, 0>(sweeps, A, ctas);
     return run_T<MODE_STRICT, 0>(sweeps, A, ctas);
@@ -130,6 +139,27 @@ int emu_lin_solve(int N, int b, float *x, const float *x0, float alpha, float be
     if (!rb && zero_guess && (plan.size() & 1)) { cur = scratch.data(); nxt = x; }
     for (size_t k = 0; k < plan.size(); ++k) {
         if (launch(nxt, cur, x0, N, b, mode, alpha, beta, plan[k], zero_guess && k == 0, chunk_rows, rb, omega)) return -1;
+        std::swap(cur, nxt);
+    }
+    if (cur != x) std::memcpy(x, cur, cells * sizeof(float));
+    return 0;
+}
+
+// source_lin_solve of csrc/sf_api.cu, fused form: x = source field and initial guess (receives the result), x0 = the raw
+// field (left untouched); the first launch forms x0 + dt * x and stores it to a separate right-hand-side field
+int emu_source_lin_solve(int N, int b, float *x, const float *x0, float dt, float alpha, float beta, int iters, int T, int chunk_rows)
+{
+    using namespace sf;
+    const size_t cells = (size_t)(N + 2) * (N + 2);
+    std::vector<float> scratch(cells, NAN), rhs(cells, NAN);
+    int L = (iters + T - 1) / T;
+    if ((L & 1) && L + 1 <= iters) ++L;
+    std::vector<int> plan(L, iters / L);
+    for (int k = 0; k < iters % L; ++k) ++plan[k];
+    float *cur = x, *nxt = scratch.data();
+    for (size_t k = 0; k < plan.size(); ++k) {
+        if (launch(nxt, cur, k == 0 ? x0 : rhs.data(), N, b, MODE_STRICT, alpha, beta, plan[k], 0, chunk_rows, 0, 1.0f,
+                   k == 0 ? rhs.data() : nullptr, dt)) return -1;
         std::swap(cur, nxt);
     }
     if (cur != x) std::memcpy(x, cur, cells * sizeof(float));

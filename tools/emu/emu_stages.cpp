@@ -64,9 +64,9 @@ void emu_advect(int N, int b, float *d, const float *d0, const float *u, const f
     const Geom g = full(N);
     const int rows = interior_row_count(g);
     const float dt0 = dt * (float)g.N;
-    if (row4_ok(g, {d, d0, u, v})) {
-        const dim3 b4(32, 8);
-        run_kernel(row4_grid(g, b4, rows), b4, [&] { advect4_kernel<1>(d, nullptr, d0, nullptr, u, v, g, dt0, b); });
+    if (g.G % 4 == 0) {
+        const PeerView sA{d0, nullptr, nullptr};
+        run_kernel(lanes_grid(g, rows), dim3(32, 8), [&] { advect_lanes_kernel<1, false>(d, nullptr, sA, sA, u, v, g, PeerGeom(), dt0, b); });
     } else {
         const dim3 block(64, 4);
         run_kernel(cell_grid(g, block, rows), block, [&] { advect_kernel<1>(d, nullptr, d0, nullptr, u, v, g, dt0, b); });
@@ -77,9 +77,9 @@ void emu_advect_uv(int N, float *du, float *dv, const float *u0, const float *v0
     const Geom g = full(N);
     const int rows = interior_row_count(g);
     const float dt0 = dt * (float)g.N;
-    if (row4_ok(g, {du, dv, u0, v0})) {
-        const dim3 b4(32, 8);
-        run_kernel(row4_grid(g, b4, rows), b4, [&] { advect4_kernel<2>(du, dv, u0, v0, u0, v0, g, dt0, 1); });
+    if (g.G % 4 == 0) {
+        const PeerView sA{u0, nullptr, nullptr}, sB{v0, nullptr, nullptr};
+        run_kernel(lanes_grid(g, rows), dim3(32, 8), [&] { advect_lanes_kernel<2, false>(du, dv, sA, sB, u0, v0, g, PeerGeom(), dt0, 1); });
     } else {
         const dim3 block(64, 4);
         run_kernel(cell_grid(g, block, rows), block, [&] { advect_kernel<2>(du, dv, u0, v0, u0, v0, g, dt0, 1); });
