@@ -523,6 +523,16 @@ __global__ void __launch_bounds__(256) advect_lanes_kernel(float *__restrict__ d
         else advect_cell<NF>(sA.loc, sB.loc, g, row, cl, uu[k], vv[k], dt0, hiC, oA[k], oB[k]);
     }
     const bool top = (row == 1) && (g.own_lo == 0), bot = (row == g.N) && (g.own_hi == g.G);
+    if (seg > 0 && seg + 128 < g.G && !(top | bot)) {
+        // warp-uniform fast path (all but the first / last segment of a row and the two rows next to a wall row):
+        // no wall column, no idle lane, no wall row -- four coalesced stores per field
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dA[rowoff + seg + 32 * k + lane] = oA[k];
+            if (NF == 2) dB[rowoff + seg + 32 * k + lane] = oB[k];
+        }
+        return;
+    }
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         float *o = f == 0 ? oA : oB;

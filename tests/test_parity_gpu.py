@@ -297,10 +297,17 @@ def test_launch_counter_counts_kernels(SF):
     n0 = s.launch_count
     s.step(*f, VIS, DIFF, DT, 40)
     per_step = s.launch_count - n0
-    # 5 lin_solves of 6 launches (40 sweeps as 7,7,7,7,6,6) + add(2) + div(2) + grad(2) + advect(2)
-    assert per_step == 5 * 6 + 8, per_step
-    s.step(*f, VIS, DIFF, DT, 40); s.step(*f, VIS, DIFF, DT, 40)   # direct, then captured+replayed
-    assert s.launch_count - n0 == 3 * per_step
+    # 5 lin_solves of 6 launches (40 sweeps as 7,7,7,7,6,6; add_source rides in the first launch of the three solves
+    # that have one) + div(2) + grad(2) + advect(2)
+    assert per_step == 5 * 6 + 6, per_step
+    s.set_option(SF.SF_OPT_FUSE_SOURCES, 0)
+    n1 = s.launch_count
+    s.step(*f, VIS, DIFF, DT, 40)
+    assert s.launch_count - n1 == 5 * 6 + 6 + 3        # three separate add_source kernels (u, v, dens)
+    s.set_option(SF.SF_OPT_FUSE_SOURCES, 1)
+    n0 = s.launch_count
+    s.step(*f, VIS, DIFF, DT, 40); s.step(*f, VIS, DIFF, DT, 40)   # captured + replayed
+    assert s.launch_count - n0 == 2 * per_step
 
 
 def test_c_example_with_reference_names(oracle, tmp_path):
