@@ -43,6 +43,9 @@ enum ArithMode {
 //  ~5 ms, cached per beta); a beta that fails, or cannot be checked, runs MODE_IEEE.
 #define SF_DIV_LO 1e-30f
 #define SF_DIV_HI 1e30f
+// a right-hand-side cell of at least this magnitude (2^-75) proves that no numerator it enters lies in (0, SF_DIV_LO):
+// see row_flags in sf_jacobi.cu (2^-99 > 1e-30)
+#define SF_RHS_LO 2.6469779601696886e-23f
 struct DivConst {
     float b, y;      // divisor, RN32(1/b)
     float nz, pad;   // -0.0f as a RUN-TIME value (see mul2_exact)

@@ -213,7 +213,9 @@ __device__ __forceinline__ float4 scale4(float4 v, float s)
 //                               into `ok`; no branch sits between the sweep levels.  The caller votes
 //                               once per tick and redoes the tick GUARDED if any lane failed (the high
 //                               end is proved per fetched row, see row_is_big).
-template <int MODE, bool GUARDED>
+//                CHECK = false : no test at all -- the caller has proved from the right-hand-side rows that no numerator
+//                               of this tick can lie in (0, SF_DIV_LO) (see row_flags in stream_rows).
+template <int MODE, bool GUARDED, bool CHECK = true>
 __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rgt, const float4 &up, const float4 &dn,
                                           const float4 &r, float alpha, const DivConst &d, bool &ok)
 {
@@ -235,7 +237,7 @@ __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rg
         }
         if (MODE == MODE_STRICT && !GUARDED) {
             const float2 o01 = div_const_fast2(a01, d), o23 = div_const_fast2(a23, d);
-            ok = ok & div_low_ok(a01.x) & div_low_ok(a01.y) & div_low_ok(a23.x) & div_low_ok(a23.y);
+            if (CHECK) ok = ok & div_low_ok(a01.x) & div_low_ok(a01.y) & div_low_ok(a23.x) & div_low_ok(a23.y);
             return make_float4(o01.x, o01.y, o23.x, o23.y);
         }
         if (MODE == MODE_STRICT) {
@@ -287,7 +289,8 @@ __device__ __forceinline__ float4 jacobi4(float lft, const float4 &mid, float rg
 // on black levels only (wall columns and wall rows copy through on red levels).  A lane's first column is a multiple of 4,
 // so which two of its four cells a level updates is warp-uniform.  omega travels in A.div.pad (1.0f = plain Gauss-Seidel).
 // GUARD = true: the wall-free tick with the binary64 division for every cell (groups inside a guarded span).
-template <int T, int MODE, int PH, bool WALLS, bool RB = false, bool GUARD = false>
+// CHECK = false: the strict wall-free tick without the per-cell low-range test (see jacobi4).
+template <int T, int MODE, int PH, bool WALLS, bool RB = false, bool GUARD = false, bool CHECK = true>
 __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const float4 &row_in, float4 (&W)[T][3],
                                               const float4 *rring, bool ownsL, bool ownsR, float4 &out)
 {
@@ -301,7 +304,7 @@ __device__ __forceinline__ bool pipeline_tick(const StreamArgs &A, int s, const 
         const float4 r = rring[(a & (RING_R - 1)) * 32];
         const float lft = __shfl_up_sync(0xffffffffu, mid.w, 1);
         const float rgt = __shfl_down_sync(0xffffffffu, mid.x, 1);
-        float4 o = jacobi4<MODE, WALLS || GUARD>(lft, mid, rgt, up, dn, r, A.alpha, A.div, ok);
+        float4 o = jacobi4<MODE, WALLS || GUARD, CHECK>(lft, mid, rgt, up, dn, r, A.alpha, A.div, ok);
         if constexpr (RB) {
             const bool black = (t & 1) != 0;                 // compile-time: t is an unrolled index
             const float om = A.div.pad;
@@ -452,6 +455,36 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             cp_async_wait<PREFETCH>();
         }
     };
+    // MODE_STRICT only: the wall-free tick guards just the LOW end of the exact division's range per
+    // cell.  The high end follows from a maximum principle: |numerator| <= (1 + 4|alpha|) * max|input|,
+    // so rows whose magnitudes stay below A.hi_in can never produce a numerator above SF_DIV_HI.
+    // Every row is checked when it is fetched; one outlier switches the warp to the fully guarded
+    // tick for the next rows (up to the next multiple of 64).
+    // (both lambdas below are only used inside a fast group, whose rows s..s+2 <= fast_hi <= load_hi)
+    auto xrow_in = [&](int row) -> float4 {
+        return zero_guess ? make_float4(0.f, 0.f, 0.f, 0.f) : xring[(row & (RING_X - 1)) * 32];
+    };
+    // The LOW end needs no per-cell test where the right-hand side is not tiny.  A numerator is a = RN(x0 + w), w = RN(alpha *
+    // sum), with the SAME x0 at every level.  If |x0| >= 2^-75: either |w| <= |x0|/2 or |w| >= 2|x0|, and then |a| >= |x0|/2;
+    // or w is within a factor 2 of x0, both are integer multiples of 2^(floor(log2|x0|) - 24) >= 2^-99, and so is their exact
+    // sum -- it is 0 or at least 2^-99 in magnitude, and rounding keeps that.  Either way a == 0 or |a| >= 2^-99 > SF_DIV_LO:
+    // inside the range the exhaustive validation of div_const_fast covers.  So a row of the right-hand side whose cells all
+    // have |x0| >= SF_RHS_LO proves every numerator that will ever use it, and a group all of whose right-hand-side rows are
+    // proven (rows s-T .. s+1: `unproven_until`) runs the tick WITHOUT the test: ~125 of ~875 instructions per group less.
+    // Rows with a zero or tiny right-hand side (outside the support of a density field, its decaying front) keep the tested
+    // tick.  bit 0 = outlier (see above), bit 1 = a right-hand-side cell of this lane is zero / below SF_RHS_LO / NaN.
+    auto row_flags = [&](int row) -> unsigned {
+        if (MODE != MODE_STRICT) return 0u;
+        const float4 a = xrow_in(row), b = rring[(row & (RING_R - 1)) * 32];
+        const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                              fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        const float lo = fminf(fminf(fabsf(b.x), fabsf(b.y)), fminf(fabsf(b.z), fabsf(b.w)));
+        // (lanes outside the grid hold zeros: their cells are never stored and never reach a stored cell)
+        return (!(m <= A.hi_in) ? 1u : 0u) | ((indom && !(lo >= SF_RHS_LO)) ? 2u : 0u);   // NaN counts as big and as unproven
+    };
+    // first tick none of whose numerators uses an unproven right-hand-side row (row r is used by ticks r+1 .. r+T)
+    [[maybe_unused]] int unproven_until = 0;
+
     [[maybe_unused]] auto fuse_src = [&](int row) {      // exactly once per landed row
         if constexpr (SRC) {
             if (row <= load_hi) {
@@ -470,6 +503,9 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
         issue(row + PREFETCH);
         landed(row, 1);
         fuse_src(row);
+        if constexpr (MODE == MODE_STRICT && !TMA && !STRIP) {
+            if (row <= load_hi && __any_sync(0xffffffffu, (row_flags(row) & 2u) != 0)) unproven_until = row + T + 1;
+        }
         float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!zero_guess && row <= load_hi) in = xring[(row & (RING_X - 1)) * 32];
         return in;
@@ -479,23 +515,6 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
         if (!zero_guess && row <= load_hi) in = xring[(row & (RING_X - 1)) * 32];
         return in;
     };
-    // MODE_STRICT only: the wall-free tick guards just the LOW end of the exact division's range per
-    // cell.  The high end follows from a maximum principle: |numerator| <= (1 + 4|alpha|) * max|input|,
-    // so rows whose magnitudes stay below A.hi_in can never produce a numerator above SF_DIV_HI.
-    // Every row is checked when it is fetched; one outlier switches the warp to the fully guarded
-    // tick for the next rows (up to the next multiple of 64).
-    // (both lambdas below are only used inside a fast group, whose rows s..s+2 <= fast_hi <= load_hi)
-    auto xrow_in = [&](int row) -> float4 {
-        return zero_guess ? make_float4(0.f, 0.f, 0.f, 0.f) : xring[(row & (RING_X - 1)) * 32];
-    };
-    auto row_is_big = [&](int row) -> bool {
-        if (MODE != MODE_STRICT) return false;
-        const float4 a = xrow_in(row), b = rring[(row & (RING_R - 1)) * 32];
-        const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
-                              fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
-        return !(m <= A.hi_in);   // NaN counts as big
-    };
-
     float4 W[T][3];
 
     // peer-memory slabs: a boundary strip stores the rows its neighbour needs straight into the
@@ -564,6 +583,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
 
     for (;;) {   // (re)start of the pipeline at `first`
     bool restart = false;
+    unproven_until = 0;          // every row the restarted pipeline uses lands (and is looked at) again
 #pragma unroll
     for (int t = 0; t < T; ++t) W[t][0] = W[t][1] = W[t][2] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -604,7 +624,12 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             landed(s, 3);                    // rows <= s+2 have landed
             fuse_src(s); fuse_src(s + 1); fuse_src(s + 2);
             bool big = false;
-            if (MODE == MODE_STRICT) big = __any_sync(0xffffffffu, row_is_big(s) | row_is_big(s + 1) | row_is_big(s + 2));
+            if (MODE == MODE_STRICT) {
+                // one warp-wide OR for both row properties of the three rows that have just landed
+                const unsigned fl = __reduce_or_sync(0xffffffffu, row_flags(s) | row_flags(s + 1) | row_flags(s + 2));
+                big = (fl & 1u) != 0;
+                if (fl & 2u) unproven_until = s + 2 + T + 1;
+            }
             if (!big) {
                 float4 o;
                 if constexpr (GROUP_VOTE || BRANCH_FREE_GROUP) {
@@ -614,6 +639,19 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                     auto emit_plain = [&](int a, const float4 &ov) {
                         if (a >= first && a < a_hi && st_ok) *reinterpret_cast<float4 *>(A.xout + (e0 + (cell_t)(a - (s - T)) * Gu)) = ov;
                     };
+                    if constexpr (GROUP_VOTE) {
+                        if (unproven_until <= s) {
+                            // every right-hand-side row these three ticks use is proven: no range test, no vote, no restart
+                            pipeline_tick<T, MODE, 0, false, RB, false, false>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
+                            emit_plain(s - T, o);
+                            pipeline_tick<T, MODE, 1, false, RB, false, false>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
+                            emit_plain(s + 1 - T, o);
+                            pipeline_tick<T, MODE, 2, false, RB, false, false>(A, s + 2, xrow_in(s + 2), W, rring, ownsL, ownsR, o);
+                            emit_plain(s + 2 - T, o);
+                            s += 3;
+                            continue;
+                        }
+                    }
                     ok = pipeline_tick<T, MODE, 0, false, RB>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
                     emit_plain(s - T, o);
                     ok &= pipeline_tick<T, MODE, 1, false, RB>(A, s + 1, xrow_in(s + 1), W, rring, ownsL, ownsR, o);
@@ -682,6 +720,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                 issue3(s + PREFETCH);
                 landed(s, 3);
                 fuse_src(s); fuse_src(s + 1); fuse_src(s + 2);
+                if (__any_sync(0xffffffffu, ((row_flags(s) | row_flags(s + 1) | row_flags(s + 2)) & 2u) != 0)) unproven_until = s + 2 + T + 1;
                 float4 o;
                 pipeline_tick<T, MODE, 0, false, RB, true>(A, s, xrow_in(s), W, rring, ownsL, ownsR, o);
                 emit_plain(s - T, o);

@@ -91,6 +91,39 @@ def test_fused_add_source_in_the_kernel_source(oracle):
             assert same(raw_in, raw)
 
 
+def test_unproven_right_hand_side_rows_keep_the_range_test(oracle):
+    """The strict group drops the per-cell low-range test where every right-hand-side row it uses is proven (|x0| >= 2^-75,
+    row_flags in csrc/sf_jacobi.cu).  Adversarial layout for the bookkeeping: an O(1) right-hand side with scattered blocks of
+    zero / 1e-41 cells (single cells, single rows, blocks that straddle the band edge and chunk boundaries) over a TINY
+    iterate, so that the numerators inside the blocks sit far below the fast division's range for several levels -- a tick
+    that used an unproven row without the test would round a subnormal quotient wrongly.  A failing seed prints its layout."""
+    L = emu("default")
+    N = 126; G = N + 2
+    al, be = 2683.2, 10733.8
+    for seed in range(6):
+        rng = np.random.default_rng(100 + seed)
+        x0 = (rng.uniform(0.1, 1, (G, G)) * rng.choice([-1.0, 1.0], (G, G))).astype(np.float32)
+        x = (10.0 ** rng.uniform(-43, -37, (G, G)) * rng.choice([-1.0, 1.0], (G, G))).astype(np.float32)
+        blocks = []
+        for k in range(10):
+            # (the 3-instruction division is wrong only for a small fraction of the numerators below its range: tall, wide
+            # blocks keep thousands of them tiny down to the deepest level.  What random data cannot reach is the tail of the
+            # window -- the ticks r+1 .. r+T after a block's last row r: there the block's cells have proven neighbours
+            # below them, whose values are far from tiny unless they cancel to within 2^-24; the window is kept anyway,
+            # the proof in row_flags needs it)
+            h, w = (int(rng.choice([12, 20, 30])), int(rng.choice([40, 90, 120]))) if k < 3 else (int(rng.choice([1, 1, 2, 5, 9])), int(rng.choice([1, 3, 9, 30])))
+            r0, c0 = int(rng.integers(1, G - h - 1)), int(rng.choice([int(rng.integers(1, G - w - 1)), 108, 112, 2]))
+            c0 = min(c0, G - w - 1)
+            val = float(rng.choice([0.0, 1e-41, -3e-40, 1e-30]))
+            x0[r0:r0 + h, c0:c0 + w] = np.float32(val)
+            blocks.append((r0, h, c0, w, val))
+        for T, K, chunk, b in ((7, 14, 0, 0), (7, 13, 16, 1), (6, 12, 24, 2), (5, 10, 20, 0)):
+            want = x.copy(); oracle.diffuse(N, b, want, x0, al, be, K)
+            got = x.copy()
+            assert L.emu_lin_solve(N, b, p(got), p(x0), al, be, K, T, 0, chunk, 0, 1.0) == 0
+            assert same(got, want), (seed, T, K, chunk, b, blocks)
+
+
 @pytest.mark.parametrize("variant", list(VARIANTS))
 def test_kernel_source_two_bands_chunks_and_a_decaying_front(oracle, variant):
     """G = 128 (two bands), small chunks, and a compactly supported field whose front decays through the low end of the exact

@@ -84,6 +84,15 @@ inline int __all_sync(unsigned, int pred)
     emu::warp_barrier->arrive_and_wait();
     return r;
 }
+inline unsigned __reduce_or_sync(unsigned, unsigned v)
+{
+    emu::exchange[emu::lane()] = v;
+    emu::warp_barrier->arrive_and_wait();
+    unsigned r = 0;
+    for (int k = 0; k < 32; ++k) r |= (unsigned)emu::exchange[k];
+    emu::warp_barrier->arrive_and_wait();
+    return r;
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier->arrive_and_wait(); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
