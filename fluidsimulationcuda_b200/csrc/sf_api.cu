@@ -677,15 +677,57 @@ int sf_step_host(sf_context *c, float *dens, float *dens_prev, float *u, float *
     if (!c) return SF_ERR_INVALID;
     SF_REQUIRE(c, dens && dens_prev && u && u_prev && v && v_prev, "step_host: null field");
     SF_REQUIRE(c, iters >= 1, "step_host: iters < 1");
-    SF_REQUIRE(c, is_full_grid(c), "step_host: full-grid contexts only");
+    SF_REQUIRE(c, is_full_grid(c) || is_linked_slab(c), "step_host: full-grid contexts and connected peer slabs only");
     DeviceGuard guard(c->device);
-    const size_t bytes = field_cells(c) * sizeof(float);
     if (!c->h2d) {
         SF_CUDA(c, cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
         SF_CUDA(c, cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
         for (auto &e : c->ev) SF_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        for (auto &s : c->stage) SF_CUDA(c, cudaMalloc(&s, bytes));
     }
+    if (is_linked_slab(c)) {
+        // Connected peer slab (collective, one caller per slab): the host arrays hold this slab's OWNED rows
+        // (own_rows x (N+2)); the device fields are the first six fields of the arena in the order of the arguments
+        // (sf_slab_field 0..5).  Ghost rows need no upload: every stage that reads them refreshes them from the neighbour.
+        SF_REQUIRE(c, c->link.nfields >= 6, "step_host on a peer slab: the arena needs at least six fields");
+        c->link.barrier_valid = false;
+        int rc = check_multi_launch_ok(c, iters);
+        if (rc) return rc;
+        if ((rc = slab_prevalidate(c, visc, dt)) || (rc = slab_prevalidate(c, diff, dt))) return rc;
+        const size_t G = (size_t)c->g.G;
+        const size_t own_bytes = (size_t)(c->g.own_hi - c->g.own_lo) * G * sizeof(float);
+        const size_t own_off = (size_t)(c->g.own_lo - c->g.row_base) * G;
+        float *dev[6];
+        for (int k = 0; k < 6; ++k) dev[k] = reinterpret_cast<float *>(c->link.base + (size_t)k * c->link.field_bytes);
+        float *host[6] = {dens, dens_prev, u, u_prev, v, v_prev};
+        SF_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+        SF_CUDA(c, cudaStreamWaitEvent(c->h2d, c->ev[5], 0));            // the previous step is done with the device fields
+        for (int k : {2, 3, 4, 5}) SF_CUDA(c, cudaMemcpyAsync(dev[k] + own_off, host[k], own_bytes, cudaMemcpyHostToDevice, c->h2d));
+        SF_CUDA(c, cudaEventRecord(c->ev[0], c->h2d));                   // velocity first: vel_step starts while the density fields travel
+        for (int k : {0, 1}) SF_CUDA(c, cudaMemcpyAsync(dev[k] + own_off, host[k], own_bytes, cudaMemcpyHostToDevice, c->h2d));
+        SF_CUDA(c, cudaEventRecord(c->ev[1], c->h2d));
+        SF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[0], 0));
+        rc = run_graphed(c, make_key(c, 2, {dev[2], dev[4], dev[3], dev[5]}, visc, dt, 0.f, iters),
+                         [&] { return enqueue_vel_step(c, dev[2], dev[4], dev[3], dev[5], visc, dt, iters); });
+        if (rc) return rc;
+        SF_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+        SF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[1], 0));
+        rc = run_graphed(c, make_key(c, 1, {dev[0], dev[1], dev[2], dev[4]}, diff, dt, 0.f, iters),
+                         [&] { return enqueue_dens_step(c, dev[0], dev[1], dev[2], dev[4], diff, dt, iters); });
+        if (rc) return rc;
+        SF_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+        SF_CUDA(c, cudaStreamWaitEvent(c->d2h, c->ev[2], 0));            // u, v drain while dens_step runs
+        for (int k : {2, 4}) SF_CUDA(c, cudaMemcpyAsync(host[k], dev[k] + own_off, own_bytes, cudaMemcpyDeviceToHost, c->d2h));
+        if (download_scratch)
+            for (int k : {3, 5}) SF_CUDA(c, cudaMemcpyAsync(host[k], dev[k] + own_off, own_bytes, cudaMemcpyDeviceToHost, c->d2h));
+        SF_CUDA(c, cudaStreamWaitEvent(c->d2h, c->ev[3], 0));
+        SF_CUDA(c, cudaMemcpyAsync(host[0], dev[0] + own_off, own_bytes, cudaMemcpyDeviceToHost, c->d2h));
+        if (download_scratch) SF_CUDA(c, cudaMemcpyAsync(host[1], dev[1] + own_off, own_bytes, cudaMemcpyDeviceToHost, c->d2h));
+        SF_CUDA(c, cudaStreamSynchronize(c->d2h));
+        return SF_OK;
+    }
+    const size_t bytes = field_cells(c) * sizeof(float);
+    if (!c->stage[0])
+        for (auto &s : c->stage) SF_CUDA(c, cudaMalloc(&s, bytes));
     int rc = ensure_scratch(c);
     if (rc) return rc;
     float *d_dens = c->stage[0], *d_dens0 = c->stage[1], *d_u = c->stage[2], *d_u0 = c->stage[3], *d_v = c->stage[4], *d_v0 = c->stage[5];

@@ -525,9 +525,14 @@ class PeerSlabSolver(SlabLayout):
         return [t.empty((self.own_rows, self.G), dtype=t.float32, pin_memory=True).zero_() for _ in self.NAMES]
 
     def step_host(self, host_fields, visc: float, diff: float, dt: float):
-        """``step_host_begin`` + ``step_host_end`` (one process per GPU)."""
-        self.step_host_begin(host_fields, visc, diff, dt)
-        self.step_host_end()
+        """The loop body with HOST fields through the C ABI (``sf_step_host`` on a connected peer slab): uploads this rank's
+        owned rows of the six fields, steps (collectively), downloads dens, u, v; returns when the host arrays are valid.
+        One caller per slab at the same time: one process per GPU, or one thread per slab (ctypes releases the GIL).
+        ``step_host_begin`` / ``step_host_end`` below are the same schedule split in two for a single thread that drives
+        several slabs."""
+        if self.world == 1:
+            raise SF.StableFluidsError("PeerSlabSolver.step_host: world == 1, use StableFluids.step_host")
+        self.ctx.step_host(*host_fields, visc, diff, dt, self.iters)
 
     def step_host_end(self):
         """Returns when the host arrays of the step begun last are valid."""

@@ -285,11 +285,13 @@ class StableFluids:
 
     def step_host(self, dens, dens_prev, u, u_prev, v, v_prev, visc, diff, dt, iters, download_scratch=False):
         """Same loop body with HOST fields (numpy float32 arrays or CPU tensors, ideally pinned)."""
+        cells = (self.row_hi - self.row_lo) * self.G      # a slab context exchanges its owned rows only
+
         def hp(a):
             if hasattr(a, "data_ptr"):
-                assert not a.is_cuda and a.is_contiguous() and a.numel() == self.G * self.G
+                assert not a.is_cuda and a.is_contiguous() and a.numel() == cells
                 return C.c_void_p(a.data_ptr())
-            assert a.dtype.name == "float32" and a.flags["C_CONTIGUOUS"] and a.size == self.G * self.G
+            assert a.dtype.name == "float32" and a.flags["C_CONTIGUOUS"] and a.size == cells
             return C.c_void_p(a.ctypes.data)
         self._check(self.L.sf_step_host(self.h, hp(dens), hp(dens_prev), hp(u), hp(u_prev), hp(v), hp(v_prev),
                                         visc, diff, dt, iters, 1 if download_scratch else 0))

@@ -172,7 +172,10 @@ int sf_step(sf_context *ctx, float *dens, float *dens_prev, float *u, float *u_p
 /* Same loop body for a caller whose six fields live in HOST memory (the reference's CPU path,
  * seq:277-282): uploads the six fields, runs the step on the device, downloads dens, u, v (and,
  * if download_scratch != 0, the three clobbered *_prev fields) and returns when the host buffers
- * are valid.  Pinned host memory makes the copies overlap the compute. */
+ * are valid.  Pinned host memory makes the copies overlap the compute.
+ * On a connected peer slab (sf_slab_connect_*) the call is collective -- one caller per slab, all at the same time -- the
+ * host arrays hold the slab's OWNED rows only ((row_hi - row_lo) x (N+2) floats) and the device fields are the first six
+ * fields of the slab's arena in the order of the arguments (sf_slab_field 0..5). */
 int sf_step_host(sf_context *ctx, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev,
                  float visc, float diff, float dt, int iters, int download_scratch);
 

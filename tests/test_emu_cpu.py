@@ -28,6 +28,7 @@ def emu(variant):
         L.emu_lin_solve.restype = C.c_int
         L.emu_source_lin_solve.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
         L.emu_source_lin_solve.restype = C.c_int
+        L.emu_set_steal_variant.argtypes = [C.c_int]
         _libs[variant] = L
     return _libs[variant]
 
@@ -89,6 +90,44 @@ def test_fused_add_source_in_the_kernel_source(oracle):
             assert L.emu_source_lin_solve(N, b, p(got), p(raw_in), dt, al, be, K, T, chunk) == 0
             assert same(got, want), (N, T, K, chunk, b)
             assert same(raw_in, raw)
+
+
+def test_zero_row_shortcut_of_the_scalar_field_variants(oracle):
+    """jacobi_stream_kernel<T, STRICT, 3 / 7> (scalar fields: dens_step's solve): groups whose last 2T+3 input rows were
+    all-zero bits only store zeros.  Compactly supported fields with zero margins of every width around them, a blob that
+    starts right after a long zero run (the shortcut must end in time), -0.0 rows (not zero bits), the fused-source form."""
+    L = emu("default")
+    L.emu_set_steal_variant(1)
+    try:
+        rng = np.random.default_rng(9)
+        N = 254; G = N + 2
+        al, be = 107322.0, 429289.0
+        for case in range(5):
+            x = np.zeros((G, G), np.float32); x0 = np.zeros((G, G), np.float32)
+            for _ in range(3):
+                r0, c0 = int(rng.integers(1, G - 40)), int(rng.integers(1, G - 40))
+                h, w = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+                x0[r0:r0 + h, c0:c0 + w] = rng.uniform(0, 0.1, (h, w)).astype(np.float32)
+                if case % 2:
+                    x[r0:r0 + h, c0:c0 + w] = rng.uniform(0, 0.1, (h, w)).astype(np.float32)
+            if case == 3:
+                x[100:103, :] = np.float32(-0.0)           # -0.0 is not "zero bits": ((-0) + (-0)) stays -0 through a sweep
+                x0[100:103, :] = np.float32(-0.0)
+            if case == 4:
+                x0[G - 2, 5] = np.float32(1e-3)            # a single cell at the very end of a band's rows
+            for T, K, chunk in ((7, 14, 0), (7, 20, 64), (5, 10, 0), (6, 12, 100)):
+                want = x.copy(); oracle.diffuse(N, 0, want, x0, al, be, K)
+                got = x.copy()
+                assert L.emu_lin_solve(N, 0, p(got), p(x0), al, be, K, T, 0, chunk, 0, 1.0) == 0
+                assert same(got, want), ("zero rows", case, T, K, chunk)
+            dt = 0.016
+            rhs = x0.copy(); oracle.add_source(N, rhs, x, dt)
+            want = x.copy(); oracle.diffuse(N, 0, want, rhs, al, be, 14)
+            got, raw = x.copy(), x0.copy()
+            assert L.emu_source_lin_solve(N, 0, p(got), p(raw), dt, al, be, 14, 7, 0) == 0
+            assert same(got, want), ("zero rows, fused source", case)
+    finally:
+        L.emu_set_steal_variant(0)
 
 
 def test_unproven_right_hand_side_rows_keep_the_range_test(oracle):

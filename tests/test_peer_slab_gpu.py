@@ -136,6 +136,45 @@ def test_peer_slab_host_field_step(oracle):
         s.close()
 
 
+def test_peer_slab_step_host_through_the_c_abi(oracle):
+    """sf_step_host on connected slabs (collective): one host thread per slab calls the C entry point with its owned rows."""
+    import threading
+    N, K, world = 254, 12, 3
+    solvers = make(N, world, K)
+    w = oracle.init_synthetic(N, 9)
+    hosts = []
+    for s in solvers:
+        hf = s.new_host_fields()
+        for h, name in zip(hf, s.names):
+            h.copy_(torch.from_numpy(w[name][s.row_lo:s.row_hi]))
+        hosts.append(hf)
+    errors = []
+
+    def run(s, hf):
+        try:
+            s.step_host(hf, VIS, DIFF, DT)
+        except Exception as e:      # noqa: BLE001 -- reported by the main thread
+            errors.append(e)
+    for step in range(3):
+        threads = [threading.Thread(target=run, args=(s, hf)) for s, hf in zip(solvers, hosts)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+        oracle.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=0)
+        for i, name in enumerate(solvers[0].names):
+            if name in ("dens", "u", "v"):
+                got = torch.cat([hf[i] for hf in hosts], dim=0).numpy()
+                assert bits_equal(got, w[name]), mismatch_report(got, w[name], f"C ABI step_host, step {step} {name}")
+        for i, name in enumerate(solvers[0].names):
+            if name.endswith("_prev"):
+                w[name][...] = torch.cat([hf[i] for hf in hosts], dim=0).numpy()
+    for s in solvers:
+        s.status()
+        s.close()
+
+
 def test_missing_neighbour_times_out_instead_of_hanging():
     from fluidsimulationcuda_b200.slab import PeerSlabSolver
     from fluidsimulationcuda_b200.solver import StableFluidsError

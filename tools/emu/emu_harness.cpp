@@ -12,6 +12,7 @@
 namespace sf {
 namespace {
 float4 ring[WPC * (RING_X + RING_R) * 32 + 256];     // the kernel's `extern __shared__ float4 ring[]` (+ mbarrier words)
+bool g_steal_variant = false;                         // emu_set_steal_variant: strict launches run VAR 3 / 7 instead of 0 / 6
 
 template <int T, int MODE, int VAR>
 void run_grid(const StreamArgs &A, int ctas)
@@ -103,6 +104,27 @@ int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mo
         if (mode == MODE_PRESSURE) return run_T<MODE_PRESSURE, 5>(sweeps, A, ctas);
         return run_T<MODE_STRICT, 5>(sweeps, A, ctas);
     }
+    if (g_steal_variant && mode == MODE_STRICT && !rb && items > 1) {
+        // the work-stealing variants (VAR 3 / 7: scalar fields).  Warps run one after the other here, so nobody ever finds
+        // a range to take over -- what this exercises is the variant's own streaming code (zero-row shortcut, polls)
+        static std::vector<char> ctl_mem;
+        const int capacity = 16384;
+        ctl_mem.assign(sizeof(StealCtl) + (size_t)capacity * sizeof(StealSlot), 0);
+        StealCtl *ctl = reinterpret_cast<StealCtl *>(ctl_mem.data());
+        ctl->min_pct = 30;
+        for (int k = 0; k < capacity; ++k) ctl->slots[k].pos = 0x3fffffff;
+        if (items > capacity) return -1;
+        A.steal = ctl;
+        if (rhs_out != nullptr) {
+            switch (sweeps) {
+                case 5: run_grid<5, MODE_STRICT, 7>(A, ctas); return 0;
+                case 6: run_grid<6, MODE_STRICT, 7>(A, ctas); return 0;
+                case 7: run_grid<7, MODE_STRICT, 7>(A, ctas); return 0;
+            }
+            return -1;
+        }
+        return run_T<MODE_STRICT, 3>(sweeps, A, ctas);
+    }
     if (rhs_out != nullptr) {      // fused add_source: the depths launch_stream_T builds (5, 6, 7), strict arithmetic
         switch (sweeps) {
             case 5: run_grid<5, MODE_STRICT, 6>(A, ctas); return 0;
@@ -118,6 +140,7 @@ int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mo
 }  // namespace sf
 
 extern "C" {
+void emu_set_steal_variant(int on) { sf::g_steal_variant = on != 0; }
 // lin_solve of csrc/sf_api.cu (Jacobi: plan_launches; red-black: three iterations per launch); result ends in x
 int emu_lin_solve(int N, int b, float *x, const float *x0, float alpha, float beta, int iters, int T, int zero_guess,
                   int chunk_rows, int rb, float omega)
