@@ -205,6 +205,220 @@ def scaling_base(Gs, K, steps=5, timeout_s=240):
         return {"grid": Gs, "value": None, "error": repr(e)}
 
 
+def child_json(extra_args, timeout_s):
+    """Run this file as a child process (so that nothing the extra measurement does -- an allocation failure, a CUDA error,
+    a hang -- can cost the headline line) and return the last JSON object it printed."""
+    cmd = [sys.executable, os.path.abspath(__file__)] + extra_args
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+                                                             "ROLE_RANK", "TORCHELASTIC_RUN_ID")}
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s, env=env)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        return json.loads(lines[-1])
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+REFGPU_BLOCKS = {"LOOPUNROLLED-Interleaved": ("16", "16"), "FluidParallelBlockPerElement-Naive": ("32", "16"),
+                 "FluidParallelBlockPerElement-SM": ("32", "16")}     # the block shapes of the reference's report.txt
+
+
+def refgpu_elapsed(name, N, K, steps, mode, repeats=2):
+    """Wall clock the reference's own CUDA program prints ("elapsed ... sec"), best of `repeats` runs; None if not built.
+    oracle/_ref/refgpu_* are built from the reference's sources by `make -C oracle refgpu` (sed sets hN, the iteration
+    count and the step count; *_resident drops the loop's per-step host zeroing + three uploads)."""
+    import re
+    exe = os.path.join(ROOT, "oracle", "_ref", f"refgpu_{name}_N{N}_K{K}_S{steps}_{mode}")
+    if not os.path.exists(exe):
+        return None
+    best = None
+    for _ in range(repeats):
+        out = subprocess.run([exe, *REFGPU_BLOCKS[name]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120).stdout
+        m = re.search(r"elapsed ([0-9.]+) sec", out)
+        if not m:
+            return None
+        best = float(m.group(1)) if best is None else min(best, float(m.group(1)))
+    return best
+
+
+def run_config2_child(args):
+    """BASELINE configs[1]: G = 1024, 20 iterations, 1000 steps on one B200 against the reference's smPar / optPar / naivePar
+    CUDA programs rebuilt for sm_100a and run on this same GPU; plus the reference's fastest program at the headline size.
+    Reference per-step time = (T(many steps) - T(1 step)) / (many - 1) of the program's own wall-clock print, which removes
+    its one-time rand() init and uploads (the programs have no per-step timer)."""
+    import torch
+    from fluidsimulationcuda_b200 import solver as SF
+    torch.cuda.set_device(0)
+    out = {"workload": "G=1024 (N=1022), 20 Jacobi iterations per lin_solve, 1000 steps, device-resident loop (sf_run_steps, "
+                       "synthetic source refresh every step); the working set (9 fields x 4 MiB) is L2-resident: launch- and "
+                       "L2-bound, not HBM-bound"}
+    N, K, steps = 1022, 20, 1000
+    s = SF.StableFluids(N)
+    f = [s.new_field() for _ in range(6)]
+    s.init_synthetic(1, *f)
+    s.run_steps(*f, VIS, DIFF, DT, K, 20, SF.SOURCES_SYNTHETIC, 10)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = s.launch_count
+    a.record(); s.run_steps(*f, VIS, DIFF, DT, K, steps, SF.SOURCES_SYNTHETIC, 100); b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    out.update({"grid": 1024, "iters": K, "steps": steps, "ms_per_step": ms, "kernel_launches_per_step": (s.launch_count - n0) / steps,
+                "value": 5.0 * K * N * N / (ms * 1e-3), "unit": "cell-updates/s", "reference_cuda_programs_same_gpu": {}})
+    s.close(); del f
+    ref = out["reference_cuda_programs_same_gpu"]
+    for name in REFGPU_BLOCKS:
+        for mode in ("resident", "asis"):
+            t1, th = refgpu_elapsed(name, N, K, 1, mode), refgpu_elapsed(name, N, K, 201, mode)
+            if t1 is None or th is None:
+                continue
+            per = (th - t1) / 200 * 1e3
+            ref[f"{name} ({'kernels only' if mode == 'resident' else 'as shipped: per-step host zeroing + 3 uploads'})"] = {
+                "ms_per_step": per, "speedup_of_ours": per / ms}
+    if not ref:
+        out["reference_cuda_programs_same_gpu"] = "not built (oracle/_ref/refgpu_*: `make -C oracle refgpu` where /root/reference exists)"
+    # the reference's fastest program (report.txt:45-46) at the headline size, against the headline time passed in
+    big = {}
+    for mode in ("resident", "asis"):
+        t1, th = refgpu_elapsed("LOOPUNROLLED-Interleaved", 8190, 40, 1, mode, 1), refgpu_elapsed("LOOPUNROLLED-Interleaved", 8190, 40, 6, mode, 1)
+        if t1 is None or th is None:
+            continue
+        per = (th - t1) / 5 * 1e3
+        big[f"LOOPUNROLLED-Interleaved ({'kernels only' if mode == 'resident' else 'as shipped'})"] = {
+            "ms_per_step": per, "speedup_of_ours": (per / args.headline_ms) if args.headline_ms > 0 else None}
+    if big:
+        out["headline_size_G8192_K40"] = {"ours_ms_per_step": args.headline_ms, "reference_cuda_programs_same_gpu": big}
+    print(json.dumps(out))
+
+
+def reference_schedule(SF, torch, N, K, steps=50):
+    """The reference loop's own source rule (FluidSequential.c:298-302: sources act in step 0 only, the three *_prev fields are
+    zeroed before every later step).  Density then decays into the 1e-30 .. subnormal range where the exact division takes
+    its guarded (binary64) ticks; the headline instead refreshes the sources every step.  ms per step, zeroing included."""
+    s = SF.StableFluids(N)
+    f = [s.new_field() for _ in range(6)]
+    s.init_synthetic(1, *f)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for k in range(steps):
+        if k > 0:
+            for t in (f[1], f[3], f[5]):
+                t.zero_()
+        s.step(*f, VIS, DIFF, DT, K)
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+    dmax = s.reduce_max_abs(f[0])
+    s.close()
+    pick = [k for k in (1, 2, 5, 10, 25, 50) if k <= steps]
+    return {"schedule": "sources in step 0 only, *_prev fields zeroed before every later step (FluidSequential.c:298-302)",
+            "grid": N + 2, "iters": K, "ms_at_step": {str(k): ms[k - 1] for k in pick}, "ms_mean_steps_3_to_end": sum(ms[2:]) / len(ms[2:]),
+            "max_dens_after": dmax,
+            "note": "steps 1-2 include the one-time direct run and graph capture; compare with ms_per_step of the headline "
+                    "(sources refreshed every step)"}
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's host threads (and therefore the first-touch placement of the pinned host buffers it allocates next)
+    to the NUMA node its GPU hangs off.  Returns a description for the JSON line; never fatal."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bus is None:
+            import ctypes
+            buf = ctypes.create_string_buffer(32)
+            torch.cuda.cudart().cudaDeviceGetPCIBusId(buf, 32, local)
+            bus = buf.value.decode()
+    except Exception:
+        bus = None
+    try:
+        if bus is None:
+            q = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                               stdout=subprocess.PIPE, text=True, timeout=20).stdout.strip()
+            bus = q
+        dom = bus.lower()
+        if len(dom.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit domain, sysfs uses 4
+            dom = dom[4:]
+        node = int(open(f"/sys/bus/pci/devices/{dom}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA affinity reported for this GPU"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed), "pci": dom}
+    except Exception as e:
+        return {"numa_node": None, "note": repr(e)[:120]}
+
+
+def slab_parity(torch, dist, rank, world, G=2048, K=20, steps=2):
+    """Correctness bit of a multi-GPU line: the SAME peer-slab path (CUDA IPC mappings, fused strip exchange, device-side
+    barriers, one graph per GPU) on a problem the CPU oracle finishes in a second, every field of every rank compared
+    BITWISE with the oracle after `steps` steps (reference schedule: sources zeroed after step 0)."""
+    import numpy as np
+    from fluidsimulationcuda_b200.slab import PeerSlabSolver
+    N = G - 2
+    sim = PeerSlabSolver(N, rank, world, iters=K)
+    sim.connect_dist()
+    sim.init_synthetic(3)
+    for st in range(steps):
+        if st > 0:
+            sim.zero_sources()
+        sim.step(None, VIS, DIFF, DT)
+    sim.status()
+    torch.cuda.synchronize()
+    from oracle.pyoracle import Oracle          # the checker, on every rank's own rows (never timed, never the product path)
+    o = Oracle()
+    w = o.init_synthetic(N, 3)
+    o.run_steps(N, steps, w, VIS, DIFF, DT, K)
+    bad = 0
+    for k in sim.names:
+        got = sim.owned(sim.f[k]).cpu().numpy()
+        want = w[k][sim.row_lo:sim.row_hi]
+        bad += int((got.view(np.uint32) != want.view(np.uint32)).sum())
+    t = torch.tensor([bad], device="cuda", dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    sim.close()
+    return {"ok": int(t.item()) == 0, "mismatching_cells": int(t.item()), "grid": G, "iters": K, "steps": steps, "fields": 6,
+            "against": "CPU oracle (restatement pinned to the reference's sequential build), bitwise, every rank's owned rows"}
+
+
+def config5(torch, dist, rank, world, local, G=16384, K=200, steps=3):
+    from fluidsimulationcuda_b200.slab import PeerSlabSolver
+    from fluidsimulationcuda_b200 import solver as SF
+    N = G - 2
+    sim = PeerSlabSolver(N, rank, world, iters=K, arithmetic=SF.STRICT)
+    sim.connect_dist()
+    sim.init_synthetic(1)
+    for i in range(2):
+        sim.step(100 + i, VIS, DIFF, DT)
+    torch.cuda.synchronize(); dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(sim.stream)
+    for i in range(steps):
+        sim.step(1000 + i, VIS, DIFF, DT)
+    b.record(sim.stream)
+    sim.status()
+    torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([a.elapsed_time(b) / steps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    sim.close()
+    torch.cuda.empty_cache()
+    base = None
+    if rank == 0:
+        j = child_json(["--gpus", "1", "--grid", str(G), "--iters", str(K), "--steps", str(steps), "--warmup", "3", "--skip-extras",
+                        "--scaling-base", "0"], 240)
+        base = {"n_gpus": 1, "ms_per_step": j.get("ms_per_step"), "value": j.get("value"), "error": j.get("error")}
+    dist.barrier()
+    return {"workload": f"G={G} (N={N}), {K} Jacobi iterations per lin_solve, row slabs x{world} (strong scaling of one problem)",
+            "grid": G, "iters": K, "n_gpus": world, "steps": steps, "ms_per_step": ms, "value": 5.0 * K * N * N / (ms * 1e-3),
+            "unit": "cell-updates/s", "same_run_one_gpu": base}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -224,9 +438,16 @@ def run_ours(args):
     cells = G * G
     peak, peak_how = measured_peak()
 
+    parity = numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
         from fluidsimulationcuda_b200.slab import SlabSolver, TorchDistComm, PeerSlabSolver
+        if args.slab_comm == "peer" and not args.skip_extras:
+            numa = bind_to_gpu_numa_node(torch, local)
+            try:      # correctness bit of this line, before anything is timed
+                parity = slab_parity(torch, dist, rank, world)
+            except Exception as e:
+                parity = {"ok": False, "error": repr(e)[:300]}
         if args.slab_comm == "peer":
             # product path: neighbours' slabs mapped over NVLink (CUDA IPC), halo pushes fused into the
             # Jacobi strips, device-side neighbour barriers, one CUDA-graph replay per step per GPU
@@ -301,6 +522,8 @@ def run_ours(args):
         "effective_hbm_gbs": eff_gbs, "effective_hbm_frac_of_measured_peak": eff_gbs / (peak * world),
         "gpu_launches": n_launch, "clocks": clocks,
     }
+    if parity is not None:
+        out["parity"] = parity
     if world > 1:
         out["scaling_note"] = (f"strong scaling of the G={G} problem over {world} GPUs; the N=1 bench line runs G=8192 (the size the "
                                "metric is quoted on), so compare with the single-GPU time of THIS problem: the `scaling_base` object "
@@ -328,7 +551,7 @@ def run_ours(args):
         out["roofline"] = {
             "kernel": "jacobi_stream_kernel (temporally blocked lin_solve)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_how,
-            "traffic": PROFILED_DRAM_BYTES_PER_LAUNCH.get(G),
+            "traffic": PROFILED_DRAM_BYTES_PER_LAUNCH.get(G), "traffic_capture": PROFILED_DRAM_META or None,
             "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launches_per_lin_solve": jl,
             "avg_launch_ms": tot_ms / (sweeps / K) / jl,
             "note": "algorithmic bytes = 12 B per cell per sweep (read x, read x0, write x'); one launch fuses "
@@ -367,6 +590,17 @@ def run_ours(args):
         # that the strong-scaling lines have their own base next to the G = 8192 headline (reported, never fatal)
         if G == 8192 and args.scaling_base:
             out["scaling_base"] = scaling_base(args.scaling_base, K)
+        # ---- the other BASELINE configurations that fit one GPU, and the reference's own source schedule (reported, never fatal)
+        out["extra"] = {}
+        try:
+            out["extra"]["reference_schedule"] = reference_schedule(SF, torch, N, K)
+        except Exception as e:
+            out["extra"]["reference_schedule"] = {"error": repr(e)[:300]}
+        if G == 8192 and args.config2:
+            f.clear()                               # (the child runs on the same GPU: give the memory back first)
+            s.close()
+            torch.cuda.empty_cache()
+            out["extra"]["config2"] = child_json(["--child", "config2", "--headline-ms", repr(ms_step)], 240)
     elif world > 1 and args.slab_comm == "peer" and not args.skip_extras:
         # ---- end to end on N GPUs: every rank keeps its slab of the six fields in pinned host memory;
         # per step it uploads them, steps (collectively) and downloads dens, u, v -- all inside the timed region
@@ -388,11 +622,19 @@ def run_ours(args):
             dt_ = float(tt.item())
             out["e2e"] = {"value": 5.0 * K * N * N / dt_, "unit": "cell-updates/s", "ms_per_step": dt_ * 1e3,
                           "h2d_bytes_per_step": 6 * cells * 4, "d2h_bytes_per_step": 3 * cells * 4,
-                          "api": "PeerSlabSolver.step_host: every rank uploads its slab of the six pinned host fields, steps, "
-                                 "downloads dens/u/v (bytes are the sum over ranks; max over ranks of the wall time)"}
+                          "api": "sf_step_host (C ABI) on connected peer slabs, one call per rank: uploads the rank's owned rows of the "
+                                 "six pinned host fields, steps collectively, downloads dens/u/v (bytes are the sum over ranks; "
+                                 "max over ranks of the wall time)",
+                          "host_numa": numa}
             del hf
         except Exception as e:
             out["e2e"] = {"value": None, "unit": "cell-updates/s", "error": repr(e)}
+        # ---- BASELINE configs[4]: pressure-projection stress, G = 16384, 200 iterations, strong scaling -- this run's
+        # N-GPU time and, measured by rank 0 in a child process while the others wait, the 1-GPU time of the same problem
+        try:
+            out["extra"] = {"config5": config5(torch, dist, rank, world, local)}
+        except Exception as e:
+            out["extra"] = {"config5": {"error": repr(e)[:300]}}
     elif rank == 0:
         out["e2e"] = {"value": None, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                       "note": "not measured in this run (--skip-extras or --slab-comm nccl); see the N=1 line"}
@@ -404,10 +646,14 @@ def run_ours(args):
 
 # ncu `dram__bytes_read.sum + dram__bytes_write.sum` per jacobi_stream_kernel launch, from the
 # committed capture profiles/ (see profiles/README.md); None until a capture exists for that size.
-PROFILED_DRAM_BYTES_PER_LAUNCH = {}
+PROFILED_DRAM_BYTES_PER_LAUNCH, PROFILED_DRAM_META = {}, {}
 try:
     with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as _f:
-        PROFILED_DRAM_BYTES_PER_LAUNCH = {int(k): v for k, v in json.load(_f).items()}
+        for _k, _v in json.load(_f).items():
+            if _k.isdigit():
+                PROFILED_DRAM_BYTES_PER_LAUNCH[int(_k)] = _v
+            else:
+                PROFILED_DRAM_META[_k] = _v      # commit and kernel the capture was taken on
 except Exception:
     pass
 
@@ -424,10 +670,16 @@ def main():
                     help="multi-GPU halo traffic: peer = fused peer-memory pushes + device barriers (default), nccl = NCCL send/recv")
     ap.add_argument("--scaling-base", type=int, default=32768,
                     help="N=1 only: also time one GPU on this grid (the N>1 workload); 0 = skip")
+    ap.add_argument("--config2", type=int, default=1, help="N=1 only: also run BASELINE configs[1] (G=1024, K=20, 1000 steps) in a child; 0 = skip")
+    ap.add_argument("--child", default="", choices=["", "config2"], help="internal: run one extra measurement and print its JSON object")
+    ap.add_argument("--headline-ms", type=float, default=0.0, help="internal (--child config2): this run's G=8192 ms/step")
     ap.add_argument("--skip-extras", action="store_true",
                     help="only the timed region (no roofline / e2e / cpu_baseline passes): for ncu launch lists")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.child == "config2":
+        run_config2_child(args)
+        return
     if args.impl == "reference":
         if args.grid == 0:
             args.grid = 8192      # the reference arm always samples the single-GPU configuration

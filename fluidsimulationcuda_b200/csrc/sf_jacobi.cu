@@ -38,7 +38,7 @@ namespace {
 constexpr int BAND_W = 128;   // columns per warp (32 lanes x float4)
 constexpr int HALO_X = 8;     // band halo columns on each side (>= max T, multiple of 4)
 constexpr int VALID_W = BAND_W - 2 * HALO_X;  // 112 output columns per band
-constexpr int STEAL_MIN_ROWS = 64;            // work stealing: smallest remaining range worth halving
+constexpr int STEAL_MIN_ROWS = 16;            // work stealing: smallest remaining range worth halving, whatever the option says
 #ifndef SF_WPC
 #define SF_WPC 4
 #define SF_RING_X 8
@@ -611,7 +611,8 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
             // the progress and look at the slot's end.  Rows leave the pipeline in increasing order, so once
             // every row below an end lowered by a thief has been emitted (s - T >= end) this warp is done;
             // nothing else about the loop changes.  The load is consumed one poll LATER: no stall.
-            if (((s - a_lo) & 31) < 3) {
+            // (every 8 rows inside a guarded span: those rows cost ~3x as much, and the ranges worth taking there are short)
+            if (((s - a_lo) & (slow_until > s ? 7 : 31)) < 3) {
                 if (end_seen <= s - T) break;
                 // (the slot address is recomputed here rather than kept in registers across the hot loop)
                 StealSlot *slot = A.steal->slots + (blockIdx.x * WPC + (threadIdx.x >> 5));
