@@ -81,6 +81,7 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
     JacobiLaunch L;
     L.xin = xin; L.rhs = x0; L.xout = xout;
     L.rhs_out = rhs_out; L.src_dt = src_dt;
+    L.wave_skew_pct = c->wave_skew;
     L.alpha = alpha; L.beta = beta; L.b = b; L.sweeps = sweeps;
     L.mode = arith_mode(c, alpha, beta);
     L.out_lo = out_lo; L.out_hi = out_hi;
@@ -314,7 +315,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.iters = iters;
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
     k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan + 16 * c->solver +
-                32 * c->omega_milli + 65536 * c->rbgs_blocked + 131072 * c->fuse_sources;
+                32 * c->omega_milli + 65536 * c->rbgs_blocked + 131072 * c->fuse_sources + 262144 * c->wave_skew;
     return k;
 }
 
@@ -431,6 +432,7 @@ int sf_set_option(sf_context *c, int option, int value)
         case SF_OPT_SOR_OMEGA_MILLI: SF_REQUIRE(c, value >= 1 && value <= 1999, "SOR omega in 1/1000: 1..1999"); c->omega_milli = value; break;
         case SF_OPT_RBGS_BLOCKED: c->rbgs_blocked = value ? 1 : 0; break;
         case SF_OPT_FUSE_SOURCES: c->fuse_sources = value ? 1 : 0; break;
+        case SF_OPT_WAVE_SKEW: SF_REQUIRE(c, value >= 0 && value <= 60, "wave skew: 0..60 percent of a chunk"); c->wave_skew = value; break;
         case SF_OPT_STEAL_SCOPE: SF_REQUIRE(c, value == 0 || value == 1, "steal scope: 0 scalar fields / 1 every strict solve"); c->steal_scope = value; break;
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }
@@ -454,6 +456,7 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_SOR_OMEGA_MILLI: *value = c->omega_milli; break;
         case SF_OPT_RBGS_BLOCKED: *value = c->rbgs_blocked; break;
         case SF_OPT_FUSE_SOURCES: *value = c->fuse_sources; break;
+        case SF_OPT_WAVE_SKEW: *value = c->wave_skew; break;
         case SF_OPT_STEAL_COUNT: {   // diagnostics: row ranges taken over by another warp so far (synchronises)
             *value = 0;
             if (c->steal) {

@@ -278,6 +278,8 @@ struct JacobiLaunch {
     // the launch forms raw + src_dt * xin on the fly and stores it to rhs_out (nullptr = off)
     float *rhs_out = nullptr;
     float src_dt = 0.0f;
+    // chunks of the CTAs an SM receives first get this many percent more rows than the next "wave" of CTAs (0 = equal chunks)
+    int wave_skew_pct = 0;
 };
 // can launch_jacobi_stream fuse add_source into a launch of this depth and mode?  (the instantiations that exist)
 inline bool jacobi_src_fusion_built(int sweeps, int mode) { return sweeps >= 5 && sweeps <= 7 && (mode == MODE_STRICT || mode == MODE_IEEE); }

@@ -89,7 +89,29 @@ struct StreamArgs {
     // as the rows land and stored to rhs_out for the later launches of the solve; `rhs` points at the raw field
     float *rhs_out;
     float src_dt;
+    // wave skew (see chunk_range): bits 0..15 = h rows, bits 16..27 = chunks per wave, bits 28..31 = waves; 0 = uniform chunks
+    unsigned skew;
 };
+// Output rows of chunk `chunk`.  All warps of a launch are resident at once (one wave of CTAs, W = 3 or 4 per SM), but they do
+// not finish together: the warp schedulers favour the oldest warp, i.e. the CTAs the SM received first.  With equal chunks
+// the first third of the grid's CTAs finished a T = 7 launch after ~150 us and the last third after ~235 us
+// (tools/warp_times.py, profiles/r02/), and the schedulers idle more and more in between.  CTA i holds chunk i / (CTAs per
+// chunk row), so the chunks of the w-th "wave" of CTAs (chunks w * cpw .. (w+1) * cpw - 1) get chunk_rows + h * (W-1-2w) rows:
+// older warps take more rows, the sum is unchanged.
+__device__ __forceinline__ void chunk_range(const StreamArgs &A, int chunk, int &a_lo, int &a_hi)
+{
+    if (A.skew == 0u) {
+        a_lo = A.a_lo + chunk * A.chunk_rows;
+        a_hi = min(a_lo + A.chunk_rows, A.a_hi);
+        return;
+    }
+    const int h = (int)(A.skew & 0xffffu), cpw = (int)((A.skew >> 16) & 0xfffu), W = (int)(A.skew >> 28);
+    const int w = chunk / cpw, j = chunk - w * cpw;
+    const int rows = A.chunk_rows + h * (W - 1 - 2 * w);
+    a_lo = A.a_lo + cpw * (w * A.chunk_rows + h * (w * (W - w))) + j * rows;
+    a_hi = min(a_lo + rows, A.a_hi);
+    a_lo = min(a_lo, A.a_hi);
+}
 
 // GPU-scope relaxed accesses for the stealing words (plain `volatile` would be system-scope strong accesses)
 __device__ __forceinline__ int ld_relaxed_gpu(const int *p)
@@ -867,6 +889,21 @@ __device__ __noinline__ void strip_warp(const StreamArgs A, float4 *ring, const 
     strip_post(P->arrive, P->seq, P->nbr_inbox, A.nbands, lane);
 }
 
+#ifdef SF_WARP_TIMES
+// developer build (-DSF_WARP_TIMES): every range a warp streams is logged as (start ns, end ns, band, lo, hi, stolen) into a
+// device buffer set with sf_debug_warp_times -- where a launch's time goes when its warps are not equally loaded
+struct WarpTimeRec { unsigned long long t0, t1; int band, lo, hi, stolen; };
+__device__ WarpTimeRec *g_warp_times = nullptr;
+__device__ unsigned int g_warp_times_n = 0, g_warp_times_cap = 0;
+__device__ __forceinline__ void log_range(unsigned long long t0, int band, int lo, int hi, int stolen)
+{
+    if ((threadIdx.x & 31) == 0 && g_warp_times != nullptr) {
+        const unsigned k = atomicAdd(&g_warp_times_n, 1u);
+        if (k < g_warp_times_cap) g_warp_times[k] = WarpTimeRec{t0, globaltimer_ns(), band, lo, hi, stolen};
+    }
+}
+#endif
+
 template <int T, int MODE, int VAR>
 __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
 {
@@ -886,16 +923,30 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     const int nitems = A.nbands * A.nchunks;
     if (item >= nitems) return;
     const int band = item % A.nbands, chunk = item / A.nbands;
-    const int a_lo = A.a_lo + chunk * A.chunk_rows;
-    const int a_hi = min(a_lo + A.chunk_rows, A.a_hi);
+    int a_lo, a_hi;
+    chunk_range(A, chunk, a_lo, a_hi);
     if constexpr (!STEALS) {
         if (a_lo >= a_hi) return;
+#ifdef SF_WARP_TIMES
+        const unsigned long long t0 = globaltimer_ns();
+#endif
         stream_rows<T, MODE, TMA, false, false, RB, SRC>(A, ring, lane, warp, band, a_lo, a_hi, nullptr);
+#ifdef SF_WARP_TIMES
+        log_range(t0, band, a_lo, a_hi, 0);
+#endif
     } else {
         int b = band, lo = a_lo, hi = a_hi;
         steal_publish(A.steal, b, lo, hi);
+        [[maybe_unused]] int stolen = 0;
         for (;;) {
+#ifdef SF_WARP_TIMES
+            const unsigned long long t0 = globaltimer_ns();
+#endif
             if (lo < hi) stream_rows<T, MODE, false, false, true, false, SRC>(A, ring, lane, warp, b, lo, hi, nullptr);
+#ifdef SF_WARP_TIMES
+            log_range(t0, b, lo, hi, stolen);      // (hi = the range as taken; the owner may have stopped earlier)
+            stolen = 1;
+#endif
             if (!steal_next(A.steal, nitems, A.chunk_rows, A.a_lo, A.a_hi, b, lo, hi)) break;
         }
     }
@@ -1159,6 +1210,16 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     if (chunk > rows) chunk = max(rows, 1);
     A.chunk_rows = chunk;
     A.nchunks = rows > 0 ? (rows + chunk - 1) / chunk : 0;
+    A.skew = 0u;
+    if (L.wave_skew_pct > 0 && L.chunk_rows <= 0 && n_strip_items == 0 && A.nchunks > 0) {
+        // one chunk row of CTAs per `nbands / WPC` CTAs; the skew only makes sense when the grid really is one full wave
+        const bool heavy3 = (L.mode == MODE_STRICT || L.mode == MODE_IEEE || L.mode == MODE_PRESSURE) && L.sweeps >= 6;
+        const int W = heavy3 ? 3 : 4, slots = sm_count * W * WPC, items = A.nbands * A.nchunks;
+        const int h = chunk * L.wave_skew_pct / 200;      // adjacent waves differ by 2h rows = wave_skew_pct % of a chunk
+        if (A.nchunks % W == 0 && items <= slots && items * 10 >= slots * 9 && h > 0 && h < 0x10000 && A.nchunks / W < 0x1000 &&
+            chunk - h * (W - 1) >= 2 * L.sweeps)
+            A.skew = (unsigned)h | ((unsigned)(A.nchunks / W) << 16) | ((unsigned)W << 28);
+    }
     const int items = max(n_strip_items, A.nbands * A.nchunks);   // strip warps go on to an interior item
     A.steal = (L.steal != nullptr && L.mode == MODE_STRICT && L.staging != 1 && A.nbands * A.nchunks <= L.steal_capacity &&
                A.nbands * A.nchunks > 1) ? L.steal : nullptr;
@@ -1214,3 +1275,19 @@ cudaError_t launch_jacobi_generic(const Geom &g, const JacobiLaunch &L, cudaStre
 }
 
 }  // namespace sf
+
+#ifdef SF_WARP_TIMES
+extern "C" int sf_debug_warp_times(void *dev_buffer, unsigned int capacity_records)
+{
+    sf::WarpTimeRec *p = static_cast<sf::WarpTimeRec *>(dev_buffer);
+    unsigned int zero = 0;
+    if (cudaMemcpyToSymbol(sf::g_warp_times, &p, sizeof(p)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(sf::g_warp_times_cap, &capacity_records, sizeof(unsigned int)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(sf::g_warp_times_n, &zero, sizeof(unsigned int)) != cudaSuccess) return -1;
+    return 0;
+}
+extern "C" int sf_debug_warp_times_count(unsigned int *n)
+{
+    return cudaMemcpyFromSymbol(n, sf::g_warp_times_n, sizeof(unsigned int)) == cudaSuccess ? 0 : -1;
+}
+#endif

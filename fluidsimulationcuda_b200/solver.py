@@ -36,6 +36,7 @@ SF_OPT_SOLVER = 11
 SF_OPT_SOR_OMEGA_MILLI = 12
 SF_OPT_RBGS_BLOCKED = 13
 SF_OPT_FUSE_SOURCES = 14
+SF_OPT_WAVE_SKEW = 15
 STRICT, FAST = 0, 1
 SOLVER_JACOBI, SOLVER_RBGS = 0, 1    # SF_OPT_SOLVER: the reference's Jacobi (default) / opt-in red-black Gauss-Seidel (SOR)
 

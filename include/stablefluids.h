@@ -102,7 +102,13 @@ enum {
      * the rows stream in and kept in a context-owned field, one pass over x and s less per solve.  The fields the
      * reference's step functions leave behind (u, v, dens and the clobbered *_prev buffers) are unchanged, bit for bit.
      * 0 = a separate add_source kernel, as sf_add_source + sf_diffuse would run it.  Full-grid contexts. */
-    SF_OPT_FUSE_SOURCES = 14
+    SF_OPT_FUSE_SOURCES = 14,
+    /* Temporally blocked Jacobi launches are one full wave of warps, each with one chunk of rows.  The warp schedulers favour
+     * the CTAs an SM received first, so with equal chunks those warps finish long before the last ones.  value = p (0..60):
+     * the chunks of each successive third (quarter) of the grid's CTAs are p percent of a chunk shorter than those of the
+     * one before; the total is unchanged, and so are the results (temporal blocking does not depend on where the chunks
+     * are cut).  0 = equal chunks. */
+    SF_OPT_WAVE_SKEW = 15
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 enum { SF_SOLVER_JACOBI = 0, SF_SOLVER_RBGS = 1 };
