@@ -39,6 +39,10 @@ int ensure_scratch(sf_context *c)
         SF_CUDA(c, cudaMalloc(&c->red_f, sizeof(float)));
         SF_CUDA(c, cudaMalloc(&c->red_d, sizeof(double)));
     }
+    if (!c->ticket) {
+        SF_CUDA(c, cudaMalloc(&c->ticket, 64));
+        SF_CUDA(c, cudaMemsetAsync(c->ticket, 0, 64, c->stream));
+    }
     return SF_OK;
 }
 
@@ -81,7 +85,7 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
     JacobiLaunch L;
     L.xin = xin; L.rhs = x0; L.xout = xout;
     L.rhs_out = rhs_out; L.src_dt = src_dt;
-    L.wave_skew_pct = c->wave_skew;
+    L.wave_skew = c->wave_skew; L.ticket = c->ticket;
     L.alpha = alpha; L.beta = beta; L.b = b; L.sweeps = sweeps;
     L.mode = arith_mode(c, alpha, beta);
     L.out_lo = out_lo; L.out_hi = out_hi;
@@ -391,6 +395,7 @@ int sf_destroy(sf_context *c)
     if (c->steal) cudaFree(c->steal);
     if (c->red_f) cudaFree(c->red_f);
     if (c->red_d) cudaFree(c->red_d);
+    if (c->ticket) cudaFree(c->ticket);
     for (auto &s : c->stage) if (s) cudaFree(s);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->h2d) cudaStreamDestroy(c->h2d);
@@ -432,7 +437,12 @@ int sf_set_option(sf_context *c, int option, int value)
         case SF_OPT_SOR_OMEGA_MILLI: SF_REQUIRE(c, value >= 1 && value <= 1999, "SOR omega in 1/1000: 1..1999"); c->omega_milli = value; break;
         case SF_OPT_RBGS_BLOCKED: c->rbgs_blocked = value ? 1 : 0; break;
         case SF_OPT_FUSE_SOURCES: c->fuse_sources = value ? 1 : 0; break;
-        case SF_OPT_WAVE_SKEW: SF_REQUIRE(c, value >= 0 && value <= 60, "wave skew: 0..60 percent of a chunk"); c->wave_skew = value; break;
+        case SF_OPT_WAVE_SKEW:
+            SF_REQUIRE(c, value == 0 || (value / 1000 >= 100 && value / 1000 <= 200 && value % 1000 >= 50 && value % 1000 <= value / 1000 &&
+                                         300 - value / 1000 - value % 1000 >= 20),
+                       "wave skew: 0, or p0 * 1000 + p1 with 200 >= p0 >= p1 >= 50 and p0 + p1 <= 280 (percent of the mean chunk)");
+            c->wave_skew = value;
+            break;
         case SF_OPT_STEAL_SCOPE: SF_REQUIRE(c, value == 0 || value == 1, "steal scope: 0 scalar fields / 1 every strict solve"); c->steal_scope = value; break;
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }

@@ -278,8 +278,11 @@ struct JacobiLaunch {
     // the launch forms raw + src_dt * xin on the fly and stores it to rhs_out (nullptr = off)
     float *rhs_out = nullptr;
     float src_dt = 0.0f;
-    // chunks of the CTAs an SM receives first get this many percent more rows than the next "wave" of CTAs (0 = equal chunks)
-    int wave_skew_pct = 0;
+    // unequal chunks for the three CTAs an SM holds (see chunk_range in sf_jacobi.cu): p0 * 1000 + p1 = rows of a chunk of the
+    // first / second third of the items in percent of the mean chunk (e.g. 135106); 0 = equal chunks.  `ticket`: a device
+    // word that is zero between launches (the context owns one).
+    int wave_skew = 0;
+    unsigned *ticket = nullptr;
 };
 // can launch_jacobi_stream fuse add_source into a launch of this depth and mode?  (the instantiations that exist)
 inline bool jacobi_src_fusion_built(int sweeps, int mode) { return sweeps >= 5 && sweeps <= 7 && (mode == MODE_STRICT || mode == MODE_IEEE); }

@@ -89,15 +89,20 @@ struct StreamArgs {
     // as the rows land and stored to rhs_out for the later launches of the solve; `rhs` points at the raw field
     float *rhs_out;
     float src_dt;
-    // wave skew (see chunk_range): bits 0..15 = h rows, bits 16..27 = chunks per wave, bits 28..31 = waves; 0 = uniform chunks
-    unsigned skew;
+    // age-ordered work items with unequal chunks (see chunk_range); ticket == nullptr: items by blockIdx, equal chunks
+    unsigned *ticket;    // device word, zero between launches: CTAs draw their item in the order they start
+    unsigned skew;       // rows of a chunk of the 1st third of the items | rows of a chunk of the 2nd third << 16 (0 = equal chunks)
+    unsigned skew_cpw;   // chunks per third
 };
-// Output rows of chunk `chunk`.  All warps of a launch are resident at once (one wave of CTAs, W = 3 or 4 per SM), but they do
-// not finish together: the warp schedulers favour the oldest warp, i.e. the CTAs the SM received first.  With equal chunks
-// the first third of the grid's CTAs finished a T = 7 launch after ~150 us and the last third after ~235 us
-// (tools/warp_times.py, profiles/r02/), and the schedulers idle more and more in between.  CTA i holds chunk i / (CTAs per
-// chunk row), so the chunks of the w-th "wave" of CTAs (chunks w * cpw .. (w+1) * cpw - 1) get chunk_rows + h * (W-1-2w) rows:
-// older warps take more rows, the sum is unchanged.
+// Output rows of chunk `chunk`.  All warps of a launch are resident at once (one wave of CTAs, three per SM at T >= 6), but
+// they do not finish together: a warp scheduler favours its oldest warp.  With equal chunks of 342 rows (G = 8192) the warps
+// of the CTA an SM received first ran at 2.27 rows/us, those of the second at 1.78 and those of the third at ~1.0 while all
+// three were resident, a T = 7 launch took 230 us, and a lone warp cannot use a scheduler's issue slots (2.2 rows/us against
+// 5.05 for three): the last third of the launch runs at a fraction of the machine (tools/warp_times.py, profiles/r02/).
+// So (i) CTAs draw their work item from a ticket counter in the order they START -- blockIdx order is not start order for
+// a few percent of the CTAs, and those would become the critical path -- and (ii) the chunks of the first / second / last
+// third of the items get rows in proportion to those rates; the total is unchanged, and so is every bit of the result
+// (temporal blocking does not depend on where the chunks are cut).
 __device__ __forceinline__ void chunk_range(const StreamArgs &A, int chunk, int &a_lo, int &a_hi)
 {
     if (A.skew == 0u) {
@@ -105,10 +110,10 @@ __device__ __forceinline__ void chunk_range(const StreamArgs &A, int chunk, int 
         a_hi = min(a_lo + A.chunk_rows, A.a_hi);
         return;
     }
-    const int h = (int)(A.skew & 0xffffu), cpw = (int)((A.skew >> 16) & 0xfffu), W = (int)(A.skew >> 28);
+    const int r0 = (int)(A.skew & 0xffffu), r1 = (int)(A.skew >> 16), r2 = 3 * A.chunk_rows - r0 - r1, cpw = (int)A.skew_cpw;
     const int w = chunk / cpw, j = chunk - w * cpw;
-    const int rows = A.chunk_rows + h * (W - 1 - 2 * w);
-    a_lo = A.a_lo + cpw * (w * A.chunk_rows + h * (w * (W - w))) + j * rows;
+    const int rows = w == 0 ? r0 : (w == 1 ? r1 : r2);
+    a_lo = A.a_lo + cpw * (w == 0 ? 0 : (w == 1 ? r0 : r0 + r1)) + j * rows;
     a_hi = min(a_lo + rows, A.a_hi);
     a_lo = min(a_lo, A.a_hi);
 }
@@ -911,8 +916,19 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     constexpr bool SRC = (VAR == 6 || VAR == 7);       // fused add_source (first launch of a solve), without / with work stealing
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.
-    const int item = blockIdx.x * WPC + warp;
+    // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.  CTAs take their items in
+    // the order they start (see chunk_range); the CTA that draws the last ticket re-arms the counter for the next launch.
+    unsigned cta = blockIdx.x;
+    if (A.ticket != nullptr) {
+        __shared__ unsigned s_ticket;
+        if (threadIdx.x == 0) {
+            s_ticket = atomicAdd(A.ticket, 1u);
+            if (s_ticket == gridDim.x - 1) *A.ticket = 0u;
+        }
+        __syncthreads();
+        cta = s_ticket;
+    }
+    const int item = (int)cta * WPC + warp;
     if constexpr (STRIPS) {
         // the first warps of the grid compute a boundary strip BEFORE their interior item: the strips are
         // scheduled first and travel while everybody computes, and the grid still is one wave of warps
@@ -1210,15 +1226,19 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
     if (chunk > rows) chunk = max(rows, 1);
     A.chunk_rows = chunk;
     A.nchunks = rows > 0 ? (rows + chunk - 1) / chunk : 0;
-    A.skew = 0u;
-    if (L.wave_skew_pct > 0 && L.chunk_rows <= 0 && n_strip_items == 0 && A.nchunks > 0) {
-        // one chunk row of CTAs per `nbands / WPC` CTAs; the skew only makes sense when the grid really is one full wave
+    A.skew = 0u; A.skew_cpw = 0u; A.ticket = nullptr;
+    if (L.wave_skew > 0 && L.ticket != nullptr && L.chunk_rows <= 0 && n_strip_items == 0 && A.nchunks > 0) {
+        // three CTAs per SM (min_ctas<T, MODE>() == 3) and a grid that really is one full wave: thirds of the items = the
+        // first / second / third CTA of every SM
         const bool heavy3 = (L.mode == MODE_STRICT || L.mode == MODE_IEEE || L.mode == MODE_PRESSURE) && L.sweeps >= 6;
-        const int W = heavy3 ? 3 : 4, slots = sm_count * W * WPC, items = A.nbands * A.nchunks;
-        const int h = chunk * L.wave_skew_pct / 200;      // adjacent waves differ by 2h rows = wave_skew_pct % of a chunk
-        if (A.nchunks % W == 0 && items <= slots && items * 10 >= slots * 9 && h > 0 && h < 0x10000 && A.nchunks / W < 0x1000 &&
-            chunk - h * (W - 1) >= 2 * L.sweeps)
-            A.skew = (unsigned)h | ((unsigned)(A.nchunks / W) << 16) | ((unsigned)W << 28);
+        const int slots = sm_count * 3 * WPC, items = A.nbands * A.nchunks;
+        const int r0 = chunk * (L.wave_skew / 1000) / 100, r1 = chunk * (L.wave_skew % 1000) / 100, r2 = 3 * chunk - r0 - r1;
+        if (heavy3 && A.nchunks % 3 == 0 && items <= slots && items * 10 >= slots * 9 && r0 < 0x10000 && r1 < 0x10000 &&
+            r0 >= r1 && r1 >= r2 && r2 >= 2 * L.sweeps) {
+            A.skew = (unsigned)r0 | ((unsigned)r1 << 16);
+            A.skew_cpw = (unsigned)(A.nchunks / 3);
+            A.ticket = L.ticket;
+        }
     }
     const int items = max(n_strip_items, A.nbands * A.nchunks);   // strip warps go on to an interior item
     A.steal = (L.steal != nullptr && L.mode == MODE_STRICT && L.staging != 1 && A.nbands * A.nchunks <= L.steal_capacity &&

@@ -103,11 +103,12 @@ enum {
      * reference's step functions leave behind (u, v, dens and the clobbered *_prev buffers) are unchanged, bit for bit.
      * 0 = a separate add_source kernel, as sf_add_source + sf_diffuse would run it.  Full-grid contexts. */
     SF_OPT_FUSE_SOURCES = 14,
-    /* Temporally blocked Jacobi launches are one full wave of warps, each with one chunk of rows.  The warp schedulers favour
-     * the CTAs an SM received first, so with equal chunks those warps finish long before the last ones.  value = p (0..60):
-     * the chunks of each successive third (quarter) of the grid's CTAs are p percent of a chunk shorter than those of the
-     * one before; the total is unchanged, and so are the results (temporal blocking does not depend on where the chunks
-     * are cut).  0 = equal chunks. */
+    /* Temporally blocked Jacobi launches are one full wave of warps, each with one chunk of rows, three CTAs per SM at the
+     * default depth.  A warp scheduler favours its oldest warp, so with equal chunks the warps of the CTA an SM received
+     * first finish long before those of the third, and the tail of the launch runs at a fraction of the machine.
+     * value = p0 * 1000 + p1: CTAs draw their work item in the order they start, and the chunks of the first / second third
+     * of the items get p0 / p1 percent of the mean chunk's rows (the last third gets the rest), e.g. 135106.  Results are
+     * unchanged (temporal blocking does not depend on where the chunks are cut).  0 = equal chunks in blockIdx order. */
     SF_OPT_WAVE_SKEW = 15
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };

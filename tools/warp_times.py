@@ -7,6 +7,9 @@ import numpy as np, torch
 from fluidsimulationcuda_b200 import solver as SF
 G, K = 8192, 40
 s = SF.StableFluids(G - 2, use_graph=False)
+import os
+if os.environ.get("SF_SKEW"):
+    s.set_option(SF.SF_OPT_WAVE_SKEW, int(os.environ["SF_SKEW"]))
 lib = SF.load_library()
 f = [s.new_field() for _ in range(6)]
 s.init_synthetic(1, *f)
@@ -51,13 +54,19 @@ def capture(fn, what):
             for x in own:
                 byband.setdefault(int(x["band"]), []).append((int(x["t1"]) - int(x["t0"])) / 1e3)
             print("     own-range duration by band (max us):", " ".join(f"{b}:{max(v):.0f}" for b, v in sorted(byband.items())))
+            bychunk = {}
+            for x in own:
+                bychunk.setdefault(int(x["lo"]), []).append((int(x["t1"]) - int(x["t0"])) / 1e3)
+            print("     own-range duration by first row of the chunk (min/mean/max us):",
+                  " ".join(f"{lo}:{min(v):.0f}/{sum(v) / len(v):.0f}/{max(v):.0f}" for lo, v in sorted(bychunk.items())))
 
 import numpy as np
 f32 = np.float32
 def ab(c):
     a = f32(0.016) * f32(c); a = a * f32(G - 2); a = a * f32(G - 2); return float(a), float(f32(1) + f32(4) * a)
 s.init_sources(50, f[1], f[3], f[5])
-capture(lambda: s.dens_step(f[0], f[1], f[2], f[4], 0.1, 0.016, K), "dens_step (work-stealing variants)")
+if "--dens" in sys.argv:
+    capture(lambda: s.dens_step(f[0], f[1], f[2], f[4], 0.1, 0.016, K), "dens_step (work-stealing variants)")
 al, be = ab(0.0025)
 capture(lambda: s.diffuse(1, f[3], f[2], al, be, K), "viscosity solve of u (plain variant)")
 capture(lambda: s.diffuse(0, f[5], f[4], 1.0, 4.0, K), "pressure-like solve")
