@@ -916,19 +916,19 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     constexpr bool SRC = (VAR == 6 || VAR == 7);       // fused add_source (first launch of a solve), without / with work stealing
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.  CTAs take their items in
-    // the order they start (see chunk_range); the CTA that draws the last ticket re-arms the counter for the next launch.
-    unsigned cta = blockIdx.x;
+    // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.  warps take their items in
+    // the order they start (see chunk_range); the warp that draws the last ticket re-arms the counter for the next launch.
+    // (per warp, through a shuffle: the 48 KB of dynamic shared memory are all ring, and a static word would push the CTA
+    // over the default limit)
+    int item = blockIdx.x * WPC + warp;
     if (A.ticket != nullptr) {
-        __shared__ unsigned s_ticket;
-        if (threadIdx.x == 0) {
-            s_ticket = atomicAdd(A.ticket, 1u);
-            if (s_ticket == gridDim.x - 1) *A.ticket = 0u;
+        unsigned t = 0;
+        if (lane == 0) {
+            t = atomicAdd(A.ticket, 1u);
+            if (t == gridDim.x * WPC - 1) *A.ticket = 0u;
         }
-        __syncthreads();
-        cta = s_ticket;
+        item = (int)__shfl_sync(0xffffffffu, t, 0);
     }
-    const int item = (int)cta * WPC + warp;
     if constexpr (STRIPS) {
         // the first warps of the grid compute a boundary strip BEFORE their interior item: the strips are
         // scheduled first and travel while everybody computes, and the grid still is one wave of warps
