@@ -90,19 +90,18 @@ struct StreamArgs {
     float *rhs_out;
     float src_dt;
     // age-ordered work items with unequal chunks (see chunk_range); ticket == nullptr: items by blockIdx, equal chunks
-    unsigned *ticket;    // device word, zero between launches: CTAs draw their item in the order they start
+    unsigned *ticket;    // four device words, zero between launches: per-class item counters + arrivals (see the kernel)
     unsigned skew;       // rows of a chunk of the 1st third of the items | rows of a chunk of the 2nd third << 16 (0 = equal chunks)
     unsigned skew_cpw;   // chunks per third
 };
 // Output rows of chunk `chunk`.  All warps of a launch are resident at once (one wave of CTAs, three per SM at T >= 6), but
-// they do not finish together: a warp scheduler favours its oldest warp.  With equal chunks of 342 rows (G = 8192) the warps
-// of the CTA an SM received first ran at 2.27 rows/us, those of the second at 1.78 and those of the third at ~1.0 while all
-// three were resident, a T = 7 launch took 230 us, and a lone warp cannot use a scheduler's issue slots (2.2 rows/us against
-// 5.05 for three): the last third of the launch runs at a fraction of the machine (tools/warp_times.py, profiles/r02/).
-// So (i) CTAs draw their work item from a ticket counter in the order they START -- blockIdx order is not start order for
-// a few percent of the CTAs, and those would become the critical path -- and (ii) the chunks of the first / second / last
-// third of the items get rows in proportion to those rates; the total is unchanged, and so is every bit of the result
-// (temporal blocking does not depend on where the chunks are cut).
+// they do not finish together: a warp scheduler favours the warp in its lowest hardware slot.  With equal chunks of 342 rows
+// (G = 8192, strict T = 7) the warps of the three resident CTAs of an SM ran at about 2.4 / 1.9 / 1.2 rows per us while all
+// three were active and finished after 144 / 173 / 216 us; a lone warp cannot use a scheduler's issue slots (~2.6 rows/us
+// against ~5.4 for three), so the last third of the launch runs at a fraction of the machine (tools/warp_times.py).
+// So (i) every warp draws its work item according to the hardware slot it runs in (see the kernel) and (ii) the chunks of the
+// first / second / last third of the items get rows in proportion to the rates of the three slots classes; the total is
+// unchanged, and so is every bit of the result (temporal blocking does not depend on where the chunks are cut).
 __device__ __forceinline__ void chunk_range(const StreamArgs &A, int chunk, int &a_lo, int &a_hi)
 {
     if (A.skew == 0u) {
@@ -904,7 +903,10 @@ __device__ __forceinline__ void log_range(unsigned long long t0, int band, int l
 {
     if ((threadIdx.x & 31) == 0 && g_warp_times != nullptr) {
         const unsigned k = atomicAdd(&g_warp_times_n, 1u);
-        if (k < g_warp_times_cap) g_warp_times[k] = WarpTimeRec{t0, globaltimer_ns(), band, lo, hi, stolen};
+        unsigned smid, warpid;
+        asm volatile("mov.u32 %0, %%smid;\n" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;\n" : "=r"(warpid));
+        if (k < g_warp_times_cap) g_warp_times[k] = WarpTimeRec{t0, globaltimer_ns(), band, lo, hi, stolen | (int)(smid << 8) | (int)(warpid << 20)};
     }
 }
 #endif
@@ -918,16 +920,32 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.  warps take their items in
     // the order they start (see chunk_range); the warp that draws the last ticket re-arms the counter for the next launch.
-    // (per warp, through a shuffle: the 48 KB of dynamic shared memory are all ring, and a static word would push the CTA
-    // over the default limit)
     int item = blockIdx.x * WPC + warp;
     if (A.ticket != nullptr) {
-        unsigned t = 0;
+        // Unequal chunks by scheduling priority (see chunk_range).  What a warp scheduler favours is the warp in the LOWEST
+        // hardware slot: with three resident CTAs per SM, %warpid / WPC = 0, 1, 2 ran at 2.37 / 1.98 / 1.58 rows per us on
+        // equal chunks, cleanly separated (tools/warp_times.py --hw).  blockIdx does not tell the slot for a few percent of
+        // the CTAs, and neither does the order in which warps start -- so every warp reads its slot and draws its item
+        // from that class's counter (class c owns the c-th third of the items; a class that ever runs dry -- %warpid is
+        // only a hint -- falls through to the next one, so every item is drawn exactly once whatever the slots are).
+        // The warp that arrives last re-arms the counters for the next launch.
+        int it = 0;
         if (lane == 0) {
-            t = atomicAdd(A.ticket, 1u);
-            if (t == gridDim.x * WPC - 1) *A.ticket = 0u;
+            unsigned wid;
+            asm volatile("mov.u32 %0, %%warpid;\n" : "=r"(wid));
+            const unsigned ipc = A.skew_cpw * (unsigned)A.nbands;
+            const int cls = min((int)(wid / WPC), 2);
+            it = A.nbands * A.nchunks;                     // nothing left: retire
+            for (int k = 0; k < 3; ++k) {
+                const int c = cls + k < 3 ? cls + k : cls + k - 3;
+                const unsigned t = atomicAdd(A.ticket + c, 1u);
+                if (t < ipc) { it = c * (int)ipc + (int)t; break; }
+            }
+            if (atomicAdd(A.ticket + 3, 1u) == gridDim.x * WPC - 1) {
+                A.ticket[0] = 0u; A.ticket[1] = 0u; A.ticket[2] = 0u; A.ticket[3] = 0u;
+            }
         }
-        item = (int)__shfl_sync(0xffffffffu, t, 0);
+        item = __shfl_sync(0xffffffffu, it, 0);
     }
     if constexpr (STRIPS) {
         // the first warps of the grid compute a boundary strip BEFORE their interior item: the strips are

@@ -5,7 +5,7 @@ from fluidsimulationcuda_b200 import solver as SF
 G, K = 8192, 40
 f32 = np.float32
 al = f32(0.016) * f32(0.0025); al = al * f32(G - 2); al = al * f32(G - 2); be = f32(1) + f32(4) * al
-for pct in [int(a) for a in (sys.argv[1:] or ["0", "120104", "130106", "135106", "140108", "145110"])]:
+for pct in [int(a) for a in (sys.argv[1:] or ["0", "120102", "125102", "131103", "135104", "140105"])]:
     s = SF.StableFluids(G - 2)
     s.set_option(SF.SF_OPT_WAVE_SKEW, pct)
     f = [s.new_field() for _ in range(6)]

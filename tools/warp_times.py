@@ -27,6 +27,17 @@ def capture(fn, what):
     lib.sf_debug_warp_times(C.c_void_p(0), C.c_uint(0))
     r = np.frombuffer(buf.cpu().numpy().tobytes(), dtype=rec)[:min(n.value, cap)]
     r = np.sort(r, order="t0")
+    r = r.copy()
+    smid = (r["stolen"] >> 8) & 0xfff; warpid = (r["stolen"] >> 20) & 0xfff
+    r["stolen"] &= 0xff
+    if "--hw" in sys.argv:       # speed of a range against the hardware warp slot it ran in
+        speed = (r["hi"] - r["lo"]) / ((r["t1"] - r["t0"]).astype(np.float64) / 1e3)
+        own = r["stolen"] == 0
+        print(f"== {what}: rows/us by %warpid (all launches, own ranges):")
+        for wslot in sorted(set(warpid[own].tolist())):
+            m = own & (warpid == wslot)
+            print(f"   warpid {wslot:3d}: n={int(m.sum()):5d} rows/us min {speed[m].min():.2f} mean {speed[m].mean():.2f} max {speed[m].max():.2f}")
+        print("   SMs seen:", len(set(smid.tolist())), " ranges per SM min/max:", np.bincount(smid[own]).min(), np.bincount(smid[own]).max())
     # split into launches at gaps: a new launch starts when t0 jumps past every earlier t1
     launches, cur, hi = [], [], 0
     for x in r:
