@@ -72,7 +72,7 @@ struct sf_context {
     int staging = 0;
     float *scratch2 = nullptr;       // right-hand side of a solve whose add_source is fused into its first launch
     int fuse_sources = 1;            // SF_OPT_FUSE_SOURCES
-    int wave_skew = 0;               // SF_OPT_WAVE_SKEW (p0 * 1000 + p1)
+    int wave_skew = 131103;          // SF_OPT_WAVE_SKEW (p0 * 1000 + p1); swept in profiles/r02/s15_*_skew_sweep.txt
     unsigned *ticket = nullptr;      // device word: start-order tickets of the CTAs of a Jacobi launch
     float *scratch = nullptr;        // lin_solve ping-pong partner (inside the arena for peer slabs)
     bool scratch_in_arena = false;

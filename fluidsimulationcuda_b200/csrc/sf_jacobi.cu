@@ -135,6 +135,21 @@ __device__ __forceinline__ void st_relaxed_gpu(int *p, int v)
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
+// the hardware warp slot this warp runs in (%warpid: a hint -- it may change under preemption; used for load balance only)
+__device__ __forceinline__ unsigned hw_warp_slot()
+{
+    unsigned wid;
+    asm volatile("mov.u32 %0, %%warpid;\n" : "=r"(wid));
+    return wid;
+}
+
+__device__ __forceinline__ unsigned hw_sm_id()
+{
+    unsigned id;
+    asm volatile("mov.u32 %0, %%smid;\n" : "=r"(id));
+    return id;
+}
+
 // ---- fused strip exchange (peer-memory slabs) -----------------------------------------------------
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
 {
@@ -903,9 +918,7 @@ __device__ __forceinline__ void log_range(unsigned long long t0, int band, int l
 {
     if ((threadIdx.x & 31) == 0 && g_warp_times != nullptr) {
         const unsigned k = atomicAdd(&g_warp_times_n, 1u);
-        unsigned smid, warpid;
-        asm volatile("mov.u32 %0, %%smid;\n" : "=r"(smid));
-        asm volatile("mov.u32 %0, %%warpid;\n" : "=r"(warpid));
+        const unsigned smid = hw_sm_id(), warpid = hw_warp_slot();
         if (k < g_warp_times_cap) g_warp_times[k] = WarpTimeRec{t0, globaltimer_ns(), band, lo, hi, stolen | (int)(smid << 8) | (int)(warpid << 20)};
     }
 }
@@ -931,8 +944,7 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
         // The warp that arrives last re-arms the counters for the next launch.
         int it = 0;
         if (lane == 0) {
-            unsigned wid;
-            asm volatile("mov.u32 %0, %%warpid;\n" : "=r"(wid));
+            const unsigned wid = hw_warp_slot();
             const unsigned ipc = A.skew_cpw * (unsigned)A.nbands;
             const int cls = min((int)(wid / WPC), 2);
             it = A.nbands * A.nchunks;                     // nothing left: retire

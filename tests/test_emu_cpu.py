@@ -92,6 +92,28 @@ def test_fused_add_source_in_the_kernel_source(oracle):
             assert same(raw_in, raw)
 
 
+def test_slot_class_tickets_and_unequal_chunks_partition_the_rows(oracle):
+    """SF_OPT_WAVE_SKEW: warps draw their item from the counter of their hardware-slot class and the three thirds of the
+    items have chunks of different heights.  Whatever the slots are (the emulated ones put every fifth CTA out of order, so
+    classes run dry and fall through), every row must be produced exactly once, and the counters must be back at zero."""
+    L = emu("default")
+    L.emu_set_wave_skew.argtypes = [C.c_int]
+    rng = np.random.default_rng(21)
+    try:
+        for code in (131103, 150110, 120100):
+            L.emu_set_wave_skew(code)
+            for N, chunk, T, K in ((126, 14, 6, 12), (254, 28, 7, 14), (254, 42, 7, 7), (510, 85, 7, 14)):
+                G = N + 2
+                x = rng.uniform(-1, 1, (G, G)).astype(np.float32); x0 = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+                want = x.copy(); oracle.diffuse(N, 1, want, x0, 2683.2, 10733.8, K)
+                got = x.copy()
+                assert L.emu_lin_solve(N, 1, p(got), p(x0), 2683.2, 10733.8, K, T, 0, chunk, 0, 1.0) == 0
+                assert same(got, want), (code, N, chunk, T)
+                assert L.emu_ticket_words_nonzero() == 0
+    finally:
+        L.emu_set_wave_skew(0)
+
+
 def test_zero_row_shortcut_of_the_scalar_field_variants(oracle):
     """jacobi_stream_kernel<T, STRICT, 3 / 7> (scalar fields: dens_step's solve): groups whose last 2T+3 input rows were
     all-zero bits only store zeros.  Compactly supported fields with zero margins of every width around them, a blob that

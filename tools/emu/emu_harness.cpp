@@ -12,6 +12,8 @@
 namespace sf {
 namespace {
 float4 ring[WPC * (RING_X + RING_R) * 32 + 256];     // the kernel's `extern __shared__ float4 ring[]` (+ mbarrier words)
+int g_wave_skew = 0;                                  // emu_set_wave_skew: p0 * 1000 + p1, see chunk_range (0 = equal chunks)
+unsigned g_ticket[4] = {0, 0, 0, 0};
 bool g_steal_variant = false;                         // emu_set_steal_variant: strict launches run VAR 3 / 7 instead of 0 / 6
 
 template <int T, int MODE, int VAR>
@@ -100,6 +102,16 @@ int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mo
     A.nchunks = rows > 0 ? (rows + chunk - 1) / chunk : 0;
     const int items = A.nbands * A.nchunks;
     const int ctas = (items + WPC - 1) / WPC;
+    if (g_wave_skew > 0 && !rb && A.nchunks % 3 == 0) {
+        // as launch_jacobi_stream sets it up, minus the "one full wave of 148 SMs" condition (the emulated grid is whatever
+        // the problem needs): what is checked here is that the slot-class tickets and the unequal chunks still partition the rows
+        const int r0 = chunk * (g_wave_skew / 1000) / 100, r1 = chunk * (g_wave_skew % 1000) / 100, r2 = 3 * chunk - r0 - r1;
+        if (r0 >= r1 && r1 >= r2 && r2 >= 2 * sweeps) {
+            A.skew = (unsigned)r0 | ((unsigned)r1 << 16);
+            A.skew_cpw = (unsigned)(A.nchunks / 3);
+            A.ticket = g_ticket;
+        }
+    }
     if (rb) {
         if (mode == MODE_PRESSURE) return run_T<MODE_PRESSURE, 5>(sweeps, A, ctas);
         return run_T<MODE_STRICT, 5>(sweeps, A, ctas);
@@ -141,6 +153,8 @@ int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mo
 
 extern "C" {
 void emu_set_steal_variant(int on) { sf::g_steal_variant = on != 0; }
+void emu_set_wave_skew(int code) { sf::g_wave_skew = code; }
+int emu_ticket_words_nonzero() { return (sf::g_ticket[0] | sf::g_ticket[1] | sf::g_ticket[2] | sf::g_ticket[3]) != 0; }
 // lin_solve of csrc/sf_api.cu (Jacobi: plan_launches; red-black: three iterations per launch); result ends in x
 int emu_lin_solve(int N, int b, float *x, const float *x0, float alpha, float beta, int iters, int T, int zero_guess,
                   int chunk_rows, int rb, float omega)
