@@ -322,13 +322,11 @@ def reference_schedule(SF, torch, N, K, steps=50):
 def bind_to_gpu_numa_node(torch, local):
     """Pin this rank's host threads (and therefore the first-touch placement of the pinned host buffers it allocates next)
     to the NUMA node its GPU hangs off.  Returns a description for the JSON line; never fatal."""
+    bus = None
     try:
-        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        if bus is None:
-            import ctypes
-            buf = ctypes.create_string_buffer(32)
-            torch.cuda.cudart().cudaDeviceGetPCIBusId(buf, 32, local)
-            bus = buf.value.decode()
+        pr = torch.cuda.get_device_properties(local)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{int(pr.pci_domain_id):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
     except Exception:
         bus = None
     try:
