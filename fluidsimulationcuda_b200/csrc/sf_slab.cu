@@ -29,6 +29,9 @@
 // waiting (sticky), so a lost neighbour is an error report, never a hung GPU.
 #include <algorithm>
 
+#include <mutex>
+#include <vector>
+
 #include "sf_internal.h"
 
 namespace sf {
@@ -390,6 +393,11 @@ void slab_release(sf_context *c)
 
 using namespace sf;
 
+namespace {
+std::mutex g_arena_devices_mutex;
+std::vector<int> g_arena_devices;      // devices on which this process has created a slab arena (see sf_slab_connect_local)
+}  // namespace
+
 // =================================================================================================
 extern "C" {
 
@@ -407,6 +415,12 @@ int sf_slab_arena_create(sf_context *c, int nfields)
     const size_t off = arena_flags_offset(nfields, L.field_bytes);
     SF_CUDA(c, cudaMalloc(&L.base, off + 256));
     SF_CUDA(c, cudaMemset(L.base, 0, off + 256));
+    {
+        std::lock_guard<std::mutex> lock(g_arena_devices_mutex);
+        bool seen = false;
+        for (int d : g_arena_devices) seen = seen || d == c->device;
+        if (!seen) g_arena_devices.push_back(c->device);
+    }
     L.flags = reinterpret_cast<SlabFlags *>(L.base + off);
     c->scratch = reinterpret_cast<float *>(L.base + (size_t)nfields * L.field_bytes);
     c->scratch_in_arena = true;
@@ -493,6 +507,26 @@ int sf_slab_connect_local(sf_context *c, int dir, sf_context *nb)
         cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
         if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
         SF_CUDA(c, e);
+        // One process driving three or more devices: with peer access enabled between NEIGHBOURING slabs' devices only, the
+        // first step faulted (illegal address) as soon as one slab had two neighbours on two other devices; with access also
+        // enabled between the non-neighbouring devices the same run is bit-identical to the oracle (tools/
+        // peer_multi_dev_check.py, SF_ALL_PEERS=nbr / far).  No kernel of this library dereferences a non-neighbour's
+        // memory, and one process per GPU (CUDA IPC, neighbours only) runs at 4 and 8 GPUs; the cause on the in-process
+        // path is not identified, so every device that holds an arena of this process gets access to every other one.
+        std::vector<int> devs;
+        {
+            std::lock_guard<std::mutex> lock(g_arena_devices_mutex);
+            devs = g_arena_devices;
+        }
+        for (int a : devs)
+            for (int b : devs) {
+                if (a == b) continue;
+                int ok = 0;
+                if (cudaDeviceCanAccessPeer(&ok, a, b) != cudaSuccess || !ok) { (void)cudaGetLastError(); continue; }
+                DeviceGuard ga(a);
+                (void)cudaDeviceEnablePeerAccess(b, 0);
+                (void)cudaGetLastError();
+            }
     }
     return connect_common(c, dir, nb->link.base, false, nb->g.own_lo, nb->g.own_hi);
 }
