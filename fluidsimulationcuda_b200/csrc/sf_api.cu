@@ -171,7 +171,11 @@ int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, floa
     // of 8 sweeps were measured SLOWER, 9.42 vs 8.87 ms per step at G=8192 -- at depth 8 the pressure kernel
     // spills under its 128-register cap.)
     const bool odd_ok = stream_ok && zero_guess && c->pressure_plan != 0;
-    const std::vector<int> plan = plan_launches(iters, stream_ok ? default_sweeps(c) : 1, odd_ok);
+    int depth = stream_ok ? default_sweeps(c) : 1;
+    // SF_OPT_PRESSURE_PLAN = 2: the pressure kernel (alpha = 1, beta = 4) is built for 3 CTAs per SM since round 2 and no longer
+    // spills at depth 8 (154 registers), so K = 40 can run as 5 launches of 8 sweeps instead of 6 of 7,7,7,7,6,6
+    if (stream_ok && c->pressure_plan == 2 && c->sweeps_opt == 0 && alpha == 1.0f && beta == 4.0f) depth = 8;
+    const std::vector<int> plan = plan_launches(iters, depth, odd_ok);
     float *cur = x, *nxt = c->scratch;
     if (odd_ok && (plan.size() & 1)) { cur = c->scratch; nxt = x; }   // `cur` is not read by the first launch
     for (size_t k = 0; k < plan.size(); ++k) {
@@ -428,7 +432,7 @@ int sf_set_option(sf_context *c, int option, int value)
             SF_CUDA(c, cudaStreamSynchronize(c->stream));
             break;
         }
-        case SF_OPT_PRESSURE_PLAN: c->pressure_plan = value ? 1 : 0; break;
+        case SF_OPT_PRESSURE_PLAN: SF_REQUIRE(c, value >= 0 && value <= 2, "pressure plan: 0, 1 or 2"); c->pressure_plan = value; break;
         case SF_OPT_SOLVER:
             SF_REQUIRE(c, value == SF_SOLVER_JACOBI || value == SF_SOLVER_RBGS, "solver: 0 Jacobi (reference) / 1 red-black Gauss-Seidel");
             if (value == SF_SOLVER_RBGS && !is_full_grid(c)) return fail(c, SF_ERR_UNSUPPORTED, "SF_SOLVER_RBGS: full-grid contexts only (no slabs yet)");

@@ -80,7 +80,7 @@ struct sf_context {
     int steal_capacity = 0;
     int steal_opt = 30;              // SF_OPT_WORK_STEALING (percent; 0 = off)
     int steal_scope = 0;             // SF_OPT_STEAL_SCOPE
-    int pressure_plan = 1;           // SF_OPT_PRESSURE_PLAN
+    int pressure_plan = 2;           // SF_OPT_PRESSURE_PLAN (2: odd launch counts + depth 8 for the pressure solves)
     int solver = SF_SOLVER_JACOBI;   // SF_OPT_SOLVER
     int omega_milli = 1000;          // SF_OPT_SOR_OMEGA_MILLI
     int rbgs_blocked = 0;            // SF_OPT_RBGS_BLOCKED

@@ -297,13 +297,13 @@ def test_launch_counter_counts_kernels(SF):
     n0 = s.launch_count
     s.step(*f, VIS, DIFF, DT, 40)
     per_step = s.launch_count - n0
-    # 5 lin_solves of 6 launches (40 sweeps as 7,7,7,7,6,6; add_source rides in the first launch of the three solves
-    # that have one) + div(2) + grad(2) + advect(2)
-    assert per_step == 5 * 6 + 6, per_step
+    # 3 viscosity / diffusion solves of 6 launches (40 sweeps as 7,7,7,7,6,6; add_source rides in the first launch) + 2 pressure
+    # solves of 5 launches (8 sweeps each, from the implicit zero guess) + div(2) + grad(2) + advect(2)
+    assert per_step == 3 * 6 + 2 * 5 + 6, per_step
     s.set_option(SF.SF_OPT_FUSE_SOURCES, 0)
     n1 = s.launch_count
     s.step(*f, VIS, DIFF, DT, 40)
-    assert s.launch_count - n1 == 5 * 6 + 6 + 3        # three separate add_source kernels (u, v, dens)
+    assert s.launch_count - n1 == 3 * 6 + 2 * 5 + 6 + 3        # three separate add_source kernels (u, v, dens)
     s.set_option(SF.SF_OPT_FUSE_SOURCES, 1)
     n0 = s.launch_count
     s.step(*f, VIS, DIFF, DT, 40); s.step(*f, VIS, DIFF, DT, 40)   # captured + replayed
