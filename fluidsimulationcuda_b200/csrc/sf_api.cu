@@ -46,6 +46,23 @@ int ensure_scratch(sf_context *c)
     return SF_OK;
 }
 
+// SF_OPT_ADVECT_TILE = 1 is automatic: advect_tile_kernel counts the tiles whose traces fitted the TMA box and those that fell
+// back to gathers.  Where most tiles fall back (a velocity field whose back-traces scatter further than the box: the same
+// initial condition on a much finer grid, dt0 = dt * N) the plain gather kernel is the better choice, since it keeps twice the
+// warps in flight.  The counters are looked at when a step is about to be captured into a graph -- the one place where the
+// library synchronises anyway -- and the choice is frozen into that graph.
+int refresh_advect_policy(sf_context *c)
+{
+    if (c->advect_tile != 1 || !c->tile_stats) return SF_OK;
+    unsigned int now[2] = {0u, 0u};
+    SF_CUDA(c, cudaStreamSynchronize(c->stream));
+    SF_CUDA(c, cudaMemcpy(now, c->tile_stats, sizeof(now), cudaMemcpyDeviceToHost));
+    const unsigned int tma = now[0] - c->tile_seen[0], fallback = now[1] - c->tile_seen[1];
+    c->tile_seen[0] = now[0]; c->tile_seen[1] = now[1];
+    if (tma + fallback > 0u) c->advect_tile_live = (fallback <= tma);
+    return SF_OK;
+}
+
 int arith_mode(const sf_context *c, float alpha, float beta)
 {
     if (alpha == 1.0f && beta == 4.0f) return MODE_PRESSURE;   // exact identity, see jacobi_cell
@@ -250,7 +267,7 @@ int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const 
     int rc = source_lin_solve(c, 0, x0, x, dt, alpha, beta, iters);   // add_source(x, x0); SWAP; diffuse(0, x, x0): solves into the old x0
     c->steal_now = false;
     if (rc) return rc;
-    SF_CUDA(c, launch_advect(c->g, 0, x, x0, u, v, dt, c->work));   // SWAP; advect(0, x, x0, u, v)
+    SF_CUDA(c, launch_advect(c->g, 0, x, x0, u, v, dt, advect_tile_now(c), c->tile_stats, c->work));   // SWAP; advect(0, x, x0, u, v)
     ++c->launches;
     return SF_OK;
 }
@@ -287,7 +304,7 @@ int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, fl
 {
     int rc = enqueue_project(c, u0, v0, u, v, iters);                  // :213-223 (p in u, div in v)
     if (rc) return rc;
-    SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, c->work));   // :228-237
+    SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, advect_tile_now(c), c->tile_stats, c->work));   // :228-237
     ++c->launches;
     return enqueue_project(c, u, v, u0, v0, iters);                    // :238-240 (p in u0, div in v0)
 }
@@ -307,7 +324,7 @@ int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, fl
     if (rc) return rc;
     rc = enqueue_project(c, u0, v0, u, v, iters);                      // :213-223 (p in u, div in v)
     if (rc) return rc;
-    SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, c->work));   // :228-237
+    SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, advect_tile_now(c), c->tile_stats, c->work));   // :228-237
     ++c->launches;
     return enqueue_project(c, u, v, u0, v0, iters);                    // :238-240 (p in u0, div in v0)
 }
@@ -323,7 +340,8 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.iters = iters;
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
     k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan + 16 * c->solver +
-                32 * c->omega_milli + 65536 * c->rbgs_blocked + 131072 * c->fuse_sources + 262144 * c->wave_skew;
+                32 * c->omega_milli + 65536 * c->rbgs_blocked + 131072 * c->fuse_sources;
+    k.opts[5] = c->wave_skew; k.opts[6] = c->advect_tile;
     return k;
 }
 
@@ -363,6 +381,12 @@ int create_common(sf_context **out, int N, int device, void *stream, bool own_st
         c->stream = (cudaStream_t)stream;
     }
     c->work = c->stream;
+    // counters of the TMA-staged advect kernel (a context without them runs the gather kernels)
+    if (cudaMalloc(&c->tile_stats, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(c->tile_stats, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (c->tile_stats) cudaFree(c->tile_stats);
+        c->tile_stats = nullptr;
+    }
     *out = c;
     return SF_OK;
 }
@@ -400,6 +424,7 @@ int sf_destroy(sf_context *c)
     if (c->red_f) cudaFree(c->red_f);
     if (c->red_d) cudaFree(c->red_d);
     if (c->ticket) cudaFree(c->ticket);
+    if (c->tile_stats) cudaFree(c->tile_stats);
     for (auto &s : c->stage) if (s) cudaFree(s);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->h2d) cudaStreamDestroy(c->h2d);
@@ -441,6 +466,22 @@ int sf_set_option(sf_context *c, int option, int value)
         case SF_OPT_SOR_OMEGA_MILLI: SF_REQUIRE(c, value >= 1 && value <= 1999, "SOR omega in 1/1000: 1..1999"); c->omega_milli = value; break;
         case SF_OPT_RBGS_BLOCKED: c->rbgs_blocked = value ? 1 : 0; break;
         case SF_OPT_FUSE_SOURCES: c->fuse_sources = value ? 1 : 0; break;
+        case SF_OPT_ADVECT_TILE_COUNT:
+        case SF_OPT_ADVECT_FALLBACK_COUNT: {
+            SF_REQUIRE(c, value == 0, "advect tile counters: only 0 (reset) can be set");
+            DeviceGuard guard(c->device);
+            if (c->tile_stats) {
+                SF_CUDA(c, cudaStreamSynchronize(c->stream));
+                SF_CUDA(c, cudaMemset(c->tile_stats, 0, 2 * sizeof(unsigned int)));
+            }
+            c->tile_seen[0] = c->tile_seen[1] = 0u;
+            break;
+        }
+        case SF_OPT_ADVECT_TILE:
+            SF_REQUIRE(c, (value >= 0 && value <= 8) || (value >= 12 && value <= 18),
+                       "advect tile: 0 off / 1 automatic / 2..8 on, 32-row tiles with that many 8-row copies of shared memory per field / 12..18 on, 16-row tiles");
+            c->advect_tile = value; c->advect_tile_live = true;
+            break;
         case SF_OPT_WAVE_SKEW:
             SF_REQUIRE(c, value == 0 || (value / 1000 >= 100 && value / 1000 <= 200 && value % 1000 >= 50 && value % 1000 <= value / 1000 &&
                                          300 - value / 1000 - value % 1000 >= 20),
@@ -470,6 +511,16 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_SOR_OMEGA_MILLI: *value = c->omega_milli; break;
         case SF_OPT_RBGS_BLOCKED: *value = c->rbgs_blocked; break;
         case SF_OPT_FUSE_SOURCES: *value = c->fuse_sources; break;
+        case SF_OPT_ADVECT_TILE: *value = c->advect_tile; break;
+        case SF_OPT_ADVECT_TILE_COUNT:
+        case SF_OPT_ADVECT_FALLBACK_COUNT: {
+            DeviceGuard guard(c->device);
+            unsigned int st[2] = {0u, 0u};
+            if (c->tile_stats && (cudaStreamSynchronize(c->stream) != cudaSuccess ||
+                                  cudaMemcpy(st, c->tile_stats, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess)) return SF_ERR_CUDA;
+            *value = (int)st[option == SF_OPT_ADVECT_TILE_COUNT ? 0 : 1];
+            break;
+        }
         case SF_OPT_WAVE_SKEW: *value = c->wave_skew; break;
         case SF_OPT_STEAL_COUNT: {   // diagnostics: row ranges taken over by another warp so far (synchronises)
             *value = 0;
@@ -604,7 +655,19 @@ int sf_advect(sf_context *c, int b, float *d, const float *d0, const float *u, c
     DeviceGuard guard(c->device);
     c->link.barrier_valid = false;   // barriers collapse only within one call (see slab_barrier)
     if (is_linked_slab(c)) return slab_advect(c, b, d, d0, u, v, dt, true);
-    SF_CUDA(c, launch_advect(c->g, b, d, d0, u, v, dt, c->stream));
+    SF_CUDA(c, launch_advect(c->g, b, d, d0, u, v, dt, advect_tile_now(c), c->tile_stats, c->stream));
+    ++c->launches;
+    return SF_OK;
+}
+
+int sf_advect_velocity(sf_context *c, float *u, float *v, const float *u0, const float *v0, float dt)
+{
+    if (!c) return SF_ERR_INVALID;
+    SF_REQUIRE(c, u && v && u0 && v0 && u != v && u != u0 && u != v0 && v != u0 && v != v0 && u0 != v0,
+               "advect_velocity: null fields or an output aliases another field");
+    if (is_linked_slab(c)) return fail(c, SF_ERR_UNSUPPORTED, "advect_velocity on a connected slab: use sf_vel_step (it is one pass there too)");
+    DeviceGuard guard(c->device);
+    SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, advect_tile_now(c), c->tile_stats, c->stream));   // :228-237
     ++c->launches;
     return SF_OK;
 }

@@ -315,10 +315,12 @@ struct PushSegment {
 };
 cudaError_t launch_push_rows(const PushSegment *segs, int nsegs, cudaStream_t st);
 // advect whose gather may leave the slab: rows outside [own_lo, own_hi) are read from the neighbours
+// `tile` (everywhere below): 0 = gather from global memory, > 0 = source tile staged by the TMA unit (SF_OPT_ADVECT_TILE);
+// `tile_stats`: two device words that count the tiles served by the TMA box / by the gather fallback
 cudaError_t launch_advect_peer(const Geom &g, int b, float *d, const float *d0, const float *u, const float *v, float dt,
-                               PeerSrc d0p, PeerGeom pg, cudaStream_t st);
+                               PeerSrc d0p, PeerGeom pg, int tile, unsigned int *tile_stats, cudaStream_t st);
 cudaError_t launch_advect_uv_peer(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt,
-                                  PeerSrc u0p, PeerSrc v0p, PeerGeom pg, cudaStream_t st);
+                                  PeerSrc u0p, PeerSrc v0p, PeerGeom pg, int tile, unsigned int *tile_stats, cudaStream_t st);
 
 // force-load every kernel of the library (see preload_jacobi_kernels)
 void preload_jacobi_kernels();
@@ -327,11 +329,11 @@ void preload_stage_kernels();
 cudaError_t launch_set_bnd(const Geom &g, int b, float *x, cudaStream_t st);
 cudaError_t launch_add_source(const Geom &g, int nfields, float *const *x, const float *const *s, float dt,
                               cudaStream_t st);
-cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const float *u, const float *v, float dt,
-                          cudaStream_t st);
+cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const float *u, const float *v, float dt, int tile,
+                          unsigned int *tile_stats, cudaStream_t st);
 // both velocity components in one pass: d_u <- advect(b=1, u0), d_v <- advect(b=2, v0) by (u0, v0)
-cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt,
-                             cudaStream_t st);
+cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt, int tile,
+                             unsigned int *tile_stats, cudaStream_t st);
 cudaError_t launch_divergence(const Geom &g, const float *u, const float *v, float *p, float *div, int write_p,
                               cudaStream_t st);
 cudaError_t launch_last_project(const Geom &g, float *u, float *v, const float *p, cudaStream_t st);

@@ -18,7 +18,7 @@ struct GraphKey {   // laid out without padding so memcmp is a valid equality
     const void *p[6];
     float f[4];
     int iters;
-    int opts[5];
+    int opts[7];
     bool operator==(const GraphKey &o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 struct GraphEntry {
@@ -72,6 +72,10 @@ struct sf_context {
     int staging = 0;
     float *scratch2 = nullptr;       // right-hand side of a solve whose add_source is fused into its first launch
     int fuse_sources = 1;            // SF_OPT_FUSE_SOURCES
+    int advect_tile = 1;             // SF_OPT_ADVECT_TILE (1 = automatic: see refresh_advect_policy)
+    bool advect_tile_live = true;    // automatic mode: what the launches enqueued now use
+    unsigned int *tile_stats = nullptr;        // device: tiles served by the TMA box / by the gather fallback
+    unsigned int tile_seen[2] = {0u, 0u};      // their values when the policy last looked
     int wave_skew = 131103;          // SF_OPT_WAVE_SKEW (p0 * 1000 + p1); swept in profiles/r02/s15_*_skew_sweep.txt
     unsigned *ticket = nullptr;      // device word: start-order tickets of the CTAs of a Jacobi launch
     float *scratch = nullptr;        // lin_solve ping-pong partner (inside the arena for peer slabs)
@@ -160,6 +164,10 @@ void slab_release(sf_context *c);
 const StripArgs *slab_strip_args(const sf_context *c, const float *xout, int rows);   // device pointer, or nullptr
 
 // ---- CUDA graph cache ------------------------------------------------------------------------
+// what the advect launches enqueued next get as `tile`
+inline int advect_tile_now(const sf_context *c) { return c->advect_tile == 1 ? (c->advect_tile_live ? 1 : 0) : c->advect_tile; }
+int refresh_advect_policy(sf_context *c);
+
 template <class Body>
 int run_graphed(sf_context *c, const GraphKey &key, Body body)
 {
@@ -194,6 +202,7 @@ int run_graphed(sf_context *c, const GraphKey &key, Body body)
         c->graphs.push_back(GraphEntry{key, nullptr, nullptr, 0, c->tick});
         return body();
     }
+    if ((rc = refresh_advect_policy(c))) return rc;   // the first (direct) run has shown whether the advect tiles fit: freeze the choice
     // Capture on a private stream: the caller's stream may be the legacy default stream, which
     // cannot be captured.  The instantiated graph is then launched on the caller's stream.
     if (!c->cap_stream) SF_CUDA(c, cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));

@@ -272,7 +272,7 @@ int slab_advect(sf_context *c, int b, float *d, const float *d0, const float *u,
     int rc = peer_src(c, d0, s);
     if (rc) return rc;
     if ((rc = slab_barrier(c, c->work, 0))) return rc;     // d0 is final on both neighbours
-    SF_CUDA(c, launch_advect_peer(c->g, b, d, d0, u, v, dt, s, peer_geom(c), c->work));
+    SF_CUDA(c, launch_advect_peer(c->g, b, d, d0, u, v, dt, s, peer_geom(c), advect_tile_now(c), c->tile_stats, c->work));
     ++c->launches;
     if (trailing_barrier) rc = slab_barrier(c, c->work, 0);   // neighbours are done reading my d0
     return rc;
@@ -298,7 +298,7 @@ int slab_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float
     PeerSrc su, sv;
     if ((rc = peer_src(c, u0, su)) || (rc = peer_src(c, v0, sv))) return rc;
     if ((rc = slab_barrier(c, c->work, 0))) return rc;                 // u0, v0 final everywhere
-    SF_CUDA(c, launch_advect_uv_peer(c->g, u, v, u0, v0, dt, su, sv, peer_geom(c), c->work));
+    SF_CUDA(c, launch_advect_uv_peer(c->g, u, v, u0, v0, dt, su, sv, peer_geom(c), advect_tile_now(c), c->tile_stats, c->work));
     ++c->launches;
     // the exchange's first barrier also tells the neighbours that this slab is done reading their u0, v0
     if ((rc = slab_exchange(c, {HaloSpec{u, 1}, HaloSpec{v, 1}}))) return rc;

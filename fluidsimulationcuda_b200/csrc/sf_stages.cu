@@ -5,6 +5,8 @@
 // :143-158 (computeDivergenceAndPressure), :161-173 (lastProject), :244-271 (initial condition).
 // All arithmetic uses __f*_rn intrinsics so nvcc cannot contract mul+add into FMA: results are
 // bit-identical to the reference's sequential build.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is looked up at run time, the library does not link libcuda)
+
 #include <initializer_list>
 
 #include "sf_common.cuh"
@@ -392,17 +394,27 @@ __global__ void __launch_bounds__(256) last_project4_kernel(float *__restrict__ 
     store_row4_walls(v, g, row, c, vv, 1.0f, -1.0f);   // set_bnd(2, v)
 }
 
-// one back-trace + bilinear gather (FluidSequential.c:114-137); NF source fields share the trace
-template <int NF>
-__device__ __forceinline__ void advect_cell(const float *__restrict__ srcA, const float *__restrict__ srcB, const Geom &g,
-                                            int row, int col, float uu, float vv, float dt0, float hiC, float &oA, float &oB)
+// the back-trace of one cell (FluidSequential.c:114-124): position clamped to [0.5, N + 0.5] in both directions
+__device__ __forceinline__ void trace_back(int row, int col, float uu, float vv, float dt0, float hiC, float &px, float &py)
 {
-    float px = __fsub_rn((float)col, __fmul_rn(dt0, uu));
-    float py = __fsub_rn((float)row, __fmul_rn(dt0, vv));
+    px = __fsub_rn((float)col, __fmul_rn(dt0, uu));
+    py = __fsub_rn((float)row, __fmul_rn(dt0, vv));
     if (px < 0.5f) px = 0.5f;
     if (px > hiC) px = hiC;
     if (py < 0.5f) py = 0.5f;
     if (py > hiC) py = hiC;
+}
+// the interpolation of :125-137 from the four source cells (a10 = next row, a01 = next column)
+__device__ __forceinline__ float bilinear4(float a00, float a10, float a01, float a11, float wx0, float wx1, float wy0, float wy1)
+{
+    return __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
+                     __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
+}
+// bilinear gather at a traced position from global memory; NF source fields share the trace
+template <int NF>
+__device__ __forceinline__ void gather_global(const float *__restrict__ srcA, const float *__restrict__ srcB, const Geom &g,
+                                              float px, float py, float &oA, float &oB)
+{
     const int c0 = (int)px, r0 = (int)py;
     const float wx1 = __fsub_rn(px, (float)c0), wx0 = __fsub_rn(1.0f, wx1);
     const float wy1 = __fsub_rn(py, (float)r0), wy0 = __fsub_rn(1.0f, wy1);
@@ -411,16 +423,18 @@ __device__ __forceinline__ void advect_cell(const float *__restrict__ srcA, cons
     // too few -- slab.SlabSolver verifies the reach afterwards and raises) reads the nearest stored rows, never outside the array
     const int rs = min(max(r0, g.row_base), g.row_base + g.rows - 2);
     const size_t j = (size_t)(rs - g.row_base) * G + c0;
-    {
-        const float a00 = __ldg(srcA + j), a10 = __ldg(srcA + j + G), a01 = __ldg(srcA + j + 1), a11 = __ldg(srcA + j + G + 1);
-        oA = __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
-                       __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
-    }
-    if (NF == 2) {
-        const float a00 = __ldg(srcB + j), a10 = __ldg(srcB + j + G), a01 = __ldg(srcB + j + 1), a11 = __ldg(srcB + j + G + 1);
-        oB = __fadd_rn(__fmul_rn(wx0, __fadd_rn(__fmul_rn(wy0, a00), __fmul_rn(wy1, a10))),
-                       __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
-    }
+    oA = bilinear4(__ldg(srcA + j), __ldg(srcA + j + G), __ldg(srcA + j + 1), __ldg(srcA + j + G + 1), wx0, wx1, wy0, wy1);
+    if (NF == 2)
+        oB = bilinear4(__ldg(srcB + j), __ldg(srcB + j + G), __ldg(srcB + j + 1), __ldg(srcB + j + G + 1), wx0, wx1, wy0, wy1);
+}
+// one back-trace + bilinear gather (FluidSequential.c:114-137)
+template <int NF>
+__device__ __forceinline__ void advect_cell(const float *__restrict__ srcA, const float *__restrict__ srcB, const Geom &g,
+                                            int row, int col, float uu, float vv, float dt0, float hiC, float &oA, float &oB)
+{
+    float px, py;
+    trace_back(row, col, uu, vv, dt0, hiC, px, py);
+    gather_global<NF>(srcA, srcB, g, px, py, oA, oB);
 }
 
 // ---- advect on a peer-memory slab ---------------------------------------------------------------
@@ -456,15 +470,9 @@ __device__ __forceinline__ float bilinear(const float *p0, const float *p1, floa
                      __fmul_rn(wx1, __fadd_rn(__fmul_rn(wy0, a01), __fmul_rn(wy1, a11))));
 }
 template <int NF>
-__device__ __forceinline__ void advect_cell_peer(const PeerView &sA, const PeerView &sB, const Geom &g, const PeerGeom &pg,
-                                                 int row, int col, float uu, float vv, float dt0, float hiC, float &oA, float &oB)
+__device__ __forceinline__ void gather_peer(const PeerView &sA, const PeerView &sB, const Geom &g, const PeerGeom &pg,
+                                            float px, float py, float &oA, float &oB)
 {
-    float px = __fsub_rn((float)col, __fmul_rn(dt0, uu));
-    float py = __fsub_rn((float)row, __fmul_rn(dt0, vv));
-    if (px < 0.5f) px = 0.5f;
-    if (px > hiC) px = hiC;
-    if (py < 0.5f) py = 0.5f;
-    if (py > hiC) py = hiC;
     const int c0 = (int)px, r0 = (int)py;
     const float wx1 = __fsub_rn(px, (float)c0), wx0 = __fsub_rn(1.0f, wx1);
     const float wy1 = __fsub_rn(py, (float)r0), wy0 = __fsub_rn(1.0f, wy1);
@@ -480,6 +488,60 @@ __device__ __forceinline__ void advect_cell_peer(const PeerView &sA, const PeerV
     const int w0 = peer_row(g, pg, r0, off0), w1 = peer_row(g, pg, r0 + 1, off1);
     oA = bilinear(peer_base(sA, w0) + off0 + c0, peer_base(sA, w1) + off1 + c0, wx0, wx1, wy0, wy1);
     if (NF == 2) oB = bilinear(peer_base(sB, w0) + off0 + c0, peer_base(sB, w1) + off1 + c0, wx0, wx1, wy0, wy1);
+}
+template <int NF>
+__device__ __forceinline__ void advect_cell_peer(const PeerView &sA, const PeerView &sB, const Geom &g, const PeerGeom &pg,
+                                                 int row, int col, float uu, float vv, float dt0, float hiC, float &oA, float &oB)
+{
+    float px, py;
+    trace_back(row, col, uu, vv, dt0, hiC, px, py);
+    gather_peer<NF>(sA, sB, g, pg, px, py, oA, oB);
+}
+
+// store one row's four lane-strided cells per field, with set_bnd fused (see advect_lanes_kernel)
+template <int NF>
+__device__ __forceinline__ void store_lanes_row(float *__restrict__ dA, float *__restrict__ dB, const Geom &g, int row, int seg,
+                                                int lane, float (&oA)[4], float (&oB)[4], int bA)
+{
+    const size_t G = (size_t)g.G;
+    const size_t rowoff = (size_t)(row - g.row_base) * G;
+    const bool top = (row == 1) && (g.own_lo == 0), bot = (row == g.N) && (g.own_hi == g.G);
+    if (seg > 0 && seg + 128 < g.G && !(top | bot)) {
+        // warp-uniform fast path (all but the first / last segment of a row and the two rows next to a wall row):
+        // no wall column, no idle lane, no wall row -- four coalesced stores per field
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dA[rowoff + seg + 32 * k + lane] = oA[k];
+            if (NF == 2) dB[rowoff + seg + 32 * k + lane] = oB[k];
+        }
+        return;
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        float *o = f == 0 ? oA : oB;
+        float *dst = (f == 0 ? dA : dB) + rowoff;
+        const float sx = (f == 0 ? bA == 1 : false) ? -1.0f : 1.0f;     // field B of the pair is v: b = 2
+        const float sy = (f == 0 ? bA == 2 : true) ? -1.0f : 1.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = seg + 32 * k + lane;
+            const float nxt = __shfl_down_sync(0xffffffffu, o[k], 1), prv = __shfl_up_sync(0xffffffffu, o[k], 1);
+            const bool wallL = (col == 0), wallR = (col == g.G - 1);
+            float val = o[k];
+            if (wallL) val = __fmul_rn(sx, nxt);                       // x[row][0]   = sx * x[row][1]
+            if (wallR) val = __fmul_rn(sx, prv);                       // x[row][N+1] = sx * x[row][N]
+            if (col < g.G) {
+                dst[col] = val;
+                if (top | bot) {
+                    float w = __fmul_rn(sy, val);                      // wall row = sy * adjacent interior row
+                    if (wallL) w = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(sy, nxt), val));   // corner = .5 * (wall-row nbr + wall-col nbr)
+                    if (wallR) w = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(sy, prv), val));
+                    if (top) (dst - G)[col] = w;
+                    if (bot) (dst + G)[col] = w;
+                }
+            }
+        }
+    }
 }
 
 // ---- advect, lane-strided mapping (the product path for G % 4 == 0) ---------------------------------
@@ -522,44 +584,194 @@ __global__ void __launch_bounds__(256) advect_lanes_kernel(float *__restrict__ d
         if (PEER) advect_cell_peer<NF>(sA, sB, g, pg, row, cl, uu[k], vv[k], dt0, hiC, oA[k], oB[k]);
         else advect_cell<NF>(sA.loc, sB.loc, g, row, cl, uu[k], vv[k], dt0, hiC, oA[k], oB[k]);
     }
-    const bool top = (row == 1) && (g.own_lo == 0), bot = (row == g.N) && (g.own_hi == g.G);
-    if (seg > 0 && seg + 128 < g.G && !(top | bot)) {
-        // warp-uniform fast path (all but the first / last segment of a row and the two rows next to a wall row):
-        // no wall column, no idle lane, no wall row -- four coalesced stores per field
+    store_lanes_row<NF>(dA, dB, g, row, seg, lane, oA, oB, bA);
+}
+
+// [emu-cut-begin] (tools/emu compiles this file for the host up to here: the TMA kernel has no host twin; its arithmetic is
+// trace_back / bilinear4 / store_lanes_row above, which the emulated kernels share)
+// ---- advect with the source tile staged in shared memory by the TMA unit ---------------------------
+// The lane-strided kernel above moves the minimum DRAM traffic but is bound by the L1 tag stage: the 32 sources of one gather
+// instruction spread over 8-10 rows of the source field (12-17 sectors per request, profiles/r02/final_*_ncu_advect_lanes_*).
+// Here a CTA (8 warps) owns a tile of 8 * RPW rows x 128 columns (RPW = 2 or 4 rows per warp) and works in three steps:
+//  1. every thread loads u, v of its 4 * RPW cells (lane-strided as above), traces them back and the CTA reduces the bounding box
+//     of the traces (redux.sync + one shared-memory exchange);
+//  2. if the box fits (<= AT_BOXW columns, <= 8 * maxsub rows, inside the rows this slab stores / owns) ONE thread asks the TMA
+//     unit for it: 2-D tiled tensor copies (cp.async.bulk.tensor.2d, SASS UTMALDG) of AT_SUB rows x AT_BOXW columns each, only as
+//     many as the box is high, completing on an mbarrier; cells beyond the array come back as zeros and are never read;
+//  3. the gathers become shared-memory loads (pitch 160 words = 0 mod 32 banks: the lanes of a warp sit in consecutive columns
+//     +- their jitter, so conflicts only arise where neighbouring traces share a column but not a row).
+// A tile whose box does not fit (a velocity field rougher than ~+-12 cells of back-trace within a tile, or a trace that
+// leaves the slab in the PEER build) falls back to the global / peer gathers of the kernel above, as a whole CTA.
+// Same arithmetic per cell (trace_back, bilinear4), same bits.
+#ifndef SF_AT_MINB
+#define SF_AT_MINB 3      // CTAs per SM the register allocation allows
+#endif
+constexpr int AT_BOXW = 160;    // box width in cells
+constexpr int AT_SUB = 8;       // rows per tensor copy
+constexpr int AT_MAXSUB = 8;    // at most 64 source rows per field in shared memory
+
+
+__device__ __forceinline__ void at_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void at_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void at_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// one box of the tensor map's size whose first cell is (column c, stored row r) -> shared memory, completing on `bar`
+__device__ __forceinline__ void at_tensor_load(void *smem_dst, const CUtensorMap *tm, int c, int r, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(tm), "r"(c), "r"(r), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+// truncation of a clamped trace coordinate (0.5 <= x <= N + 0.5 < 2^23) without the conversion unit: adding 2^23 with rounding
+// toward zero leaves the integer part in the low mantissa bits.  `fl` = (float)(int)x and `i` = (int)x, exactly.
+__device__ __forceinline__ void trunc_pos(float x, float &fl, int &i)
+{
+    const float t = __fadd_rz(x, 8388608.0f);
+    i = __float_as_int(t) - 0x4B000000;
+    fl = __fsub_rn(t, 8388608.0f);
+}
+
+template <int NF, bool PEER, int RPW>
+__global__ void __launch_bounds__(256, (RPW == 2 ? 4 : SF_AT_MINB)) advect_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                          float *__restrict__ dA, float *__restrict__ dB, PeerView sA, PeerView sB,
+                                                          const float *__restrict__ u, const float *__restrict__ v, Geom g,
+                                                          PeerGeom pg, float dt0, int bA, int maxsub, unsigned int *__restrict__ stats)
+{
+    extern __shared__ unsigned char at_dyn[];
+    __shared__ int s_red[8][4];
+    __shared__ __align__(8) uint64_t s_bar;
+    // tensor copies need a 128-byte aligned destination
+    float *tile = reinterpret_cast<float *>(at_dyn + ((128u - ((unsigned)__cvta_generic_to_shared(at_dyn) & 127u)) & 127u));
+    int lo, hi;
+    interior_rows(g, lo, hi);
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int seg = blockIdx.x * 128;
+    const int row0 = blockIdx.y * (8 * RPW) + lo + RPW * w;
+    const size_t G = (size_t)g.G;
+    const float hiC = (float)g.N + 0.5f;
+    if (threadIdx.x == 0 && threadIdx.y == 0) at_mbar_init(&s_bar, 1);
+
+    // 1. traces of the thread's 4 * RPW cells (rows past the slab's last row and idle lanes mirror the last row / column: loads stay legal
+    //    and the box does not grow)
+    float px[RPW][4], py[RPW][4];
+    {
+        float uu[RPW][4], vv[RPW][4];
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            const size_t rowoff = (size_t)(min(row0 + rr, hi - 1) - g.row_base) * G;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int cl = min(seg + 32 * k + lane, g.G - 1);
+                uu[rr][k] = __ldg(u + rowoff + cl);
+                vv[rr][k] = __ldg(v + rowoff + cl);
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                trace_back(min(row0 + rr, hi - 1), min(seg + 32 * k + lane, g.G - 1), uu[rr][k], vv[rr][k], dt0, hiC, px[rr][k], py[rr][k]);
+    }
+    float fcmin = 3.0e38f, fcmax = 0.0f, frmin = 3.0e38f, frmax = 0.0f;
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            dA[rowoff + seg + 32 * k + lane] = oA[k];
-            if (NF == 2) dB[rowoff + seg + 32 * k + lane] = oB[k];
+            // the extremes of the positions give the extremes of their integer parts (truncation is monotone)
+            fcmin = fminf(fcmin, px[rr][k]); fcmax = fmaxf(fcmax, px[rr][k]);
+            frmin = fminf(frmin, py[rr][k]); frmax = fmaxf(frmax, py[rr][k]);
+            // a NaN velocity passes the clamps (and fminf / fmaxf): such a tile must not index shared memory -- it takes the
+            // gather path, where (int)NaN = 0 reads cell (0, 0) like the other kernels
+            if (!(px[rr][k] <= hiC) || !(py[rr][k] <= hiC)) frmax = 1.0e9f;
+        }
+    int cmin = (int)fcmin, cmax = (int)fcmax, rmin = (int)frmin, rmax = (int)frmax;
+    cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
+    rmin = __reduce_min_sync(0xffffffffu, rmin); rmax = __reduce_max_sync(0xffffffffu, rmax);
+    if (lane == 0) { s_red[w][0] = cmin; s_red[w][1] = cmax; s_red[w][2] = rmin; s_red[w][3] = rmax; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        cmin = min(cmin, s_red[i][0]); cmax = max(cmax, s_red[i][1]);
+        rmin = min(rmin, s_red[i][2]); rmax = max(rmax, s_red[i][3]);
+    }
+    // 2. does the box [rmin, rmax + 1] x [cmin, cmax + 1] fit?  (the TMA unit wants the first cell of a box 16-byte aligned:
+    //    an odd first column is an illegal instruction -- tools/micro/tma_probe.cu)
+    cmin &= ~3;
+    const int span_r = rmax + 2 - rmin;
+    bool fit = (cmax + 2 - cmin <= AT_BOXW) && (span_r <= AT_SUB * maxsub);
+    if (PEER) fit = fit && rmin >= g.own_lo && rmax + 1 < g.own_hi;                 // see gather_peer
+    else fit = fit && rmin >= g.row_base && rmax + 1 < g.row_base + g.rows;         // see gather_global
+    if (!fit) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) atomicAdd(stats + 1, 1u);      // CTAs served by the fallback
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int row = row0 + rr;
+            if (row >= hi) break;                                           // uniform per warp
+            float oA[4], oB[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                oA[k] = 0.0f; oB[k] = 0.0f;
+                if (PEER) gather_peer<NF>(sA, sB, g, pg, px[rr][k], py[rr][k], oA[k], oB[k]);
+                else gather_global<NF>(sA.loc, sB.loc, g, px[rr][k], py[rr][k], oA[k], oB[k]);
+            }
+            store_lanes_row<NF>(dA, dB, g, row, seg, lane, oA, oB, bA);
         }
         return;
     }
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        float *o = f == 0 ? oA : oB;
-        float *dst = (f == 0 ? dA : dB) + rowoff;
-        const float sx = (f == 0 ? bA == 1 : false) ? -1.0f : 1.0f;     // field B of the pair is v: b = 2
-        const float sy = (f == 0 ? bA == 2 : true) ? -1.0f : 1.0f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int col = seg + 32 * k + lane;
-            const float nxt = __shfl_down_sync(0xffffffffu, o[k], 1), prv = __shfl_up_sync(0xffffffffu, o[k], 1);
-            const bool wallL = (col == 0), wallR = (col == g.G - 1);
-            float val = o[k];
-            if (wallL) val = __fmul_rn(sx, nxt);                       // x[row][0]   = sx * x[row][1]
-            if (wallR) val = __fmul_rn(sx, prv);                       // x[row][N+1] = sx * x[row][N]
-            if (col < g.G) {
-                dst[col] = val;
-                if (top | bot) {
-                    float w = __fmul_rn(sy, val);                      // wall row = sy * adjacent interior row
-                    if (wallL) w = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(sy, nxt), val));   // corner = .5 * (wall-row nbr + wall-col nbr)
-                    if (wallR) w = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(sy, prv), val));
-                    if (top) (dst - G)[col] = w;
-                    if (bot) (dst + G)[col] = w;
-                }
-            }
+    const int nsub = (span_r + AT_SUB - 1) / AT_SUB;
+    float *tA = tile, *tB = tile + (size_t)maxsub * AT_SUB * AT_BOXW;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        atomicAdd(stats, 1u);          // CTAs served by the TMA box
+        at_mbar_expect_tx(&s_bar, (unsigned)(nsub * AT_SUB * AT_BOXW * sizeof(float) * NF));
+        for (int s = 0; s < nsub; ++s) {
+            at_tensor_load(tA + s * AT_SUB * AT_BOXW, &tmA, cmin, rmin - g.row_base + s * AT_SUB, &s_bar);
+            if (NF == 2) at_tensor_load(tB + s * AT_SUB * AT_BOXW, &tmB, cmin, rmin - g.row_base + s * AT_SUB, &s_bar);
         }
     }
+    at_mbar_wait(&s_bar, 0);
+    // 3. gathers from shared memory
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int row = row0 + rr;
+        if (row >= hi) break;                                               // uniform per warp
+        float oA[4], oB[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float x = px[rr][k], y = py[rr][k];
+            int c0, r0;
+            float fc, fr;
+            trunc_pos(x, fc, c0); trunc_pos(y, fr, r0);
+            const float wx1 = __fsub_rn(x, fc), wx0 = __fsub_rn(1.0f, wx1);
+            const float wy1 = __fsub_rn(y, fr), wy0 = __fsub_rn(1.0f, wy1);
+            const int j = (r0 - rmin) * AT_BOXW + (c0 - cmin);
+            oA[k] = bilinear4(tA[j], tA[j + AT_BOXW], tA[j + 1], tA[j + AT_BOXW + 1], wx0, wx1, wy0, wy1);
+            oB[k] = 0.0f;
+            if (NF == 2) oB[k] = bilinear4(tB[j], tB[j + AT_BOXW], tB[j + 1], tB[j + AT_BOXW + 1], wx0, wx1, wy0, wy1);
+        }
+        store_lanes_row<NF>(dA, dB, g, row, seg, lane, oA, oB, bA);
+    }
 }
+
+// [emu-cut-end]
 
 inline bool row4_ok(const Geom &g, std::initializer_list<const void *> ptrs)
 {
@@ -583,6 +795,89 @@ inline int interior_row_count(const Geom &g)
     return hi > lo ? hi - lo : 0;
 }
 
+// [emu-cut-begin]
+// ---- host side of advect_tile_kernel -----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn tensor_map_encoder()
+{
+    static const EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// the locally stored rows of one field as a 2-D tensor (columns fastest), box = AT_SUB rows x AT_BOXW columns, zeros out of bounds
+inline bool make_field_map(CUtensorMap *tm, const float *field, const Geom &g)
+{
+    const EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)g.G, (cuuint64_t)g.rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.G * sizeof(float)};
+    const cuuint32_t box[2] = {AT_BOXW, AT_SUB};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(field), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool tile_ok(const Geom &g, int tile, const unsigned int *stats, std::initializer_list<const void *> srcs)
+{
+    if (tile <= 0 || !stats || g.G % 4 != 0 || g.G < 2 * AT_BOXW || g.G > (1 << 22) || g.rows < AT_SUB * AT_MAXSUB) return false;
+    for (const void *p : srcs)
+        if ((uintptr_t)p % 16 != 0) return false;
+    return true;
+}
+inline size_t tile_smem(int nf, int maxsub) { return (size_t)nf * maxsub * AT_SUB * AT_BOXW * sizeof(float) + 128; }
+inline dim3 tile_grid(const Geom &g, int rows, int rpw) { return dim3((g.G + 127) / 128, (rows + 8 * rpw - 1) / (8 * rpw)); }
+// SF_OPT_ADVECT_TILE value -> rows per warp and 8-row copies of shared memory per field: 1 = the default (see below),
+// 2..8 = 32-row tiles with that many copies, 12..18 = 16-row tiles with (value - 10) copies
+#ifndef SF_AT_DEFAULT
+#define SF_AT_DEFAULT 15
+#endif
+inline void tile_shape(int tile, int &rpw, int &maxsub)
+{
+    if (tile < 2) tile = SF_AT_DEFAULT;
+    rpw = tile >= 10 ? 2 : 4;
+    maxsub = tile >= 10 ? tile - 10 : tile;
+    if (maxsub < 2) maxsub = 2;
+    if (maxsub > AT_MAXSUB) maxsub = AT_MAXSUB;
+}
+
+template <int NF, bool PEER, int RPW>
+cudaError_t launch_advect_tile_rpw(const CUtensorMap &tmA, const CUtensorMap &tmB, const Geom &g, int maxsub, float *dA, float *dB, PeerView sA,
+                                   PeerView sB, const float *u, const float *v, PeerGeom pg, float dt0, int bA, int rows,
+                                   unsigned int *stats, cudaStream_t st)
+{
+    // per device, and cheap: set on every launch (one process may drive several devices)
+    cudaError_t e = cudaFuncSetAttribute(advect_tile_kernel<NF, PEER, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(NF, AT_MAXSUB));
+    if (e != cudaSuccess) return e;
+    advect_tile_kernel<NF, PEER, RPW><<<tile_grid(g, rows, RPW), dim3(32, 8), tile_smem(NF, maxsub), st>>>(tmA, tmB, dA, dB, sA, sB, u, v, g, pg, dt0, bA,
+                                                                                                      maxsub, stats);
+    return cudaGetLastError();
+}
+template <int NF, bool PEER>
+cudaError_t launch_advect_tile(const Geom &g, int tile, float *dA, float *dB, PeerView sA, PeerView sB, const float *u, const float *v,
+                               PeerGeom pg, float dt0, int bA, int rows, unsigned int *stats, cudaStream_t st, bool &done)
+{
+    done = false;
+    CUtensorMap tmA, tmB;
+    if (!make_field_map(&tmA, sA.loc, g)) return cudaSuccess;       // no encoder (old driver): the caller takes the gather kernel
+    if (NF == 2) { if (!make_field_map(&tmB, sB.loc, g)) return cudaSuccess; }
+    else tmB = tmA;
+    int rpw, maxsub;
+    tile_shape(tile, rpw, maxsub);
+    done = true;
+    if (rpw == 2) return launch_advect_tile_rpw<NF, PEER, 2>(tmA, tmB, g, maxsub, dA, dB, sA, sB, u, v, pg, dt0, bA, rows, stats, st);
+    return launch_advect_tile_rpw<NF, PEER, 4>(tmA, tmB, g, maxsub, dA, dB, sA, sB, u, v, pg, dt0, bA, rows, stats, st);
+}
+
+// [emu-cut-end]
+
 }  // namespace
 
 void preload_stage_kernels()
@@ -592,6 +887,10 @@ void preload_stage_kernels()
     cudaFuncGetAttributes(&a, advect_kernel<1>); cudaFuncGetAttributes(&a, advect_kernel<2>);
     cudaFuncGetAttributes(&a, advect_lanes_kernel<1, false>); cudaFuncGetAttributes(&a, advect_lanes_kernel<2, false>);
     cudaFuncGetAttributes(&a, advect_lanes_kernel<1, true>); cudaFuncGetAttributes(&a, advect_lanes_kernel<2, true>);
+    cudaFuncGetAttributes(&a, advect_tile_kernel<1, false, 2>); cudaFuncGetAttributes(&a, advect_tile_kernel<2, false, 2>);
+    cudaFuncGetAttributes(&a, advect_tile_kernel<1, true, 2>); cudaFuncGetAttributes(&a, advect_tile_kernel<2, true, 2>);
+    cudaFuncGetAttributes(&a, advect_tile_kernel<1, false, 4>); cudaFuncGetAttributes(&a, advect_tile_kernel<2, false, 4>);
+    cudaFuncGetAttributes(&a, advect_tile_kernel<1, true, 4>); cudaFuncGetAttributes(&a, advect_tile_kernel<2, true, 4>);
     cudaFuncGetAttributes(&a, divergence_kernel); cudaFuncGetAttributes(&a, divergence4_kernel);
     cudaFuncGetAttributes(&a, last_project_kernel); cudaFuncGetAttributes(&a, last_project4_kernel);
     cudaFuncGetAttributes(&a, init_kernel); cudaFuncGetAttributes(&a, init4_kernel);
@@ -624,7 +923,8 @@ cudaError_t launch_add_source(const Geom &g, int nfields, float *const *x, const
     return cudaGetLastError();
 }
 
-cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const float *u, const float *v, float dt, cudaStream_t st)
+cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const float *u, const float *v, float dt, int tile,
+                          unsigned int *tile_stats, cudaStream_t st)
 {
     const int rows = interior_row_count(g);
     if (rows == 0) return cudaSuccess;
@@ -632,6 +932,11 @@ cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const
     const float dt0 = dt * (float)g.N;   // FluidSequential.c:111, rounded once in binary32
     if (g.G % 4 == 0) {
         const PeerView sA{d0, nullptr, nullptr};
+        if (tile_ok(g, tile, tile_stats, {d0})) {
+            bool done;
+            const cudaError_t e = launch_advect_tile<1, false>(g, tile, d, nullptr, sA, sA, u, v, PeerGeom(), dt0, b, rows, tile_stats, st, done);
+            if (done || e != cudaSuccess) return e;
+        }
         advect_lanes_kernel<1, false><<<lanes_grid(g, rows), dim3(32, 8), 0, st>>>(d, nullptr, sA, sA, u, v, g, PeerGeom(), dt0, b);
         return cudaGetLastError();
     }
@@ -639,7 +944,8 @@ cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const
     return cudaGetLastError();
 }
 
-cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt, cudaStream_t st)
+cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt, int tile,
+                             unsigned int *tile_stats, cudaStream_t st)
 {
     const int rows = interior_row_count(g);
     if (rows == 0) return cudaSuccess;
@@ -647,6 +953,11 @@ cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u
     const float dt0 = dt * (float)g.N;
     if (g.G % 4 == 0) {
         const PeerView sA{u0, nullptr, nullptr}, sB{v0, nullptr, nullptr};
+        if (tile_ok(g, tile, tile_stats, {u0, v0})) {
+            bool done;
+            const cudaError_t e = launch_advect_tile<2, false>(g, tile, du, dv, sA, sB, u0, v0, PeerGeom(), dt0, 1, rows, tile_stats, st, done);
+            if (done || e != cudaSuccess) return e;
+        }
         advect_lanes_kernel<2, false><<<lanes_grid(g, rows), dim3(32, 8), 0, st>>>(du, dv, sA, sB, u0, v0, g, PeerGeom(), dt0, 1);
         return cudaGetLastError();
     }
@@ -655,25 +966,35 @@ cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u
 }
 
 cudaError_t launch_advect_peer(const Geom &g, int b, float *d, const float *d0, const float *u, const float *v, float dt,
-                               PeerSrc d0p, PeerGeom pg, cudaStream_t st)
+                               PeerSrc d0p, PeerGeom pg, int tile, unsigned int *tile_stats, cudaStream_t st)
 {
     const int rows = interior_row_count(g);
     if (rows == 0) return cudaSuccess;
     if (g.G % 4 != 0) return cudaErrorInvalidValue;
     const float dt0 = dt * (float)g.N;   // FluidSequential.c:111
     const PeerView sA{d0, d0p.up, d0p.dn};
+    if (tile_ok(g, tile, tile_stats, {d0})) {
+        bool done;
+        const cudaError_t e = launch_advect_tile<1, true>(g, tile, d, nullptr, sA, sA, u, v, pg, dt0, b, rows, tile_stats, st, done);
+        if (done || e != cudaSuccess) return e;
+    }
     advect_lanes_kernel<1, true><<<lanes_grid(g, rows), dim3(32, 8), 0, st>>>(d, nullptr, sA, sA, u, v, g, pg, dt0, b);
     return cudaGetLastError();
 }
 
 cudaError_t launch_advect_uv_peer(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt,
-                                  PeerSrc u0p, PeerSrc v0p, PeerGeom pg, cudaStream_t st)
+                                  PeerSrc u0p, PeerSrc v0p, PeerGeom pg, int tile, unsigned int *tile_stats, cudaStream_t st)
 {
     const int rows = interior_row_count(g);
     if (rows == 0) return cudaSuccess;
     if (g.G % 4 != 0) return cudaErrorInvalidValue;
     const float dt0 = dt * (float)g.N;
     const PeerView sA{u0, u0p.up, u0p.dn}, sB{v0, v0p.up, v0p.dn};
+    if (tile_ok(g, tile, tile_stats, {u0, v0})) {
+        bool done;
+        const cudaError_t e = launch_advect_tile<2, true>(g, tile, du, dv, sA, sB, u0, v0, pg, dt0, 1, rows, tile_stats, st, done);
+        if (done || e != cudaSuccess) return e;
+    }
     advect_lanes_kernel<2, true><<<lanes_grid(g, rows), dim3(32, 8), 0, st>>>(du, dv, sA, sB, u0, v0, g, pg, dt0, 1);
     return cudaGetLastError();
 }

@@ -37,6 +37,9 @@ SF_OPT_SOR_OMEGA_MILLI = 12
 SF_OPT_RBGS_BLOCKED = 13
 SF_OPT_FUSE_SOURCES = 14
 SF_OPT_WAVE_SKEW = 15
+SF_OPT_ADVECT_TILE = 16
+SF_OPT_ADVECT_TILE_COUNT = 17
+SF_OPT_ADVECT_FALLBACK_COUNT = 18
 STRICT, FAST = 0, 1
 SOLVER_JACOBI, SOLVER_RBGS = 0, 1    # SF_OPT_SOLVER: the reference's Jacobi (default) / opt-in red-black Gauss-Seidel (SOR)
 
@@ -45,7 +48,7 @@ ABI_SYMBOLS = [
     "sf_create", "sf_create_on_stream", "sf_create_slab", "sf_create_slab_own_stream", "sf_destroy", "sf_last_error_string",
     "sf_set_option", "sf_get_option", "sf_synchronize", "sf_set_stream", "sf_get_stream", "sf_launch_count", "sf_field_bytes",
     "sf_alloc_field", "sf_free_field", "sf_upload", "sf_download",
-    "sf_set_bnd", "sf_add_source", "sf_diffuse", "sf_advect", "sf_compute_divergence_and_pressure",
+    "sf_set_bnd", "sf_add_source", "sf_diffuse", "sf_advect", "sf_advect_velocity", "sf_compute_divergence_and_pressure",
     "sf_last_project", "sf_project", "sf_dens_step", "sf_vel_step", "sf_step", "sf_step_host",
     "sf_run_steps", "sf_dump_field", "sf_init_synthetic", "sf_init_sources", "sf_reduce_max_abs", "sf_reduce_max_abs_async", "sf_residual_l2",
     "sf_division_check", "sf_halo_rows_needed", "sf_jacobi_launch",
@@ -109,6 +112,7 @@ def load_library() -> C.CDLL:
     L.sf_add_source.argtypes = [vp, vp, vp, f]
     L.sf_diffuse.argtypes = [vp, i, vp, vp, f, f, i]
     L.sf_advect.argtypes = [vp, i, vp, vp, vp, vp, f]
+    L.sf_advect_velocity.argtypes = [vp, vp, vp, vp, vp, f]
     L.sf_compute_divergence_and_pressure.argtypes = [vp, vp, vp, vp, vp]
     L.sf_last_project.argtypes = [vp, vp, vp, vp, vp]
     L.sf_project.argtypes = [vp, vp, vp, vp, vp, i]
@@ -250,6 +254,10 @@ class StableFluids:
 
     def advect(self, b, d, d0, u, v, dt):
         self._check(self.L.sf_advect(self.h, b, self._p(d), self._p(d0), self._p(u), self._p(v), dt))
+
+    def advect_velocity(self, u, v, u0, v0, dt):
+        """advect(1, u, u0, u0, v0); advect(2, v, v0, u0, v0) in one pass (FluidSequential.c:228-237)."""
+        self._check(self.L.sf_advect_velocity(self.h, self._p(u), self._p(v), self._p(u0), self._p(v0), dt))
 
     def computeDivergenceAndPressure(self, u, v, p, div):
         self._check(self.L.sf_compute_divergence_and_pressure(self.h, self._p(u), self._p(v), self._p(p), self._p(div)))

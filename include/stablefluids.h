@@ -111,7 +111,18 @@ enum {
      * value = p0 * 1000 + p1: CTAs draw their work item in the order they start, and the chunks of the first / second third
      * of the items get p0 / p1 percent of the mean chunk's rows (the last third gets the rest), e.g. 135106.  Results are
      * unchanged (temporal blocking does not depend on where the chunks are cut).  0 = equal chunks in blockIdx order. */
-    SF_OPT_WAVE_SKEW = 15
+    SF_OPT_WAVE_SKEW = 15,
+    /* advect (seq:107-141).  1 (default) = a CTA owns a tile of 32 rows x 128 columns, traces its cells back, and when the
+     * bounding box of the traces fits (<= 160 columns x 64 rows, inside the rows the context stores) the box of the source
+     * field(s) is fetched into shared memory by the TMA unit (2-D tensor copies, cp.async.bulk.tensor) and the four bilinear
+     * corners are read from there; tiles whose box does not fit gather from global memory as with 0.  2..8 = at most that many
+     * 8-row copies per field (less shared memory per CTA, more fallbacks).  0 = every cell gathers from global memory.
+     * Results are unchanged, bit for bit.  Needs (N+2) % 4 == 0 and N+2 >= 320; other grids always run as with 0. */
+    SF_OPT_ADVECT_TILE = 16,
+    /* diagnostics (sf_get_option synchronises): tiles of the advect launches on this context's device that were served by
+     * the TMA box / that fell back to global gathers, since the last sf_set_option(ctx, SF_OPT_ADVECT_TILE_COUNT, 0) */
+    SF_OPT_ADVECT_TILE_COUNT = 17,
+    SF_OPT_ADVECT_FALLBACK_COUNT = 18
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 enum { SF_SOLVER_JACOBI = 0, SF_SOLVER_RBGS = 1 };
@@ -162,6 +173,9 @@ int sf_add_source(sf_context *ctx, float *x, const float *s, float dt);
 int sf_diffuse(sf_context *ctx, int b, float *x, const float *x0, float alpha, float beta, int iters);
 /* advect(b, d, d0, u, v)                 seq:107-141 gpu:147-196 */
 int sf_advect(sf_context *ctx, int b, float *d, const float *d0, const float *u, const float *v, float dt);
+/* advect(1, u, u0, u0, v0); advect(2, v, v0, u0, v0) -- the self-advection of vel_step, seq:228-237 -- in one pass sharing
+ * the back-trace (what sf_vel_step runs); same bits as the two sf_advect calls.  Full-grid and unconnected slab contexts. */
+int sf_advect_velocity(sf_context *ctx, float *u, float *v, const float *u0, const float *v0, float dt);
 /* computeDivergenceAndPressure(u, v, p, div)   seq:143-158 gpu:199-225 */
 int sf_compute_divergence_and_pressure(sf_context *ctx, const float *u, const float *v, float *p, float *div);
 /* lastProject(u, v, p, div)              seq:161-173 gpu:228-252 */
