@@ -46,6 +46,32 @@ int ensure_scratch(sf_context *c)
     return SF_OK;
 }
 
+// can this context run the independent solves of a step side by side?  (the work-stealing block and the red-black solver's
+// in-place sweeps have one user at a time; slabs sequence their exchanges on one stream)
+bool overlap_ok(const sf_context *c)
+{
+    return c->overlap && is_full_grid(c) && c->solver == SF_SOLVER_JACOBI && c->steal_scope == 0 && stream_kernels_ok(c);
+}
+
+// lanes are created on the first direct run of a step, never inside a stream capture
+int ensure_lanes(sf_context *c)
+{
+    if (!overlap_ok(c)) return SF_OK;
+    for (int k = 0; k < 2; ++k) {
+        sf_context::SolveLane &L = c->lanes[k];
+        if (!L.stream) SF_CUDA(c, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        if (!L.scratch) SF_CUDA(c, cudaMalloc(&L.scratch, field_cells(c) * sizeof(float)));
+        if (!L.scratch2) SF_CUDA(c, cudaMalloc(&L.scratch2, field_cells(c) * sizeof(float)));
+        if (!L.ticket) {
+            SF_CUDA(c, cudaMalloc(&L.ticket, 64));
+            SF_CUDA(c, cudaMemset(L.ticket, 0, 64));
+        }
+        if (!L.fork) SF_CUDA(c, cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
+        if (!L.join) SF_CUDA(c, cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming));
+    }
+    return SF_OK;
+}
+
 // SF_OPT_ADVECT_TILE = 1 is automatic: advect_tile_kernel counts the tiles whose traces fitted the TMA box and those that fell
 // back to gathers.  Where most tiles fall back (a velocity field whose back-traces scatter further than the box: the same
 // initial condition on a much finer grid, dt0 = dt * N) the plain gather kernel is the better choice, since it keeps twice the
@@ -329,6 +355,103 @@ int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, fl
     return enqueue_project(c, u, v, u0, v0, iters);                    // :238-240 (p in u0, div in v0)
 }
 
+// ---- the independent solves of a step side by side (SF_OPT_OVERLAP_SOLVES) -----------------------------
+// A temporally blocked Jacobi launch is one wave of warps with one chunk of rows each; its warps finish up to ~15 % apart, and
+// the next launch of the same solve cannot start before the last one has (it reads what that one writes).  But a step holds
+// three solves that do not depend on each other -- the viscosity solves of u and v (FluidSequential.c:193-210) and the diffusion
+// solve of the density (:177-182, which only meets the velocity in the advect that ends dens_step) -- so their launches go to
+// three streams (forked and joined by events, which a stream capture turns into graph edges): the CTAs of one solve's next
+// launch take the SM slots the previous launch of another solve frees while its last warps are still running.
+// Every lane has its own ping-pong partner, right-hand-side field and ticket word; the kernels and their arguments are those of
+// the sequential order, so the bits cannot differ.
+struct LaneScope {
+    sf_context *c;
+    cudaStream_t work;
+    float *scratch, *scratch2;
+    unsigned *ticket;
+    LaneScope(sf_context *ctx, int k) : c(ctx), work(ctx->work), scratch(ctx->scratch), scratch2(ctx->scratch2), ticket(ctx->ticket)
+    {
+        const sf_context::SolveLane &L = c->lanes[k];
+        c->work = L.stream; c->scratch = L.scratch; c->scratch2 = L.scratch2; c->ticket = L.ticket;
+    }
+    ~LaneScope() { c->work = work; c->scratch = scratch; c->scratch2 = scratch2; c->ticket = ticket; }
+};
+int lane_fork(sf_context *c, int k)
+{
+    SF_CUDA(c, cudaEventRecord(c->lanes[k].fork, c->work));
+    SF_CUDA(c, cudaStreamWaitEvent(c->lanes[k].stream, c->lanes[k].fork, 0));
+    return SF_OK;
+}
+int lane_join(sf_context *c, int k)
+{
+    SF_CUDA(c, cudaEventRecord(c->lanes[k].join, c->lanes[k].stream));
+    SF_CUDA(c, cudaStreamWaitEvent(c->work, c->lanes[k].join, 0));
+    return SF_OK;
+}
+void diffusion_coefficients(const sf_context *c, float coef, float dt, float &alpha, float &beta)
+{
+    const float fN = (float)c->g.N;
+    alpha = dt * coef;            // FluidSequential.c:179 / :199, left to right in binary32
+    alpha = alpha * fN;
+    alpha = alpha * fN;
+    beta = 4.0f * alpha;          // :180 / :200
+    beta = 1.0f + beta;
+}
+
+// the two viscosity solves of vel_step (:193-210), v on lane 0 beside u
+int enqueue_vel_solves_overlapped(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
+{
+    float av, bv;
+    diffusion_coefficients(c, visc, dt, av, bv);
+    (void)arith_mode(c, av, bv);                       // the divisor check synchronises: before anything is forked
+    int rc = lane_fork(c, 0);
+    if (rc) return rc;
+    int r0, r1;
+    { LaneScope lane(c, 0); r0 = source_lin_solve(c, 2, v0, v, dt, av, bv, iters); }              // :197, :209-210
+    r1 = source_lin_solve(c, 1, u0, u, dt, av, bv, iters);                                        // :193, :201-204
+    rc = lane_join(c, 0);                              // (always joined: an unjoined stream would poison a capture)
+    return rc ? rc : (r0 ? r0 : r1);
+}
+
+int enqueue_vel_step_overlapped(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
+{
+    const int rc = enqueue_vel_solves_overlapped(c, u, v, u0, v0, visc, dt, iters);
+    return rc ? rc : enqueue_vel_tail(c, u, v, u0, v0, dt, iters);
+}
+
+// vel_step + dens_step (FluidSequential.c:305-306)
+int enqueue_step(sf_context *c, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev, float visc, float diff,
+                 float dt, int iters)
+{
+    if (!overlap_ok(c) || !c->lanes[1].join) {
+        int r = enqueue_vel_step(c, u, v, u_prev, v_prev, visc, dt, iters);
+        if (r) return r;
+        return enqueue_dens_step(c, dens, dens_prev, u, v, diff, dt, iters);
+    }
+    // Two phases of two streams each: u || v viscosity solves, then the density solve beside the projection / advection /
+    // projection chain of vel_step, which has no other partner.  (Forking the density solve at the start as well, and stream
+    // priorities for the three branches, made no measurable difference: profiles/r02/b2_overlap_priorities.txt, b3_overlap_order.txt.)
+    float ad, bd;
+    diffusion_coefficients(c, diff, dt, ad, bd);
+    (void)arith_mode(c, ad, bd);
+    int rc = enqueue_vel_solves_overlapped(c, u, v, u_prev, v_prev, visc, dt, iters);
+    if (rc) return rc;
+    if ((rc = lane_fork(c, 1))) return rc;
+    int r2;
+    {
+        LaneScope lane(c, 1);
+        c->steal_now = true;                                                                      // see enqueue_dens_step
+        r2 = source_lin_solve(c, 0, dens_prev, dens, dt, ad, bd, iters);                          // :177-182
+        c->steal_now = false;
+    }
+    rc = enqueue_vel_tail(c, u, v, u_prev, v_prev, dt, iters);                                    // :213-240
+    const int rj = lane_join(c, 1);
+    if (rc || r2 || rj) return rc ? rc : (r2 ? r2 : rj);
+    SF_CUDA(c, launch_advect(c->g, 0, dens, dens_prev, u, v, dt, advect_tile_now(c), c->tile_stats, c->work));   // :185
+    ++c->launches;
+    return SF_OK;
+}
+
 GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const void *> ptrs, float f0, float f1, float f2, int iters)
 {
     GraphKey k;
@@ -341,7 +464,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
     k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan + 16 * c->solver +
                 32 * c->omega_milli + 65536 * c->rbgs_blocked + 131072 * c->fuse_sources;
-    k.opts[5] = c->wave_skew; k.opts[6] = c->advect_tile;
+    k.opts[5] = c->wave_skew; k.opts[6] = c->advect_tile + 32 * c->overlap;
     return k;
 }
 
@@ -385,6 +508,14 @@ int create_common(sf_context **out, int N, int device, void *stream, bool own_st
     if (cudaMalloc(&c->tile_stats, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(c->tile_stats, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
         (void)cudaGetLastError();
         if (c->tile_stats) cudaFree(c->tile_stats);
+    for (auto &L : c->lanes) {
+        if (L.stream) cudaStreamDestroy(L.stream);
+        if (L.scratch) cudaFree(L.scratch);
+        if (L.scratch2) cudaFree(L.scratch2);
+        if (L.ticket) cudaFree(L.ticket);
+        if (L.fork) cudaEventDestroy(L.fork);
+        if (L.join) cudaEventDestroy(L.join);
+    }
         c->tile_stats = nullptr;
     }
     *out = c;
@@ -425,6 +556,14 @@ int sf_destroy(sf_context *c)
     if (c->red_d) cudaFree(c->red_d);
     if (c->ticket) cudaFree(c->ticket);
     if (c->tile_stats) cudaFree(c->tile_stats);
+    for (auto &L : c->lanes) {
+        if (L.stream) cudaStreamDestroy(L.stream);
+        if (L.scratch) cudaFree(L.scratch);
+        if (L.scratch2) cudaFree(L.scratch2);
+        if (L.ticket) cudaFree(L.ticket);
+        if (L.fork) cudaEventDestroy(L.fork);
+        if (L.join) cudaEventDestroy(L.join);
+    }
     for (auto &s : c->stage) if (s) cudaFree(s);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->h2d) cudaStreamDestroy(c->h2d);
@@ -466,6 +605,7 @@ int sf_set_option(sf_context *c, int option, int value)
         case SF_OPT_SOR_OMEGA_MILLI: SF_REQUIRE(c, value >= 1 && value <= 1999, "SOR omega in 1/1000: 1..1999"); c->omega_milli = value; break;
         case SF_OPT_RBGS_BLOCKED: c->rbgs_blocked = value ? 1 : 0; break;
         case SF_OPT_FUSE_SOURCES: c->fuse_sources = value ? 1 : 0; break;
+        case SF_OPT_OVERLAP_SOLVES: c->overlap = value ? 1 : 0; break;
         case SF_OPT_ADVECT_TILE_COUNT:
         case SF_OPT_ADVECT_FALLBACK_COUNT: {
             SF_REQUIRE(c, value == 0, "advect tile counters: only 0 (reset) can be set");
@@ -511,6 +651,7 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_SOR_OMEGA_MILLI: *value = c->omega_milli; break;
         case SF_OPT_RBGS_BLOCKED: *value = c->rbgs_blocked; break;
         case SF_OPT_FUSE_SOURCES: *value = c->fuse_sources; break;
+        case SF_OPT_OVERLAP_SOLVES: *value = c->overlap; break;
         case SF_OPT_ADVECT_TILE: *value = c->advect_tile; break;
         case SF_OPT_ADVECT_TILE_COUNT:
         case SF_OPT_ADVECT_FALLBACK_COUNT: {
@@ -729,7 +870,11 @@ int sf_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float v
     if (rc) return rc;
     if (is_linked_slab(c) && (rc = slab_prevalidate(c, visc, dt))) return rc;
     const GraphKey key = make_key(c, 2, {u, v, u0, v0}, visc, dt, 0.f, iters);
-    return run_graphed(c, key, [&] { return enqueue_vel_step(c, u, v, u0, v0, visc, dt, iters); });
+    if (!c->use_graph && ((rc = ensure_scratch(c)) || (rc = ensure_lanes(c)))) return rc;
+    return run_graphed(c, key, [&] {
+        return overlap_ok(c) && c->lanes[0].join ? enqueue_vel_step_overlapped(c, u, v, u0, v0, visc, dt, iters)
+                                                 : enqueue_vel_step(c, u, v, u0, v0, visc, dt, iters);
+    });
 }
 
 int sf_step(sf_context *c, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev, float visc,
@@ -744,11 +889,8 @@ int sf_step(sf_context *c, float *dens, float *dens_prev, float *u, float *u_pre
     if (rc) return rc;
     if (is_linked_slab(c) && ((rc = slab_prevalidate(c, visc, dt)) || (rc = slab_prevalidate(c, diff, dt)))) return rc;
     const GraphKey key = make_key(c, 3, {dens, dens_prev, u, u_prev, v, v_prev}, visc, diff, dt, iters);
-    return run_graphed(c, key, [&] {
-        int r = enqueue_vel_step(c, u, v, u_prev, v_prev, visc, dt, iters);   // FluidSequential.c:305
-        if (r) return r;
-        return enqueue_dens_step(c, dens, dens_prev, u, v, diff, dt, iters);  // :306
-    });
+    if (!c->use_graph && ((rc = ensure_scratch(c)) || (rc = ensure_lanes(c)))) return rc;
+    return run_graphed(c, key, [&] { return enqueue_step(c, dens, dens_prev, u, u_prev, v, v_prev, visc, diff, dt, iters); });
 }
 
 int sf_step_host(sf_context *c, float *dens, float *dens_prev, float *u, float *u_prev, float *v, float *v_prev,

@@ -76,6 +76,15 @@ struct sf_context {
     bool advect_tile_live = true;    // automatic mode: what the launches enqueued now use
     unsigned int *tile_stats = nullptr;        // device: tiles served by the TMA box / by the gather fallback
     unsigned int tile_seen[2] = {0u, 0u};      // their values when the policy last looked
+    // SF_OPT_OVERLAP_SOLVES: independent lin_solves of a step on streams of their own (see enqueue_step in sf_api.cu); a lane
+    // owns everything a solve scribbles on
+    struct SolveLane {
+        cudaStream_t stream = nullptr;
+        float *scratch = nullptr, *scratch2 = nullptr;
+        unsigned *ticket = nullptr;
+        cudaEvent_t fork = nullptr, join = nullptr;
+    } lanes[2];
+    int overlap = 1;
     int wave_skew = 131103;          // SF_OPT_WAVE_SKEW (p0 * 1000 + p1); swept in profiles/r02/s15_*_skew_sweep.txt
     unsigned *ticket = nullptr;      // device word: start-order tickets of the CTAs of a Jacobi launch
     float *scratch = nullptr;        // lin_solve ping-pong partner (inside the arena for peer slabs)
@@ -167,6 +176,7 @@ const StripArgs *slab_strip_args(const sf_context *c, const float *xout, int row
 // what the advect launches enqueued next get as `tile`
 inline int advect_tile_now(const sf_context *c) { return c->advect_tile == 1 ? (c->advect_tile_live ? 1 : 0) : c->advect_tile; }
 int refresh_advect_policy(sf_context *c);
+int ensure_lanes(sf_context *c);
 
 template <class Body>
 int run_graphed(sf_context *c, const GraphKey &key, Body body)
@@ -186,6 +196,7 @@ int run_graphed(sf_context *c, const GraphKey &key, Body body)
         }
     int rc = ensure_scratch(c);
     if (rc) return rc;
+    if ((rc = ensure_lanes(c))) return rc;
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(c->stream, &st);
     if (st != cudaStreamCaptureStatusNone) return body();   // caller is capturing already

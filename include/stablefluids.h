@@ -122,7 +122,13 @@ enum {
     /* diagnostics (sf_get_option synchronises): tiles of the advect launches on this context's device that were served by
      * the TMA box / that fell back to global gathers, since the last sf_set_option(ctx, SF_OPT_ADVECT_TILE_COUNT, 0) */
     SF_OPT_ADVECT_TILE_COUNT = 17,
-    SF_OPT_ADVECT_FALLBACK_COUNT = 18
+    SF_OPT_ADVECT_FALLBACK_COUNT = 18,
+    /* 1 (default) = inside sf_step (and sf_run_steps) the three lin_solves that do not depend on each other -- the viscosity
+     * solves of u and v (seq:193-210) and the density's diffusion solve (seq:177-182) -- are enqueued on three streams
+     * (graph branches), so the launches of one fill the SMs that the tail of another's leaves idle (u beside v, then the density solve
+     * beside the projections and the advection of vel_step).  Costs four more scratch fields.  0 = one after the other.  Full-grid contexts with the
+     * Jacobi solver; results are unchanged (same kernels, same arguments). */
+    SF_OPT_OVERLAP_SOLVES = 19
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 enum { SF_SOLVER_JACOBI = 0, SF_SOLVER_RBGS = 1 };
