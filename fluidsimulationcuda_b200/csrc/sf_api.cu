@@ -79,7 +79,7 @@ int ensure_lanes(sf_context *c)
 // library synchronises anyway -- and the choice is frozen into that graph.
 int refresh_advect_policy(sf_context *c)
 {
-    if (c->advect_tile != 1 || !c->tile_stats) return SF_OK;
+    if (c->advect_tile != 1 || !c->tile_stats || c->link.base != nullptr) return SF_OK;
     unsigned int now[2] = {0u, 0u};
     SF_CUDA(c, cudaStreamSynchronize(c->stream));
     SF_CUDA(c, cudaMemcpy(now, c->tile_stats, sizeof(now), cudaMemcpyDeviceToHost));

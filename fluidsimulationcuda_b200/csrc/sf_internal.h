@@ -174,7 +174,13 @@ const StripArgs *slab_strip_args(const sf_context *c, const float *xout, int row
 
 // ---- CUDA graph cache ------------------------------------------------------------------------
 // what the advect launches enqueued next get as `tile`
-inline int advect_tile_now(const sf_context *c) { return c->advect_tile == 1 ? (c->advect_tile_live ? 1 : 0) : c->advect_tile; }
+// (automatic mode needs the counters of a finished step, i.e. a host synchronisation, which a connected slab must not do
+// in the middle of a collective sequence -- one thread may be driving several slabs: slabs take the tiles only on request)
+inline int advect_tile_now(const sf_context *c)
+{
+    if (c->advect_tile != 1) return c->advect_tile;
+    return (c->advect_tile_live && c->link.base == nullptr) ? 1 : 0;
+}
 int refresh_advect_policy(sf_context *c);
 int ensure_lanes(sf_context *c);
 

@@ -112,11 +112,14 @@ enum {
      * of the items get p0 / p1 percent of the mean chunk's rows (the last third gets the rest), e.g. 135106.  Results are
      * unchanged (temporal blocking does not depend on where the chunks are cut).  0 = equal chunks in blockIdx order. */
     SF_OPT_WAVE_SKEW = 15,
-    /* advect (seq:107-141).  1 (default) = a CTA owns a tile of 32 rows x 128 columns, traces its cells back, and when the
-     * bounding box of the traces fits (<= 160 columns x 64 rows, inside the rows the context stores) the box of the source
-     * field(s) is fetched into shared memory by the TMA unit (2-D tensor copies, cp.async.bulk.tensor) and the four bilinear
-     * corners are read from there; tiles whose box does not fit gather from global memory as with 0.  2..8 = at most that many
-     * 8-row copies per field (less shared memory per CTA, more fallbacks).  0 = every cell gathers from global memory.
+    /* advect (seq:107-141).  A CTA owns a tile of 16 or 32 rows x 128 columns, traces its cells back, and when the bounding
+     * box of the traces fits (<= 160 columns, <= 8 rows per copy below, inside the rows the context stores) the box of the
+     * source field(s) is fetched into shared memory by the TMA unit (2-D tensor copies, cp.async.bulk.tensor) and the four
+     * bilinear corners are read from there; tiles whose box does not fit gather from global memory as with 0.
+     * 1 (default) = automatic: 16-row tiles with 5 copies of 8 rows per field; when a step is captured into a graph the tile
+     * counters of the direct run before it decide whether the captured step keeps the tiles (most fitted) or runs as with 0;
+     * connected slabs run as with 0.  2..8 = 32-row tiles, at most that many 8-row copies per field; 12..18 = 16-row tiles,
+     * (value - 10) copies; both always on.  0 = every cell gathers from global memory.
      * Results are unchanged, bit for bit.  Needs (N+2) % 4 == 0 and N+2 >= 320; other grids always run as with 0. */
     SF_OPT_ADVECT_TILE = 16,
     /* diagnostics (sf_get_option synchronises): tiles of the advect launches on this context's device that were served by

@@ -225,3 +225,35 @@ def test_peer_slabs_on_real_devices_bit_identical_to_oracle(oracle_mt, world, N,
     for s in solvers:
         s.status()
         s.close()
+
+
+@pytest.mark.parametrize("world,tile", [(2, 15), (3, 8), (2, 4)])
+def test_peer_slabs_with_tma_staged_advect(oracle_mt, world, tile):
+    """SF_OPT_ADVECT_TILE on request on connected slabs (advect_tile_kernel<NF, PEER = true>): tiles whose traces stay inside
+    the slab's own rows take the TMA box, tiles near a slab edge gather from the neighbour's memory; same bits as the oracle"""
+    from fluidsimulationcuda_b200 import solver as SF
+    N, K = 638, 6
+    solvers = make(N, world, K, use_graph=True)
+    for s in solvers:
+        s.ctx.set_option(SF.SF_OPT_ADVECT_TILE, tile)
+        s.init_synthetic(5)
+        with torch.cuda.stream(s.stream):
+            s.f["u_prev"].mul_(25.0)      # traces of several rows: some leave the slab
+            s.f["v_prev"].mul_(25.0)
+    w = oracle_mt.init_synthetic(N, 5)
+    w["u_prev"] *= np.float32(25.0); w["v_prev"] *= np.float32(25.0)
+    for step in range(3):           # direct, capture + launch, replay
+        if step > 0:
+            for s in solvers:
+                s.zero_sources()
+        for s in solvers:
+            s.step(None, VIS, DIFF, DT)
+        oracle_mt.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=step)
+        for k in w:
+            got = gather(solvers, k)
+            assert bits_equal(got, w[k]), mismatch_report(got, w[k], f"world={world} tile={tile} step={step} {k}")
+    for s in solvers:
+        s.status()
+        tma = s.ctx.get_option(SF.SF_OPT_ADVECT_TILE_COUNT); fb = s.ctx.get_option(SF.SF_OPT_ADVECT_FALLBACK_COUNT)
+        assert tma > 0 and fb > 0, (tma, fb)      # interior tiles by TMA, tiles near the slab edges by peer gathers
+        s.close()
