@@ -430,7 +430,8 @@ int enqueue_step(sf_context *c, float *dens, float *dens_prev, float *u, float *
     }
     // Two phases of two streams each: u || v viscosity solves, then the density solve beside the projection / advection /
     // projection chain of vel_step, which has no other partner.  (Forking the density solve at the start as well, and stream
-    // priorities for the three branches, made no measurable difference: profiles/r02/b2_overlap_priorities.txt, b3_overlap_order.txt.)
+    // priorities for the three branches, made no measurable difference; forking it after the first projection was 1.5 % slower:
+    // profiles/r02/b2_overlap_priorities.txt, b3_overlap_order.txt, b4_overlap_fork_point.txt.)
     float ad, bd;
     diffusion_coefficients(c, diff, dt, ad, bd);
     (void)arith_mode(c, ad, bd);
