@@ -509,7 +509,7 @@ def run_ours(args):
                                f"STRICT arithmetic (bit-identical to the reference's sequential path)",
                    "grid": G, "iters": K, "parallelism": f"row slabs x{world}" if world > 1 else "single GPU",
                    "l2": "every field (G^2*4 B = %.0f MiB) is larger than the 126 MB L2; 9 fields live" % (cells * 4 / 2**20),
-                   "per_step": ("device-side source refresh + vel_step + dens_step, replayed from a CUDA graph" if world == 1 else
+                   "per_step": ("device-side source refresh + vel_step + dens_step, replayed from a CUDA graph whose independent lin_solves (u, v viscosity; density diffusion) are parallel branches" if world == 1 else
                                 "device-side source refresh + vel_step + dens_step per slab, one CUDA-graph replay per GPU; halo rows "
                                 "stored into the neighbour's ghost rows over NVLink by the Jacobi boundary-strip kernels (peer memory) "
                                 "while the interior launch runs; advect gathers through the peer mapping; device-side neighbour barriers"

@@ -202,10 +202,10 @@ int run_graphed(sf_context *c, const GraphKey &key, Body body)
         }
     int rc = ensure_scratch(c);
     if (rc) return rc;
-    if ((rc = ensure_lanes(c))) return rc;
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(c->stream, &st);
-    if (st != cudaStreamCaptureStatusNone) return body();   // caller is capturing already
+    if (st != cudaStreamCaptureStatusNone) return body();   // caller is capturing already (lanes that exist are used, none are made)
+    if ((rc = ensure_lanes(c))) return rc;
     if (!seen) {
         // First sighting of these arguments: launch directly (this also loads the kernels' modules
         // outside of any capture); the second call with the same arguments captures the graph.

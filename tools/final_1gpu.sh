@@ -15,7 +15,7 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_th
 # one full step (graphs off: every kernel of the step is a separate launch), full set on the kernels that matter
 # (ncu prints template arguments as "(int)7, (int)0, (int)0"; the skip counts put every capture into the 3rd / 4th step of
 # tools/prof_step.py: in step 0 the velocity right-hand side is dt * source with 1 % exact zeros, which is not what a timed step sees)
-for spec in "20:jacobi_stream_kernel<.int.7, .int.0, .int.0>" "25:jacobi_stream_kernel<.int.8, .int.1, .int.0>" "8:jacobi_stream_kernel<.int.7, .int.0, .int.3>" "5:jacobi_stream_kernel<.int.7, .int.0, .int.6>" "2:advect_lanes_kernel<.int.2" "2:advect_lanes_kernel<.int.1"; do
+for spec in "20:jacobi_stream_kernel<.int.7, .int.0, .int.0>" "25:jacobi_stream_kernel<.int.8, .int.1, .int.0>" "8:jacobi_stream_kernel<.int.7, .int.0, .int.3>" "5:jacobi_stream_kernel<.int.7, .int.0, .int.6>" "2:advect_tile_kernel<.int.2" "2:advect_tile_kernel<.int.1" "1:last_project4" "1:divergence4" "2:init4"; do
   skip=${spec%%:*}; pat=${spec#*:}
   tag=$(echo "$pat" | tr -c 'A-Za-z0-9' '_' | sed 's/__*/_/g; s/_$//')
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"$pat" -s $skip -c 1 -o gpurun_out/final_prof_$tag -f python tools/prof_step.py > gpurun_out/final_prof_$tag.log 2>&1
@@ -28,4 +28,7 @@ python tools/t_sweep.py 8192 40 1,2,3,4,5,6,7,8 > gpurun_out/final_t_sweep.log 2
 # staging A/B: per-lane cp.async (default) against one bulk copy per row piece (cp.async.bulk, SF_OPT_STAGING = 1)
 for st in 0 1; do python tools/solve_sweep.py $st; done > gpurun_out/final_staging_ab.log 2>&1; cat gpurun_out/final_staging_ab.log
 python tools/stage_times.py 8192 40 > gpurun_out/final_stage_times.log 2>&1; tail -18 gpurun_out/final_stage_times.log
+# the step against the two round-2 options that changed its schedule: overlapped solves (19), TMA-staged advect (16)
+python tools/step_ab.py 8192 40 sequential_gather=19:0,16:0 tile_only=19:0,16:1 overlap_only=19:1,16:0 default=19:1,16:1 > gpurun_out/final_step_ab.log 2>&1; cat gpurun_out/final_step_ab.log
+python tools/advect_ab.py 8192 40 0,1,15,8,6 > gpurun_out/final_advect_ab.log 2>&1; cat gpurun_out/final_advect_ab.log
 ls -la gpurun_out/final_*
