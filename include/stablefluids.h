@@ -131,7 +131,13 @@ enum {
      * (graph branches), so the launches of one fill the SMs that the tail of another's leaves idle (u beside v, then the density solve
      * beside the projections and the advection of vel_step).  Costs four more scratch fields.  0 = one after the other.  Full-grid contexts with the
      * Jacobi solver; results are unchanged (same kernels, same arguments). */
-    SF_OPT_OVERLAP_SOLVES = 19
+    SF_OPT_OVERLAP_SOLVES = 19,
+    /* 1 (default) = inside sf_step, where SF_OPT_OVERLAP_SOLVES and the TMA-staged advect apply, the gradient subtraction that
+     * ends vel_step (lastProject, seq:161-173 as called at seq:240) is folded into the advect that ends dens_step (seq:185):
+     * that advect reads u, v only at the cell it traces back from, so each thread corrects u, v of its own cells from the
+     * pressure first, stores them (set_bnd fused) and traces back with the corrected values -- one pass over u, v and one
+     * launch less per step.  u, v, dens and the *_prev fields come out unchanged, bit for bit.  0 = two kernels. */
+    SF_OPT_FUSE_PROJECT_ADVECT = 20
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 enum { SF_SOLVER_JACOBI = 0, SF_SOLVER_RBGS = 1 };
