@@ -298,7 +298,7 @@ int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const 
     return SF_OK;
 }
 
-int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters, bool defer_last)
+int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters)
 {
     if (is_linked_slab(c)) return slab_project(c, u, v, p, div, iters);
     // the streaming lin_solve can start from an implicit zero guess, so p need not be written here
@@ -308,7 +308,6 @@ int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int
     ++c->launches;
     int rc = lin_solve(c, 0, p, div, 1.0f, 4.0f, iters, stream_ok ? 1 : 0);
     if (rc) return rc;
-    if (defer_last) return SF_OK;          // the caller folds lastProject into the kernel that follows (enqueue_step)
     SF_CUDA(c, launch_last_project(c->g, u, v, p, c->work));
     ++c->launches;
     return SF_OK;
@@ -327,13 +326,13 @@ int enqueue_vel_diffuse(sf_context *c, int b, float *x, float *x0, float visc, f
     return source_lin_solve(c, b, x0, x, dt, alpha, beta, iters);
 }
 // ... and everything after the two solves (:213-240)
-int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, float dt, int iters, bool defer_last)
+int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, float dt, int iters)
 {
     int rc = enqueue_project(c, u0, v0, u, v, iters);                  // :213-223 (p in u, div in v)
     if (rc) return rc;
     SF_CUDA(c, launch_advect_uv(c->g, u, v, u0, v0, dt, advect_tile_now(c), c->tile_stats, c->work));   // :228-237
     ++c->launches;
-    return enqueue_project(c, u, v, u0, v0, iters, defer_last);        // :238-240 (p in u0, div in v0)
+    return enqueue_project(c, u, v, u0, v0, iters);                    // :238-240 (p in u0, div in v0)
 }
 
 int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
@@ -446,19 +445,9 @@ int enqueue_step(sf_context *c, float *dens, float *dens_prev, float *u, float *
         r2 = source_lin_solve(c, 0, dens_prev, dens, dt, ad, bd, iters);                          // :177-182
         c->steal_now = false;
     }
-    // SF_OPT_FUSE_PROJECT_ADVECT: the gradient subtraction that ends vel_step (:161-173 via :240) is folded into the advect that
-    // ends dens_step (:185), which reads u, v only at the cell it traces back from -- where the TMA-staged advect applies
-    const bool fold = c->fuse_project_advect && advect_tile_now(c) > 0;
-    rc = enqueue_vel_tail(c, u, v, u_prev, v_prev, dt, iters, fold);                              // :213-240
+    rc = enqueue_vel_tail(c, u, v, u_prev, v_prev, dt, iters);                                    // :213-240
     const int rj = lane_join(c, 1);
     if (rc || r2 || rj) return rc ? rc : (r2 ? r2 : rj);
-    if (fold) {
-        bool done = false;
-        SF_CUDA(c, launch_last_project_advect(c->g, u, v, u_prev, dens, dens_prev, dt, advect_tile_now(c), c->tile_stats, c->work, done));
-        if (done) { ++c->launches; return SF_OK; }
-        SF_CUDA(c, launch_last_project(c->g, u, v, u_prev, c->work));                              // not applicable on this grid
-        ++c->launches;
-    }
     SF_CUDA(c, launch_advect(c->g, 0, dens, dens_prev, u, v, dt, advect_tile_now(c), c->tile_stats, c->work));   // :185
     ++c->launches;
     return SF_OK;
@@ -476,7 +465,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
     k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan + 16 * c->solver +
                 32 * c->omega_milli + 65536 * c->rbgs_blocked + 131072 * c->fuse_sources;
-    k.opts[5] = c->wave_skew; k.opts[6] = c->advect_tile + 32 * c->overlap + 64 * c->fuse_project_advect;
+    k.opts[5] = c->wave_skew; k.opts[6] = c->advect_tile + 32 * c->overlap;
     return k;
 }
 
@@ -618,7 +607,6 @@ int sf_set_option(sf_context *c, int option, int value)
         case SF_OPT_RBGS_BLOCKED: c->rbgs_blocked = value ? 1 : 0; break;
         case SF_OPT_FUSE_SOURCES: c->fuse_sources = value ? 1 : 0; break;
         case SF_OPT_OVERLAP_SOLVES: c->overlap = value ? 1 : 0; break;
-        case SF_OPT_FUSE_PROJECT_ADVECT: c->fuse_project_advect = value ? 1 : 0; break;
         case SF_OPT_ADVECT_TILE_COUNT:
         case SF_OPT_ADVECT_FALLBACK_COUNT: {
             SF_REQUIRE(c, value == 0, "advect tile counters: only 0 (reset) can be set");
@@ -665,7 +653,6 @@ int sf_get_option(const sf_context *c, int option, int *value)
         case SF_OPT_RBGS_BLOCKED: *value = c->rbgs_blocked; break;
         case SF_OPT_FUSE_SOURCES: *value = c->fuse_sources; break;
         case SF_OPT_OVERLAP_SOLVES: *value = c->overlap; break;
-        case SF_OPT_FUSE_PROJECT_ADVECT: *value = c->fuse_project_advect; break;
         case SF_OPT_ADVECT_TILE: *value = c->advect_tile; break;
         case SF_OPT_ADVECT_TILE_COUNT:
         case SF_OPT_ADVECT_FALLBACK_COUNT: {

@@ -334,9 +334,6 @@ cudaError_t launch_advect(const Geom &g, int b, float *d, const float *d0, const
 // both velocity components in one pass: d_u <- advect(b=1, u0), d_v <- advect(b=2, v0) by (u0, v0)
 cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u0, const float *v0, float dt, int tile,
                              unsigned int *tile_stats, cudaStream_t st);
-// lastProject(u, v, p) + advect(0, d, d0, u, v) in one kernel where the TMA-staged advect applies (`done`), see sf_stages.cu
-cudaError_t launch_last_project_advect(const Geom &g, float *u, float *v, const float *p, float *d, const float *d0, float dt, int tile,
-                                       unsigned int *tile_stats, cudaStream_t st, bool &done);
 cudaError_t launch_divergence(const Geom &g, const float *u, const float *v, float *p, float *div, int write_p,
                               cudaStream_t st);
 cudaError_t launch_last_project(const Geom &g, float *u, float *v, const float *p, cudaStream_t st);

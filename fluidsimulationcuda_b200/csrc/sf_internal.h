@@ -85,7 +85,6 @@ struct sf_context {
         cudaEvent_t fork = nullptr, join = nullptr;
     } lanes[2];
     int overlap = 1;
-    int fuse_project_advect = 1;     // SF_OPT_FUSE_PROJECT_ADVECT
     int wave_skew = 131103;          // SF_OPT_WAVE_SKEW (p0 * 1000 + p1); swept in profiles/r02/s15_*_skew_sweep.txt
     unsigned *ticket = nullptr;      // device word: start-order tickets of the CTAs of a Jacobi launch
     float *scratch = nullptr;        // lin_solve ping-pong partner (inside the arena for peer slabs)
@@ -157,10 +156,10 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
                       float src_dt = 0.0f);
 int lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess);
 int enqueue_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters);
-int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters, bool defer_last = false);
+int enqueue_project(sf_context *c, float *u, float *v, float *p, float *div, int iters);
 int enqueue_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters);
 int enqueue_vel_diffuse(sf_context *c, int b, float *x, float *x0, float visc, float dt, int iters);
-int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, float dt, int iters, bool defer_last = false);
+int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, float dt, int iters);
 GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const void *> ptrs, float f0, float f1, float f2, int iters);
 
 // ---- implemented in sf_slab.cu (peer-memory slabs; every rank must issue the same call sequence) ----

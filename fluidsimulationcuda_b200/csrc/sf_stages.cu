@@ -658,19 +658,12 @@ __device__ __forceinline__ void trunc_pos(float x, float &fl, int &i)
     fl = __fsub_rn(t, 8388608.0f);
 }
 
-// LP = true (NF = 1, one GPU): the gradient subtraction that ends vel_step (lastProject, FluidSequential.c:161-173) is done on the
-// way: advect(0, d, d0, u, v) reads the velocity only at the cell it traces back from, so each thread first corrects u, v of its
-// own cells from the pressure p (u -= 0.5 (p_r - p_l) / h, v -= 0.5 (p_d - p_u) / h, same operations as last_project4_kernel),
-// stores them with set_bnd(1, u) / set_bnd(2, v) fused as usual, and traces back with the corrected values: one pass over u, v
-// and one launch less per step.  In place is safe: no thread reads another cell's u or v.
-template <int NF, bool PEER, int RPW, bool LP = false>
+template <int NF, bool PEER, int RPW>
 __global__ void __launch_bounds__(256, (RPW == 2 ? 4 : SF_AT_MINB)) advect_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                           float *__restrict__ dA, float *__restrict__ dB, PeerView sA, PeerView sB,
-                                                          const float *u, const float *v, Geom g,
-                                                          PeerGeom pg, float dt0, int bA, int maxsub, unsigned int *__restrict__ stats,
-                                                          float *uw, float *vw, const float *__restrict__ prs, float h)
+                                                          const float *__restrict__ u, const float *__restrict__ v, Geom g,
+                                                          PeerGeom pg, float dt0, int bA, int maxsub, unsigned int *__restrict__ stats)
 {
-    static_assert(!LP || (NF == 1 && !PEER), "fused lastProject: scalar field, one GPU");
     extern __shared__ unsigned char at_dyn[];
     __shared__ int s_red[8][4];
     __shared__ __align__(8) uint64_t s_bar;
@@ -696,37 +689,8 @@ __global__ void __launch_bounds__(256, (RPW == 2 ? 4 : SF_AT_MINB)) advect_tile_
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int cl = min(seg + 32 * k + lane, g.G - 1);
-                if (LP) {
-                    // a mirrored ROW must not be read: its owner (another warp) is rewriting it.  Its cells are left out of the
-                    // box below and of step 3.  (Idle lanes mirror the wall column of their own row, which only this warp
-                    // writes, after these loads.)
-                    const bool mine = row0 + rr < hi;
-                    uu[rr][k] = mine ? u[rowoff + cl] : 0.0f;
-                    vv[rr][k] = mine ? v[rowoff + cl] : 0.0f;
-                } else {
-                    uu[rr][k] = __ldg(u + rowoff + cl);
-                    vv[rr][k] = __ldg(v + rowoff + cl);
-                }
-            }
-        }
-        if (LP) {
-#pragma unroll
-            for (int rr = 0; rr < RPW; ++rr) {
-                const int row = row0 + rr;
-                if (row >= hi) break;                                       // uniform per warp
-                const size_t rowoff = (size_t)(row - g.row_base) * G;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int col = seg + 32 * k + lane;
-                    if (col >= 1 && col <= g.N) {                           // wall columns keep their old value until store_lanes_row
-                        const float *pc = prs + rowoff + col;
-                        // FluidSequential.c:167-168: u -= (0.5f*(p_r - p_l)) / h ; v -= (0.5f*(p_d - p_u)) / h
-                        uu[rr][k] = __fsub_rn(uu[rr][k], __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(__ldg(pc + 1), __ldg(pc - 1))), h));
-                        vv[rr][k] = __fsub_rn(vv[rr][k], __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(__ldg(pc + G), __ldg(pc - G))), h));
-                    }
-                }
-                float ou[4] = {uu[rr][0], uu[rr][1], uu[rr][2], uu[rr][3]}, ov[4] = {vv[rr][0], vv[rr][1], vv[rr][2], vv[rr][3]};
-                store_lanes_row<2>(uw, vw, g, row, seg, lane, ou, ov, 1);   // set_bnd(1, u), set_bnd(2, v)
+                uu[rr][k] = __ldg(u + rowoff + cl);
+                vv[rr][k] = __ldg(v + rowoff + cl);
             }
         }
 #pragma unroll
@@ -740,7 +704,6 @@ __global__ void __launch_bounds__(256, (RPW == 2 ? 4 : SF_AT_MINB)) advect_tile_
     for (int rr = 0; rr < RPW; ++rr)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (LP && row0 + rr >= hi) continue;      // see the loads above
             // the extremes of the positions give the extremes of their integer parts (truncation is monotone)
             fcmin = fminf(fcmin, px[rr][k]); fcmax = fmaxf(fcmax, px[rr][k]);
             frmin = fminf(frmin, py[rr][k]); frmax = fmaxf(frmax, py[rr][k]);
@@ -884,9 +847,11 @@ inline dim3 tile_grid(const Geom &g, int rows, int rpw) { return dim3((g.G + 127
 #ifndef SF_AT_DEFAULT
 #define SF_AT_DEFAULT 15
 #endif
-inline void tile_shape(int tile, int &rpw, int &maxsub)
+inline void tile_shape(int tile, int nf, int &rpw, int &maxsub)
 {
-    if (tile < 2) tile = SF_AT_DEFAULT;
+    // measured (profiles/r02/final_*_advect_ab.log): one field is fastest with 32-row tiles (0.226 vs 0.249 ms), the u, v pair
+    // with 16-row tiles, whose two boxes leave room for four CTAs per SM
+    if (tile < 2) tile = (nf == 1) ? AT_MAXSUB : SF_AT_DEFAULT;
     rpw = tile >= 10 ? 2 : 4;
     maxsub = tile >= 10 ? tile - 10 : tile;
     if (maxsub < 2) maxsub = 2;
@@ -902,7 +867,7 @@ cudaError_t launch_advect_tile_rpw(const CUtensorMap &tmA, const CUtensorMap &tm
     cudaError_t e = cudaFuncSetAttribute(advect_tile_kernel<NF, PEER, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(NF, AT_MAXSUB));
     if (e != cudaSuccess) return e;
     advect_tile_kernel<NF, PEER, RPW><<<tile_grid(g, rows, RPW), dim3(32, 8), tile_smem(NF, maxsub), st>>>(tmA, tmB, dA, dB, sA, sB, u, v, g, pg, dt0, bA,
-                                                                                                      maxsub, stats, nullptr, nullptr, nullptr, 0.0f);
+                                                                                                      maxsub, stats);
     return cudaGetLastError();
 }
 template <int NF, bool PEER>
@@ -915,7 +880,7 @@ cudaError_t launch_advect_tile(const Geom &g, int tile, float *dA, float *dB, Pe
     if (NF == 2) { if (!make_field_map(&tmB, sB.loc, g)) return cudaSuccess; }
     else tmB = tmA;
     int rpw, maxsub;
-    tile_shape(tile, rpw, maxsub);
+    tile_shape(tile, NF, rpw, maxsub);
     done = true;
     if (rpw == 2) return launch_advect_tile_rpw<NF, PEER, 2>(tmA, tmB, g, maxsub, dA, dB, sA, sB, u, v, pg, dt0, bA, rows, stats, st);
     return launch_advect_tile_rpw<NF, PEER, 4>(tmA, tmB, g, maxsub, dA, dB, sA, sB, u, v, pg, dt0, bA, rows, stats, st);
@@ -936,7 +901,6 @@ void preload_stage_kernels()
     cudaFuncGetAttributes(&a, advect_tile_kernel<1, true, 2>); cudaFuncGetAttributes(&a, advect_tile_kernel<2, true, 2>);
     cudaFuncGetAttributes(&a, advect_tile_kernel<1, false, 4>); cudaFuncGetAttributes(&a, advect_tile_kernel<2, false, 4>);
     cudaFuncGetAttributes(&a, advect_tile_kernel<1, true, 4>); cudaFuncGetAttributes(&a, advect_tile_kernel<2, true, 4>);
-    cudaFuncGetAttributes(&a, advect_tile_kernel<1, false, 2, true>);
     cudaFuncGetAttributes(&a, divergence_kernel); cudaFuncGetAttributes(&a, divergence4_kernel);
     cudaFuncGetAttributes(&a, last_project_kernel); cudaFuncGetAttributes(&a, last_project4_kernel);
     cudaFuncGetAttributes(&a, init_kernel); cudaFuncGetAttributes(&a, init4_kernel);
@@ -1008,32 +972,6 @@ cudaError_t launch_advect_uv(const Geom &g, float *du, float *dv, const float *u
         return cudaGetLastError();
     }
     advect_kernel<2><<<cell_grid(g, block, rows), block, 0, st>>>(du, dv, u0, v0, u0, v0, g, dt0, 1);
-    return cudaGetLastError();
-}
-
-// lastProject(u, v, p) followed by advect(b = 0, d, d0, u, v) -- the end of vel_step and the end of dens_step -- in one kernel
-// (advect_tile_kernel<1, false, 2, true>).  `done` = false: not applicable here (grid shape, alignment, tiles off, old driver);
-// nothing was launched and the caller runs the two stages separately.
-cudaError_t launch_last_project_advect(const Geom &g, float *u, float *v, const float *p, float *d, const float *d0, float dt, int tile,
-                                       unsigned int *tile_stats, cudaStream_t st, bool &done)
-{
-    done = false;
-    const int rows = interior_row_count(g);
-    if (rows == 0 || g.own_lo != 0 || g.own_hi != g.G) return cudaSuccess;
-    if (!tile_ok(g, tile, tile_stats, {d0, u, v, p})) return cudaSuccess;
-    int rpw, maxsub;
-    tile_shape(tile, rpw, maxsub);
-    if (rpw != 2) { rpw = 2; if (maxsub > 5) maxsub = 5; }      // the fused kernel is built for 16-row tiles
-    CUtensorMap tm;
-    if (!make_field_map(&tm, d0, g)) return cudaSuccess;
-    const float dt0 = dt * (float)g.N;   // FluidSequential.c:111
-    const float h = 1.0f / (float)g.N;   // :165
-    const PeerView sA{d0, nullptr, nullptr};
-    cudaError_t e = cudaFuncSetAttribute(advect_tile_kernel<1, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(1, AT_MAXSUB));
-    if (e != cudaSuccess) return e;
-    advect_tile_kernel<1, false, 2, true><<<tile_grid(g, rows, 2), dim3(32, 8), tile_smem(1, maxsub), st>>>(tm, tm, d, nullptr, sA, sA, u, v, g, PeerGeom(), dt0, 0,
-                                                                                                 maxsub, tile_stats, u, v, p, h);
-    done = true;
     return cudaGetLastError();
 }
 

@@ -116,7 +116,8 @@ enum {
      * box of the traces fits (<= 160 columns, <= 8 rows per copy below, inside the rows the context stores) the box of the
      * source field(s) is fetched into shared memory by the TMA unit (2-D tensor copies, cp.async.bulk.tensor) and the four
      * bilinear corners are read from there; tiles whose box does not fit gather from global memory as with 0.
-     * 1 (default) = automatic: 16-row tiles with 5 copies of 8 rows per field; when a step is captured into a graph the tile
+     * 1 (default) = automatic: 32-row tiles with up to 8 copies of 8 rows for one field, 16-row tiles with up to 5 copies per
+     * field for the u, v pair; when a step is captured into a graph the tile
      * counters of the direct run before it decide whether the captured step keeps the tiles (most fitted) or runs as with 0;
      * connected slabs run as with 0.  2..8 = 32-row tiles, at most that many 8-row copies per field; 12..18 = 16-row tiles,
      * (value - 10) copies; both always on.  0 = every cell gathers from global memory.
@@ -131,13 +132,7 @@ enum {
      * (graph branches), so the launches of one fill the SMs that the tail of another's leaves idle (u beside v, then the density solve
      * beside the projections and the advection of vel_step).  Costs four more scratch fields.  0 = one after the other.  Full-grid contexts with the
      * Jacobi solver; results are unchanged (same kernels, same arguments). */
-    SF_OPT_OVERLAP_SOLVES = 19,
-    /* 1 (default) = inside sf_step, where SF_OPT_OVERLAP_SOLVES and the TMA-staged advect apply, the gradient subtraction that
-     * ends vel_step (lastProject, seq:161-173 as called at seq:240) is folded into the advect that ends dens_step (seq:185):
-     * that advect reads u, v only at the cell it traces back from, so each thread corrects u, v of its own cells from the
-     * pressure first, stores them (set_bnd fused) and traces back with the corrected values -- one pass over u, v and one
-     * launch less per step.  u, v, dens and the *_prev fields come out unchanged, bit for bit.  0 = two kernels. */
-    SF_OPT_FUSE_PROJECT_ADVECT = 20
+    SF_OPT_OVERLAP_SOLVES = 19
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 enum { SF_SOLVER_JACOBI = 0, SF_SOLVER_RBGS = 1 };

@@ -59,10 +59,11 @@ def velocity(rng, G, N, kind):
     return (u * cells).astype(np.float32), (v * cells).astype(np.float32)
 
 
-def tiles_per_launch(N, tile):
-    """CTAs of one advect launch: 128 columns x 16 rows (the default and 12..18) or 32 rows (2..8)"""
+def tiles_per_launch(N, tile, nf=2):
+    """CTAs of one advect launch: 128 columns x 32 rows (2..8, and the default for one field) or 16 rows (12..18, and the
+    default for the u, v pair)"""
     G = N + 2
-    rows = 32 if 2 <= tile <= 8 else 16
+    rows = 32 if (2 <= tile <= 8 or (tile == 1 and nf == 1)) else 16
     return ((G + 127) // 128) * ((N + rows - 1) // rows)
 
 
@@ -89,7 +90,7 @@ def test_advect_scalar_field(SF, oracle_mt, N, kind, tile):
         d = dev(np.full((G, G), np.nan, np.float32)); s.advect(b, d, dev(d0), dev(u), dev(v), DT)
         assert_same(host(d), want, f"advect b={b} N={N} {kind} tile={tile}")
     tma, fallback = counters(s, SF)
-    ntiles = 3 * tiles_per_launch(N, tile)
+    ntiles = 3 * tiles_per_launch(N, tile, 1)
     assert tma + fallback == ntiles
     if kind == "drift" and tile == 1: assert fallback == 0, (tma, fallback)
     if kind == "rough": assert tma == 0, (tma, fallback)

@@ -29,6 +29,6 @@ python tools/t_sweep.py 8192 40 1,2,3,4,5,6,7,8 > gpurun_out/final_t_sweep.log 2
 for st in 0 1; do python tools/solve_sweep.py $st; done > gpurun_out/final_staging_ab.log 2>&1; cat gpurun_out/final_staging_ab.log
 python tools/stage_times.py 8192 40 > gpurun_out/final_stage_times.log 2>&1; tail -18 gpurun_out/final_stage_times.log
 # the step against the two round-2 options that changed its schedule: overlapped solves (19), TMA-staged advect (16)
-python tools/step_ab.py 8192 40 sequential_gather=19:0,16:0 tile_only=19:0,16:1 overlap_only=19:1,16:0 default=19:1,16:1 unfolded=20:0 default_again= > gpurun_out/final_step_ab.log 2>&1; cat gpurun_out/final_step_ab.log
+python tools/step_ab.py 8192 40 sequential_gather=19:0,16:0 tile_only=19:0,16:1 overlap_only=19:1,16:0 default=19:1,16:1 > gpurun_out/final_step_ab.log 2>&1; cat gpurun_out/final_step_ab.log
 python tools/advect_ab.py 8192 40 0,1,15,8,6 > gpurun_out/final_advect_ab.log 2>&1; cat gpurun_out/final_advect_ab.log
 ls -la gpurun_out/final_*
