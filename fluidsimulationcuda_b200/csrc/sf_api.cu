@@ -54,20 +54,38 @@ bool overlap_ok(const sf_context *c)
 }
 
 // lanes are created on the first direct run of a step, never inside a stream capture
+void release_lanes(sf_context *c)
+{
+    for (auto &L : c->lanes) {
+        if (L.stream) cudaStreamDestroy(L.stream);
+        if (L.scratch) cudaFree(L.scratch);
+        if (L.scratch2) cudaFree(L.scratch2);
+        if (L.ticket) cudaFree(L.ticket);
+        if (L.fork) cudaEventDestroy(L.fork);
+        if (L.join) cudaEventDestroy(L.join);
+        L = sf_context::SolveLane();
+    }
+}
+
 int ensure_lanes(sf_context *c)
 {
-    if (!overlap_ok(c)) return SF_OK;
-    for (int k = 0; k < 2; ++k) {
+    if (!overlap_ok(c) || c->lanes[1].join) return SF_OK;
+    bool ok = true;
+    for (int k = 0; k < 2 && ok; ++k) {
         sf_context::SolveLane &L = c->lanes[k];
-        if (!L.stream) SF_CUDA(c, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-        if (!L.scratch) SF_CUDA(c, cudaMalloc(&L.scratch, field_cells(c) * sizeof(float)));
-        if (!L.scratch2) SF_CUDA(c, cudaMalloc(&L.scratch2, field_cells(c) * sizeof(float)));
-        if (!L.ticket) {
-            SF_CUDA(c, cudaMalloc(&L.ticket, 64));
-            SF_CUDA(c, cudaMemset(L.ticket, 0, 64));
-        }
-        if (!L.fork) SF_CUDA(c, cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
-        if (!L.join) SF_CUDA(c, cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming));
+        ok = ok && cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaMalloc(&L.scratch, field_cells(c) * sizeof(float)) == cudaSuccess;
+        ok = ok && cudaMalloc(&L.scratch2, field_cells(c) * sizeof(float)) == cudaSuccess;
+        ok = ok && cudaMalloc(&L.ticket, 64) == cudaSuccess && cudaMemset(L.ticket, 0, 64) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {
+        // not enough device memory for four more fields (or no more streams): the solves run one after the other, as with
+        // SF_OPT_OVERLAP_SOLVES = 0 -- same results, and the call that got here still succeeds
+        (void)cudaGetLastError();
+        release_lanes(c);
+        c->overlap = 0;
     }
     return SF_OK;
 }
@@ -509,14 +527,6 @@ int create_common(sf_context **out, int N, int device, void *stream, bool own_st
     if (cudaMalloc(&c->tile_stats, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(c->tile_stats, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
         (void)cudaGetLastError();
         if (c->tile_stats) cudaFree(c->tile_stats);
-    for (auto &L : c->lanes) {
-        if (L.stream) cudaStreamDestroy(L.stream);
-        if (L.scratch) cudaFree(L.scratch);
-        if (L.scratch2) cudaFree(L.scratch2);
-        if (L.ticket) cudaFree(L.ticket);
-        if (L.fork) cudaEventDestroy(L.fork);
-        if (L.join) cudaEventDestroy(L.join);
-    }
         c->tile_stats = nullptr;
     }
     *out = c;
@@ -557,14 +567,7 @@ int sf_destroy(sf_context *c)
     if (c->red_d) cudaFree(c->red_d);
     if (c->ticket) cudaFree(c->ticket);
     if (c->tile_stats) cudaFree(c->tile_stats);
-    for (auto &L : c->lanes) {
-        if (L.stream) cudaStreamDestroy(L.stream);
-        if (L.scratch) cudaFree(L.scratch);
-        if (L.scratch2) cudaFree(L.scratch2);
-        if (L.ticket) cudaFree(L.ticket);
-        if (L.fork) cudaEventDestroy(L.fork);
-        if (L.join) cudaEventDestroy(L.join);
-    }
+    release_lanes(c);
     for (auto &s : c->stage) if (s) cudaFree(s);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->h2d) cudaStreamDestroy(c->h2d);
