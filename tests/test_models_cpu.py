@@ -27,3 +27,11 @@ def test_temporally_blocked_red_black_design_matches_the_in_place_scheme():
     """Design check for the next step of the opt-in solver: red-black Gauss-Seidel / SOR on the streaming pipeline
     (one iteration = two levels, colour-masked updates, set_bnd on black levels) is bit-identical to the in-place scheme."""
     _load("rbgs_blocked_model").main(sizes=(2, 6, 14, 114))
+
+
+def test_tma_staged_advect_model_matches_the_oracle():
+    """numpy transcription of advect_tile_kernel (bounding box of the traces, first column rounded down to the TMA unit's 16-byte
+    rule, fit test, 8-row tensor copies with zero fill, shared-memory index arithmetic, whole-tile fallback, 2^23 truncation,
+    fused set_bnd): gathers of fitted tiles are served from the modelled box only, and the result is bit-identical to the
+    oracle's advect for smooth, wall-hitting and partly rough velocity fields, both tile shapes, b = 0, 1, 2."""
+    _load("advect_tile_model").main(sizes=(318, 382))
