@@ -526,19 +526,21 @@ def test_no_write_outside_the_fields(SF, oracle_mt, N, K):
         assert (band == 0x7FC0DEAD).all(), f"canary band {i} was written ({int((band != 0x7FC0DEAD).sum())} words)"
 
 
+@pytest.mark.parametrize("use_graph", [True, False])
 @pytest.mark.parametrize("N,K", [(254, 20), (510, 33), (1022, 12)])
-def test_overlapped_solves_are_bit_identical(SF, oracle_mt, N, K):
+def test_overlapped_solves_are_bit_identical(SF, oracle_mt, N, K, use_graph):
     """SF_OPT_OVERLAP_SOLVES: the u / v viscosity solves and the density's diffusion solve of sf_step on three streams
-    (graph branches) -- direct run, capture and replays against the oracle's sequential vel_step + dens_step
-    (FluidSequential.c:305-306), and against the same context with the option off"""
+    (graph branches; with use_graph = False real streams forked and joined by events on every call) -- direct run, capture and
+    replays against the oracle's sequential vel_step + dens_step (FluidSequential.c:305-306), and against the same context
+    with the option off; vel_step alone (u || v) afterwards"""
     G = N + 2
     rng = np.random.default_rng(N + K)
     f = [rng.uniform(0.0, 1.0, (G, G)).astype(np.float32) for _ in range(6)]
     f[0][:] = 0.0; f[1][:] = 0.0; f[1][G // 3: G // 2, G // 3: G // 2] = 100.0      # a compact density source: work stealing
     want = [a.copy() for a in f]
-    s = SF.StableFluids(N)
+    s = SF.StableFluids(N, use_graph=use_graph)
     assert s.get_option(SF.SF_OPT_OVERLAP_SOLVES) == 1
-    s2 = SF.StableFluids(N)
+    s2 = SF.StableFluids(N, use_graph=use_graph)
     s2.set_option(SF.SF_OPT_OVERLAP_SOLVES, 0)
     d, d2 = [dev(a) for a in f], [dev(a) for a in f]
     names = ("dens", "dens_prev", "u", "u_prev", "v", "v_prev")
@@ -551,3 +553,8 @@ def test_overlapped_solves_are_bit_identical(SF, oracle_mt, N, K):
             assert_same(host(a), b, f"overlapped step {name} step {step}")
             assert_same(host(a2), b, f"sequential step {name} step {step}")
     assert s.launch_count == s2.launch_count
+    for step in range(3):   # sf_vel_step on its own: the two viscosity solves side by side
+        oracle_mt.vel_step(N, want[2], want[4], want[3], want[5], VIS, DT, K)
+        s.vel_step(d[2], d[4], d[3], d[5], VIS, DT, K)
+        for k in (2, 3, 4, 5):
+            assert_same(host(d[k]), want[k], f"overlapped vel_step {names[k]} step {step}")
