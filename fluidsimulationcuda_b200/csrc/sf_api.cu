@@ -21,7 +21,9 @@ int ensure_scratch(sf_context *c)
 {
     if (!c->scratch) SF_CUDA(c, cudaMalloc(&c->scratch, field_cells(c) * sizeof(float)));
     // (allocated here, on the first direct run of a step, never inside a stream capture)
-    if (!c->scratch2 && is_full_grid(c)) SF_CUDA(c, cudaMalloc(&c->scratch2, field_cells(c) * sizeof(float)));
+    // (full grids and arena slabs: the right-hand side of a solve with the add_source fused into its first launch; it is only
+    // ever written and read by its own GPU, so it need not be part of the arena the neighbours map)
+    if (!c->scratch2 && (is_full_grid(c) || c->link.base)) SF_CUDA(c, cudaMalloc(&c->scratch2, field_cells(c) * sizeof(float)));
     if (!c->steal) {
         c->steal_capacity = 16384;
         const size_t bytes = sizeof(StealCtl) + (size_t)c->steal_capacity * sizeof(StealSlot);

@@ -163,7 +163,10 @@ int enqueue_vel_tail(sf_context *c, float *u, float *v, float *u0, float *v0, fl
 GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const void *> ptrs, float f0, float f1, float f2, int iters);
 
 // ---- implemented in sf_slab.cu (peer-memory slabs; every rank must issue the same call sequence) ----
-int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess);
+// fuse_dt != nullptr: x0 is the RAW field and x the source (= the initial guess): the first launch forms x0 + *fuse_dt * x
+// itself (see slab_sources_fusable), x0 is left as it was
+int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess,
+                   const float *fuse_dt = nullptr);
 int slab_project(sf_context *c, float *u, float *v, float *p, float *div, int iters);
 int slab_advect(sf_context *c, int b, float *d, const float *d0, const float *u, const float *v, float dt, bool trailing_barrier);
 int slab_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters);

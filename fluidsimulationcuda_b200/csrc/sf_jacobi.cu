@@ -85,7 +85,7 @@ struct StreamArgs {
     DivConst div;        // beta and its reciprocals
     const StripArgs *strips;   // peer-memory slabs: the fused exchange of the top / bottom strip (device memory)
     StealCtl *steal;           // row-level work stealing (VAR 3 / 4), device memory
-    // fused add_source (VAR 6 / 7, first launch of a solve inside the step drivers): rhs = raw + src_dt * xin is formed
+    // fused add_source (VAR 6 / 7, on peer slabs 8 / 9; first launch of a solve inside the step drivers): rhs = raw + src_dt * xin is formed
     // as the rows land and stored to rhs_out for the later launches of the solve; `rhs` points at the raw field
     float *rhs_out;
     float src_dt;
@@ -548,7 +548,11 @@ __device__ __forceinline__ void stream_rows(const StreamArgs &A, float4 *ring, c
                 const float2 r23 = add2_rn(make_float2(raw.z, raw.w), mul2_exact(dup2(A.src_dt), make_float2(sv.z, sv.w), A.div.nz));
                 const float4 r = make_float4(r01.x, r01.y, r23.x, r23.y);
                 *slot = r;
-                if (row >= a_lo && row < a_hi && st_ok) *reinterpret_cast<float4 *>(A.rhs_out + cell(row)) = r;
+                // (a strip warp of a peer slab also stores the rows above / below its strip: the T ghost rows beside it, which
+                // the later launches' strips read and nobody else forms, and T interior rows that their owner stores with
+                // the same bits)
+                const bool mine = STRIP ? (row >= a_lo - T && row < a_hi + T) : (row >= a_lo && row < a_hi);
+                if (mine && st_ok) *reinterpret_cast<float4 *>(A.rhs_out + cell(row)) = r;
             }
         }
     };
@@ -894,7 +898,7 @@ __device__ __noinline__ bool steal_next(StealCtl *ctl, int nitems, int chunk_row
 // VAR = 2: cp.async staging plus the fused strip exchange of peer-memory slabs.  The strip warps run
 // their own (out-of-line) copy of the pipeline, so the interior warps execute exactly the code of the
 // single-GPU kernel.
-template <int T, int MODE>
+template <int T, int MODE, bool SRC = false>
 __device__ __noinline__ void strip_warp(const StreamArgs A, float4 *ring, const int lane, const int warp, const int item0, const int n_top)
 {
     const StripArgs *S = A.strips;
@@ -904,7 +908,7 @@ __device__ __noinline__ void strip_warp(const StreamArgs A, float4 *ring, const 
     const int a_lo = top ? S->o_lo : S->o_hi - P->rows;
     const int a_hi = top ? S->o_lo + P->rows : S->o_hi;
     float *peer = P->xpeer - (ptrdiff_t)P->peer_row_base * (ptrdiff_t)A.G;
-    stream_rows<T, MODE, false, true, false>(A, ring, lane, warp, top ? item0 : item0 - n_top, a_lo, a_hi, peer);
+    stream_rows<T, MODE, false, true, false, false, SRC>(A, ring, lane, warp, top ? item0 : item0 - n_top, a_lo, a_hi, peer);
     strip_post(P->arrive, P->seq, P->nbr_inbox, A.nbands, lane);
 }
 
@@ -927,8 +931,10 @@ __device__ __forceinline__ void log_range(unsigned long long t0, int band, int l
 template <int T, int MODE, int VAR>
 __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_kernel(const StreamArgs A)
 {
-    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2 || VAR == 4), STEALS = (VAR == 3 || VAR == 4 || VAR == 7), RB = (VAR == 5);
-    constexpr bool SRC = (VAR == 6 || VAR == 7);       // fused add_source (first launch of a solve), without / with work stealing
+    constexpr bool TMA = (VAR == 1), STRIPS = (VAR == 2 || VAR == 4 || VAR == 8 || VAR == 9);
+    constexpr bool STEALS = (VAR == 3 || VAR == 4 || VAR == 7 || VAR == 9), RB = (VAR == 5);
+    // fused add_source (first launch of a solve): 6 / 7 without / with work stealing, 8 / 9 the same on a peer slab (strips)
+    constexpr bool SRC = (VAR == 6 || VAR == 7 || VAR == 8 || VAR == 9);
     extern __shared__ float4 ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // work item = (band, row chunk); consecutive warps take consecutive bands of the same chunk.  warps take their items in
@@ -964,7 +970,7 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
         // scheduled first and travel while everybody computes, and the grid still is one wave of warps
         const StripArgs *S = A.strips;
         const int n_top = S->port[0].rows > 0 ? A.nbands : 0, n_bot = S->port[1].rows > 0 ? A.nbands : 0;
-        if (item < n_top + n_bot) strip_warp<T, MODE>(A, ring, lane, warp, item, n_top);
+        if (item < n_top + n_bot) strip_warp<T, MODE, SRC>(A, ring, lane, warp, item, n_top);
     }
     const int nitems = A.nbands * A.nchunks;
     if (item >= nitems) return;
@@ -1054,14 +1060,16 @@ cudaError_t launch_stream_T(const StreamArgs &A, dim3 grid, size_t smem, bool tm
     if (A.rhs_out != nullptr) {
         // fused add_source: built for the depths a default launch plan starts with and the two bit-exact divisions
         if constexpr ((T == 5 || T == 6 || T == 7) && (MODE == MODE_STRICT || MODE == MODE_IEEE)) {
-            if (A.strips != nullptr || tma) return cudaErrorNotSupported;
+            if (tma) return cudaErrorNotSupported;
             if constexpr (MODE == MODE_STRICT) {
                 if (A.steal != nullptr) {
-                    jacobi_stream_kernel<T, MODE_STRICT, 7><<<grid, WPC * 32, smem, st>>>(A);
+                    if (A.strips != nullptr) jacobi_stream_kernel<T, MODE_STRICT, 9><<<grid, WPC * 32, smem, st>>>(A);
+                    else jacobi_stream_kernel<T, MODE_STRICT, 7><<<grid, WPC * 32, smem, st>>>(A);
                     return cudaGetLastError();
                 }
             }
-            jacobi_stream_kernel<T, MODE, 6><<<grid, WPC * 32, smem, st>>>(A);
+            if (A.strips != nullptr) jacobi_stream_kernel<T, MODE, 8><<<grid, WPC * 32, smem, st>>>(A);
+            else jacobi_stream_kernel<T, MODE, 6><<<grid, WPC * 32, smem, st>>>(A);
             return cudaGetLastError();
         } else {
             return cudaErrorNotSupported;
@@ -1151,7 +1159,11 @@ void preload_T(cudaFuncAttributes &a)
     }
     if constexpr ((T == 5 || T == 6 || T == 7) && (MODE == MODE_STRICT || MODE == MODE_IEEE)) {
         cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE, 6>);
-        if constexpr (MODE == MODE_STRICT) cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE_STRICT, 7>);
+        cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE, 8>);
+        if constexpr (MODE == MODE_STRICT) {
+            cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE_STRICT, 7>);
+            cudaFuncGetAttributes(&a, jacobi_stream_kernel<T, MODE_STRICT, 9>);
+        }
     }
 }
 template <int MODE>

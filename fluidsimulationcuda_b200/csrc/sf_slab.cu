@@ -216,8 +216,22 @@ cudaError_t launch_push_rows(const PushSegment *segs, int nsegs, cudaStream_t st
     return cudaGetLastError();
 }
 
+// add_source fused into the first launch of the solve that consumes it (SF_OPT_FUSE_SOURCES, see source_lin_solve in
+// sf_api.cu), on a slab: the right-hand side x0 + dt * x goes to the context's second scratch field, which is NOT part of the
+// arena -- no neighbour ever writes it.  Its ghost rows are formed locally by the strip warps of the first launch from the
+// ghost rows of the raw field and of the source, which the exchange in front of the solve delivers anyway; that takes the
+// first launch to be as deep as the deepest one (it is: launch plans are non-increasing).
+static bool slab_sources_fusable(sf_context *c, float alpha, float beta, int iters)
+{
+    if (!c->fuse_sources || !c->scratch2 || c->solver != SF_SOLVER_JACOBI || c->staging != 0 || !stream_kernels_ok(c)) return false;
+    const std::vector<int> plan = plan_launches(iters, default_sweeps(c));
+    if (plan[0] != *std::max_element(plan.begin(), plan.end())) return false;
+    return jacobi_src_fusion_built(plan[0], arith_mode(c, alpha, beta));
+}
+
 // ---- lin_solve with fused strip pushes (replaces diffuse(), FluidSequential.c:85-104, on a slab) ----
-int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess)
+int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha, float beta, int iters, int zero_guess,
+                   const float *fuse_dt)
 {
     SF_REQUIRE(c, stream_kernels_ok(c), "peer slab: grid width must be a multiple of 4 (streaming kernels)");
     SF_REQUIRE(c, field_index(c, x) >= 0 && field_index(c, x0) >= 0, "peer slab: lin_solve fields must be arena fields (sf_slab_field)");
@@ -227,6 +241,7 @@ int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha,
     const int lo = c->g.own_lo, hi = c->g.own_hi;
     SF_REQUIRE(c, c->halo >= maxT, "peer slab: halo rows < sweeps per launch");
     SF_REQUIRE(c, hi - lo >= 2 * maxT, "peer slab: slab thinner than two boundary strips");
+    SF_REQUIRE(c, !fuse_dt || (!zero_guess && c->scratch2 && plan[0] == maxT), "peer slab: fused add_source not possible here");
 
     // ghost rows the launches read: plan[0] rows of the initial guess, maxT rows of the right-hand side
     int rc = slab_exchange(c, {HaloSpec{x, zero_guess ? 0 : plan[0]}, HaloSpec{x0, maxT}});
@@ -241,7 +256,14 @@ int slab_lin_solve(sf_context *c, int b, float *x, const float *x0, float alpha,
         const int need = (k + 1 < plan.size()) ? plan[k + 1] : 1;
         const int strip = std::max(need, sweeps);
         // ONE launch: strip warps (scheduled first) exchange their rows while the interior warps compute
-        if ((rc = one_jacobi_launch(c, c->work, b, nxt, cur, x0, alpha, beta, sweeps, lo, hi, (zero_guess && k == 0) ? 1 : 0, strip))) return rc;
+        if (fuse_dt) {
+            // first launch: right-hand side formed on the fly from the raw field and stored (ghost rows included) for the others
+            rc = one_jacobi_launch(c, c->work, b, nxt, cur, k == 0 ? x0 : c->scratch2, alpha, beta, sweeps, lo, hi, 0, strip,
+                                   k == 0 ? c->scratch2 : nullptr, *fuse_dt);
+        } else {
+            rc = one_jacobi_launch(c, c->work, b, nxt, cur, x0, alpha, beta, sweeps, lo, hi, (zero_guess && k == 0) ? 1 : 0, strip);
+        }
+        if (rc) return rc;
         std::swap(cur, nxt);
     }
     // the neighbours' last strips must have landed before the stencils that follow read the ghost row
@@ -280,19 +302,24 @@ int slab_advect(sf_context *c, int b, float *d, const float *d0, const float *u,
 
 int slab_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float visc, float dt, int iters)
 {
-    float *xs[2] = {u, v};
-    const float *ss[2] = {u0, v0};
-    SF_CUDA(c, launch_add_source(c->g, 2, xs, ss, dt, c->work));      // FluidSequential.c:193,197
-    ++c->launches;
     const float fN = (float)c->g.N;
     float alpha = dt * visc;      // :199, left to right in binary32
     alpha = alpha * fN;
     alpha = alpha * fN;
     float beta = 4.0f * alpha;    // :200
     beta = 1.0f + beta;
-    int rc = slab_lin_solve(c, 1, u0, u, alpha, beta, iters, 0);      // :201-204
+    // u += dt * u0, v += dt * v0 (:193,197): inside the first launch of each solve, or as a pass of their own.  Fused, u and v
+    // keep their raw values -- the projection below overwrites both (p, div) before anything reads them.
+    const bool fuse = slab_sources_fusable(c, alpha, beta, iters);
+    if (!fuse) {
+        float *xs[2] = {u, v};
+        const float *ss[2] = {u0, v0};
+        SF_CUDA(c, launch_add_source(c->g, 2, xs, ss, dt, c->work));
+        ++c->launches;
+    }
+    int rc = slab_lin_solve(c, 1, u0, u, alpha, beta, iters, 0, fuse ? &dt : nullptr);      // :201-204
     if (rc) return rc;
-    if ((rc = slab_lin_solve(c, 2, v0, v, alpha, beta, iters, 0))) return rc;   // :209-210
+    if ((rc = slab_lin_solve(c, 2, v0, v, alpha, beta, iters, 0, fuse ? &dt : nullptr))) return rc;   // :209-210
     if ((rc = slab_project(c, u0, v0, u, v, iters))) return rc;       // :213-223 (p in u, div in v)
     // :228-237  advect(1,u,u0,u0,v0); advect(2,v,v0,u0,v0) in one pass, sources pulled from the neighbours
     PeerSrc su, sv;
@@ -307,18 +334,23 @@ int slab_vel_step(sf_context *c, float *u, float *v, float *u0, float *v0, float
 
 int slab_dens_step(sf_context *c, float *x, float *x0, const float *u, const float *v, float diff, float dt, int iters)
 {
-    float *xs[1] = {x};
-    const float *ss[1] = {x0};
-    SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->work));      // :177
-    ++c->launches;
     const float fN = (float)c->g.N;
     float alpha = dt * diff;      // :179
     alpha = alpha * fN;
     alpha = alpha * fN;
     float beta = 4.0f * alpha;    // :180
     beta = 1.0f + beta;
+    // x += dt * x0 (:177): fused into the solve's first launch where that is built; x then keeps its raw values until the
+    // advect below overwrites it
+    const bool fuse = slab_sources_fusable(c, alpha, beta, iters);
+    if (!fuse) {
+        float *xs[1] = {x};
+        const float *ss[1] = {x0};
+        SF_CUDA(c, launch_add_source(c->g, 1, xs, ss, dt, c->work));
+        ++c->launches;
+    }
     c->steal_now = true;          // see enqueue_dens_step
-    int rc = slab_lin_solve(c, 0, x0, x, alpha, beta, iters, 0);      // :182
+    int rc = slab_lin_solve(c, 0, x0, x, alpha, beta, iters, 0, fuse ? &dt : nullptr);      // :182
     c->steal_now = false;
     if (rc) return rc;
     return slab_advect(c, 0, x, x0, u, v, dt, true);                   // :185

@@ -257,3 +257,39 @@ def test_peer_slabs_with_tma_staged_advect(oracle_mt, world, tile):
         tma = s.ctx.get_option(SF.SF_OPT_ADVECT_TILE_COUNT); fb = s.ctx.get_option(SF.SF_OPT_ADVECT_FALLBACK_COUNT)
         assert tma > 0 and fb > 0, (tma, fb)      # interior tiles by TMA, tiles near the slab edges by peer gathers
         s.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("N,K", [(254, 20), (510, 40), (382, 12)])      # first launches of depth 5, 7, 6
+def test_peer_slabs_fused_add_source_matches_separate_pass(oracle_mt, world, N, K):
+    """SF_OPT_FUSE_SOURCES on connected slabs (jacobi_stream_kernel<T, MODE, 8 / 9>): the first launch of the viscosity and
+    diffusion solves forms x + dt * s itself, its strip warps also write the right-hand side's ghost rows.  Same bits as the
+    separate add_source pass and as the oracle, two launches fewer per slab and step."""
+    from fluidsimulationcuda_b200 import solver as SF
+    launches = {}
+    for fuse in (1, 0):
+        solvers = make(N, world, K, use_graph=True)
+        for s in solvers:
+            s.ctx.set_option(SF.SF_OPT_FUSE_SOURCES, fuse)
+            s.init_synthetic(9)
+        w = oracle_mt.init_synthetic(N, 9)
+        n0 = [s.launch_count for s in solvers]
+        for step in range(3):           # direct, capture + launch, replay
+            if step == 2:
+                for s in solvers:
+                    s.zero_sources()
+            for s in solvers:
+                s.step(None, VIS, DIFF, DT)
+            if step == 2:
+                for k in ("dens_prev", "u_prev", "v_prev"):
+                    w[k][...] = 0
+            oracle_mt.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=0)
+            for k in w:
+                got = gather(solvers, k)
+                assert bits_equal(got, w[k]), mismatch_report(got, w[k], f"world={world} fuse={fuse} step={step} {k}")
+            if step == 0:
+                launches[fuse] = [s.launch_count - a for s, a in zip(solvers, n0)]
+        for s in solvers:
+            s.status()
+            s.close()
+    assert all(a == b - 2 for a, b in zip(launches[1], launches[0])), launches
