@@ -606,6 +606,53 @@ def run_ours(args):
             torch.cuda.empty_cache()
             out["extra"]["config2"] = child_json(["--child", "config2", "--headline-ms", repr(ms_step)], 240)
     elif world > 1 and args.slab_comm == "peer" and not args.skip_extras:
+        # ---- roofline of the dominant kernel on a slab: the same two lin_solves as in the N = 1 line, called collectively
+        # (every rank solves its slab; strip exchange and neighbour barriers included), CUDA events on the slab's stream,
+        # max over ranks.  Per-GPU figures: a slab's algorithmic bytes against one GPU's measured peak.
+        try:
+            import numpy as np
+            f32 = np.float32
+            al = f32(DT) * f32(VIS); al = al * f32(N); al = al * f32(N); be = f32(1) + f32(4) * al
+            jl = -(-K // 7)
+            if (jl & 1) and jl + 1 <= K:
+                jl += 1                          # plan_launches (sf_api.cu): an even number of launches of at most 7 sweeps
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kind_ms = {"strict": [], "pressure": []}
+            graphs = sim.ctx.get_option(SF.SF_OPT_USE_GRAPH)
+            sim.ctx.set_option(SF.SF_OPT_USE_GRAPH, 0)      # direct launches: a capture between the events would be timed too
+            for rep in range(3):
+                for (kind, b_, x, x0, alpha, beta) in (("strict", 1, sim.f["u_prev"], sim.f["u"], float(al), float(be)),
+                                                       ("pressure", 0, sim.f["dens_prev"], sim.f["dens"], 1.0, 4.0)):
+                    sync()
+                    a.record(sim.stream)
+                    with torch.cuda.stream(sim.stream):
+                        sim.ctx.diffuse(b_, x, x0, alpha, beta, K)
+                    b.record(sim.stream)
+                    sync()
+                    if rep > 0:
+                        kind_ms[kind].append(a.elapsed_time(b))
+            sim.ctx.set_option(SF.SF_OPT_USE_GRAPH, graphs)
+            sim.status()
+            tk = torch.tensor([sum(kind_ms["strict"]) / 2, sum(kind_ms["pressure"]) / 2], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+            ms_kind = {"strict": float(tk[0].item()), "pressure": float(tk[1].item())}
+            slab_cells = cells / world
+            tot_ms = ms_kind["strict"] + ms_kind["pressure"]
+            achieved = 12.0 * slab_cells * 2 * K / (tot_ms * 1e-3) / 1e9
+            out["roofline"] = {
+                "kernel": "jacobi_stream_kernel with fused strip exchange (temporally blocked lin_solve on a row slab)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_how,
+                "traffic": None, "per": "GPU (one slab's algorithmic bytes against one GPU's measured peak; max over ranks of the time)",
+                "algorithmic_bytes_per_launch": 12.0 * slab_cells * K / jl, "launches_per_lin_solve": jl,
+                "avg_launch_ms": tot_ms / 2 / jl,
+                "by_kind": {k: {"ms_per_lin_solve": v, "launches": jl, "avg_launch_ms": v / jl,
+                                "achieved_gbs": 12.0 * slab_cells * K / (v * 1e-3) / 1e9} for k, v in ms_kind.items()},
+                "note": "a lin_solve here = halo exchange of the right-hand side + the blocked launches (strip warps push halo rows "
+                        "to the neighbours over NVLink inside the kernel) + closing neighbour barrier; algorithmic bytes = 12 B per "
+                        "cell per sweep, several sweeps per launch, so achieved exceeds the DRAM peak by design",
+            }
+        except Exception as e:
+            out["roofline"] = {"error": repr(e)[:300]}
         # ---- end to end on N GPUs: every rank keeps its slab of the six fields in pinned host memory;
         # per step it uploads them, steps (collectively) and downloads dens, u, v -- all inside the timed region
         try:
