@@ -103,7 +103,8 @@ enum {
      * blocked launch of the lin_solve that follows it (seq:177-182, :193-210): the right-hand side x + dt*s is formed as
      * the rows stream in and kept in a context-owned field, one pass over x and s less per solve.  The fields the
      * reference's step functions leave behind (u, v, dens and the clobbered *_prev buffers) are unchanged, bit for bit.
-     * 0 = a separate add_source kernel, as sf_add_source + sf_diffuse would run it.  Full-grid contexts. */
+     * 0 = a separate add_source kernel, as sf_add_source + sf_diffuse would run it.  Full-grid contexts and connected
+     * peer slabs (there the boundary-strip warps of that first launch also form the right-hand side's ghost rows). */
     SF_OPT_FUSE_SOURCES = 14,
     /* Temporally blocked Jacobi launches are one full wave of warps, each with one chunk of rows, three CTAs per SM at the
      * default depth.  A warp scheduler favours its oldest warp, so with equal chunks the warps of the CTA an SM received
