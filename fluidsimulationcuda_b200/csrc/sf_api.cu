@@ -148,7 +148,7 @@ int one_jacobi_launch(sf_context *c, cudaStream_t st, int b, float *xout, const 
     JacobiLaunch L;
     L.xin = xin; L.rhs = x0; L.xout = xout;
     L.rhs_out = rhs_out; L.src_dt = src_dt;
-    L.wave_skew = c->wave_skew; L.ticket = c->ticket;
+    L.wave_skew = c->wave_skew; L.ticket = c->ticket; L.strip_balance = c->strip_balance;
     L.alpha = alpha; L.beta = beta; L.b = b; L.sweeps = sweeps;
     L.mode = arith_mode(c, alpha, beta);
     L.out_lo = out_lo; L.out_hi = out_hi;
@@ -485,7 +485,7 @@ GraphKey make_key(const sf_context *c, int kind, std::initializer_list<const voi
     k.opts[0] = c->arith; k.opts[1] = c->sweeps_opt; k.opts[2] = c->force_generic; k.opts[3] = c->chunk_rows;
     k.opts[4] = c->staging * 2 + (c->steal_opt ? 1 : 0) + 4 * c->steal_scope + 8 * c->pressure_plan + 16 * c->solver +
                 32 * c->omega_milli + 65536 * c->rbgs_blocked + 131072 * c->fuse_sources;
-    k.opts[5] = c->wave_skew; k.opts[6] = c->advect_tile + 32 * c->overlap;
+    k.opts[5] = c->wave_skew; k.opts[6] = c->advect_tile + 32 * c->overlap + 64 * c->strip_balance;
     return k;
 }
 
@@ -635,6 +635,7 @@ int sf_set_option(sf_context *c, int option, int value)
             c->wave_skew = value;
             break;
         case SF_OPT_STEAL_SCOPE: SF_REQUIRE(c, value == 0 || value == 1, "steal scope: 0 scalar fields / 1 every strict solve"); c->steal_scope = value; break;
+        case SF_OPT_STRIP_BALANCE: c->strip_balance = value ? 1 : 0; break;
         default: return fail(c, SF_ERR_INVALID, "unknown option");
     }
     return SF_OK;
@@ -669,6 +670,7 @@ int sf_get_option(const sf_context *c, int option, int *value)
             break;
         }
         case SF_OPT_WAVE_SKEW: *value = c->wave_skew; break;
+        case SF_OPT_STRIP_BALANCE: *value = c->strip_balance; break;
         case SF_OPT_STEAL_COUNT: {   // diagnostics: row ranges taken over by another warp so far (synchronises)
             *value = 0;
             if (c->steal) {

@@ -281,6 +281,7 @@ struct JacobiLaunch {
     // unequal chunks for the three CTAs an SM holds (see chunk_range in sf_jacobi.cu): p0 * 1000 + p1 = rows of a chunk of the
     // first / second third of the items in percent of the mean chunk (e.g. 135106); 0 = equal chunks.  `ticket`: a device
     // word that is zero between launches (the context owns one).
+    int strip_balance = 1;   // peer slabs: shorter chunks for the warps that computed a boundary strip first
     int wave_skew = 0;
     unsigned *ticket = nullptr;
 };

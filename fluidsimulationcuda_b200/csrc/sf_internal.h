@@ -85,6 +85,7 @@ struct sf_context {
         cudaEvent_t fork = nullptr, join = nullptr;
     } lanes[2];
     int overlap = 1;
+    int strip_balance = 1;           // SF_OPT_STRIP_BALANCE
     int wave_skew = 131103;          // SF_OPT_WAVE_SKEW (p0 * 1000 + p1); swept in profiles/r02/s15_*_skew_sweep.txt
     unsigned *ticket = nullptr;      // device word: start-order tickets of the CTAs of a Jacobi launch
     float *scratch = nullptr;        // lin_solve ping-pong partner (inside the arena for peer slabs)

@@ -102,8 +102,23 @@ struct StreamArgs {
 // So (i) every warp draws its work item according to the hardware slot it runs in (see the kernel) and (ii) the chunks of the
 // first / second / last third of the items get rows in proportion to the rates of the three slots classes; the total is
 // unchanged, and so is every bit of the result (temporal blocking does not depend on where the chunks are cut).
+// Peer-slab launches (SHORT = true; they never use the slot classes above): the warps of the first one or two chunks have
+// computed a boundary strip before they get here -- (strip rows + 2T) general ticks, about 40 rows' worth -- so those chunks
+// are that much shorter than the others (skew = rows of a short chunk | number of short chunks << 16, skew_cpw = 0,
+// chunk_rows = rows of the others) and every warp of the launch finishes at about the same time.
+template <bool SHORT = false>
 __device__ __forceinline__ void chunk_range(const StreamArgs &A, int chunk, int &a_lo, int &a_hi)
 {
+    if constexpr (SHORT) {
+        if (A.skew != 0u && A.skew_cpw == 0u) {
+            const int c0 = (int)(A.skew & 0xffffu), ns = (int)(A.skew >> 16);
+            const int rows = chunk < ns ? c0 : A.chunk_rows;
+            a_lo = A.a_lo + (chunk < ns ? chunk * c0 : ns * c0 + (chunk - ns) * A.chunk_rows);
+            a_hi = min(a_lo + rows, A.a_hi);
+            a_lo = min(a_lo, A.a_hi);
+            return;
+        }
+    }
     if (A.skew == 0u) {
         a_lo = A.a_lo + chunk * A.chunk_rows;
         a_hi = min(a_lo + A.chunk_rows, A.a_hi);
@@ -976,7 +991,7 @@ __global__ void __launch_bounds__(WPC * 32, min_ctas<T, MODE>()) jacobi_stream_k
     if (item >= nitems) return;
     const int band = item % A.nbands, chunk = item / A.nbands;
     int a_lo, a_hi;
-    chunk_range(A, chunk, a_lo, a_hi);
+    chunk_range<STRIPS>(A, chunk, a_lo, a_hi);
     if constexpr (!STEALS) {
         if (a_lo >= a_hi) return;
 #ifdef SF_WARP_TIMES
@@ -1280,6 +1295,19 @@ cudaError_t launch_jacobi_stream(const Geom &g, const JacobiLaunch &L, int sm_co
             A.skew = (unsigned)r0 | ((unsigned)r1 << 16);
             A.skew_cpw = (unsigned)(A.nchunks / 3);
             A.ticket = L.ticket;
+        }
+    }
+    if (n_strip_items > 0 && L.strip_balance) {
+        // strip warps go on to an interior item of chunk 0 (top strips) / the next chunk (bottom strips): shorten those chunks
+        // by what a strip costs, lengthen the others, so that strip + short chunk = long chunk (see chunk_range<true>)
+        const int n = A.nchunks, n_short = (st_top > 0 ? 1 : 0) + (st_bot > 0 ? 1 : 0);
+        const int cost = 2 * (max(st_top, st_bot) + 2 * L.sweeps);
+        const int c1 = n > 0 ? (rows + n_short * cost + n - 1) / n : 0, c0 = c1 - cost;
+        const int min_chunk = 2 * L.sweeps > 8 ? 2 * L.sweeps : 8;
+        if (n > n_short && c0 >= min_chunk && c0 < 0x10000 && n_short * c0 + (n - n_short) * c1 >= rows) {
+            A.chunk_rows = c1;
+            A.skew = (unsigned)c0 | ((unsigned)n_short << 16);
+            A.skew_cpw = 0u;
         }
     }
     const int items = max(n_strip_items, A.nbands * A.nchunks);   // strip warps go on to an interior item

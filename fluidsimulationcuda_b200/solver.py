@@ -41,6 +41,7 @@ SF_OPT_ADVECT_TILE = 16
 SF_OPT_ADVECT_TILE_COUNT = 17
 SF_OPT_ADVECT_FALLBACK_COUNT = 18
 SF_OPT_OVERLAP_SOLVES = 19
+SF_OPT_STRIP_BALANCE = 20
 STRICT, FAST = 0, 1
 SOLVER_JACOBI, SOLVER_RBGS = 0, 1    # SF_OPT_SOLVER: the reference's Jacobi (default) / opt-in red-black Gauss-Seidel (SOR)
 

@@ -133,7 +133,12 @@ enum {
      * (graph branches), so the launches of one fill the SMs that the tail of another's leaves idle (u beside v, then the density solve
      * beside the projections and the advection of vel_step).  Costs four more scratch fields.  0 = one after the other.  Full-grid contexts with the
      * Jacobi solver; results are unchanged (same kernels, same arguments). */
-    SF_OPT_OVERLAP_SOLVES = 19
+    SF_OPT_OVERLAP_SOLVES = 19,
+    /* Connected peer slabs: the warps that compute a boundary strip go on to an interior work item of the first (top strip)
+     * or next (bottom strip) row chunk.  1 (default) = those chunks are shorter than the others by what a strip costs
+     * (2 * (strip rows + 2 * sweeps) rows), so every warp of a launch finishes at about the same time; 0 = equal chunks.
+     * Results are unchanged (temporal blocking does not depend on where the chunks are cut). */
+    SF_OPT_STRIP_BALANCE = 20
 };
 enum { SF_ARITH_STRICT = 0, SF_ARITH_FAST = 1 };
 enum { SF_SOLVER_JACOBI = 0, SF_SOLVER_RBGS = 1 };

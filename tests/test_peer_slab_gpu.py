@@ -293,3 +293,30 @@ def test_peer_slabs_fused_add_source_matches_separate_pass(oracle_mt, world, N, 
             s.status()
             s.close()
     assert all(a == b - 2 for a, b in zip(launches[1], launches[0])), launches
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_slabs_short_chunks_behind_the_strips(oracle_mt, world):
+    """SF_OPT_STRIP_BALANCE: the warps that computed a boundary strip take a shorter interior chunk.  With a mean chunk of 60
+    rows on slabs of 170-256 rows the short chunks are 18-40 rows (one per neighbour), the others 60-82: same bits as equal
+    chunks and as the oracle."""
+    from fluidsimulationcuda_b200 import solver as SF
+    N, K = 510, 20
+    for balance in (1, 0):
+        solvers = make(N, world, K, use_graph=True)
+        for s in solvers:
+            s.ctx.set_option(SF.SF_OPT_CHUNK_ROWS, 60)
+            s.ctx.set_option(SF.SF_OPT_STRIP_BALANCE, balance)
+            assert s.ctx.get_option(SF.SF_OPT_STRIP_BALANCE) == balance
+            s.init_synthetic(11)
+        w = oracle_mt.init_synthetic(N, 11)
+        for step in range(3):           # direct, capture + launch, replay
+            for s in solvers:
+                s.step(None, VIS, DIFF, DT)
+            oracle_mt.run_steps(N, 1, w, VIS, DIFF, DT, K, first_step=0)
+            for k in w:
+                got = gather(solvers, k)
+                assert bits_equal(got, w[k]), mismatch_report(got, w[k], f"world={world} balance={balance} step={step} {k}")
+        for s in solvers:
+            s.status()
+            s.close()
