@@ -29,6 +29,9 @@ def emu(variant):
         L.emu_source_lin_solve.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
         L.emu_source_lin_solve.restype = C.c_int
         L.emu_set_steal_variant.argtypes = [C.c_int]
+        L.emu_slab_lin_solve.argtypes = [C.c_int, C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_float]
+        L.emu_slab_lin_solve.restype = C.c_int
         _libs[variant] = L
     return _libs[variant]
 
@@ -90,6 +93,43 @@ def test_fused_add_source_in_the_kernel_source(oracle):
             assert L.emu_source_lin_solve(N, b, p(got), p(raw_in), dt, al, be, K, T, chunk) == 0
             assert same(got, want), (N, T, K, chunk, b)
             assert same(raw_in, raw)
+
+
+def test_peer_slab_kernels_in_the_kernel_source(oracle):
+    """jacobi_stream_kernel<T, MODE, 2 / 8> (connected peer slabs) on the host: 2 and 3 slabs of one grid, each with 8 ghost
+    rows a side, run their launches in turn; the strip warps store into the neighbour's ghost rows and post / wait on the
+    counters as on the device.  Checked against the oracle's lin_solve on the whole grid: the plain strict and pressure solves,
+    the solve with add_source fused into its first launch (the strip warps form the ghost rows of the right-hand side
+    themselves), with equal chunks and with the short chunks behind the strips (SF_OPT_STRIP_BALANCE)."""
+    L = emu("default")
+    rng = np.random.default_rng(17)
+    dt = 0.016
+    al, be = 2683.2, 10733.8
+    #        N, world, T,  K, chunk, short chunks expected with balance = 1
+    cases = [(126, 2, 6, 12, 0, False), (254, 2, 7, 14, 60, True), (382, 3, 5, 10, 40, True)]
+    for N, world, T, K, chunk, expect in cases:
+        G = N + 2
+        for b in (0, 1, 2):
+            src = rng.uniform(0, 1, (G, G)).astype(np.float32); raw = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+            rhs = raw.copy(); oracle.add_source(N, rhs, src, dt)
+            want_fused = src.copy(); oracle.diffuse(N, b, want_fused, rhs, al, be, K)
+            want_plain = src.copy(); oracle.diffuse(N, b, want_plain, raw, al, be, K)
+            for balance in ((1, 0) if b == 1 else (1,)):
+                got = src.copy()
+                n = L.emu_slab_lin_solve(N, world, b, p(got), p(raw), al, be, K, T, 0, chunk, balance, 0, 0.0)
+                assert n >= 0 and (n > 0) == (expect and balance == 1), (N, world, T, K, b, balance, n)
+                assert same(got, want_plain), ("plain", N, world, T, K, b, balance)
+                got, raw_in = src.copy(), raw.copy()
+                n = L.emu_slab_lin_solve(N, world, b, p(got), p(raw_in), al, be, K, T, 0, chunk, balance, 1, dt)
+                assert n >= 0 and (n > 0) == (expect and balance == 1), (N, world, T, K, b, balance, n)
+                assert same(got, want_fused), ("fused", N, world, T, K, b, balance)
+                assert same(raw_in, raw)
+        # the pressure solve of project(): alpha = 1, beta = 4, implicit zero guess
+        div = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+        want = np.zeros((G, G), np.float32); oracle.diffuse(N, 0, want, div, 1.0, 4.0, K)
+        got = np.full((G, G), np.nan, np.float32)
+        assert L.emu_slab_lin_solve(N, world, 0, p(got), p(div), 1.0, 4.0, K, T, 1, chunk, 1, 0, 0.0) >= 0
+        assert same(got, want), ("pressure", N, world, T, K)
 
 
 def test_slot_class_tickets_and_unequal_chunks_partition_the_rows(oracle):

@@ -148,10 +148,167 @@ int launch(float *xout, const float *xin, const float *rhs, int N, int b, int mo
     if (mode == MODE_PRESSURE) return run_T<MODE_PRESSURE, 0>(sweeps, A, ctas);
     return run_T<MODE_STRICT, 0>(sweeps, A, ctas);
 }
+
+// ---- peer-memory slabs on the host: p slabs of one grid, each with its own rows (+ HALO ghost rows a side), exchanging
+// boundary strips exactly as the device does (strip warps store into the neighbour's ghost rows, post / wait on counters).
+// The slabs run their k-th launch one after the other, so every wait finds its counter already posted.
+struct EmuSlab {
+    int own_lo = 0, own_hi = 0, row_base = 0, rows = 0;
+    std::vector<float> x, x0, scratch, rhs;     // local fields: rows x G, NaN where nothing was delivered
+    SlabFlags flags;
+    StripArgs strips;
+};
+
+// launch_jacobi_stream (csrc/sf_jacobi.cu) for a connected slab: strips, interior segment, short chunks behind the strips
+int slab_launch(EmuSlab &S, EmuSlab *up, EmuSlab *dn, float *xout, float *up_xout, float *dn_xout, const float *xin,
+                const float *rhs, int N, int b, int mode, float alpha, float beta, int sweeps, int strip, int chunk_rows,
+                int balance, float *rhs_out, float src_dt, int zero_guess)
+{
+    StreamArgs A;
+    std::memset(&A, 0, sizeof(A));
+    const int G = N + 2;
+    A.xin = xin; A.rhs = rhs; A.xout = xout;
+    A.zero_guess = zero_guess;
+    A.G = G; A.N = N; A.row_base = S.row_base;
+    const int st_top = up ? strip : 0, st_bot = dn ? strip : 0;
+    S.strips = StripArgs();
+    S.strips.o_lo = S.own_lo; S.strips.o_hi = S.own_hi;
+    S.strips.error = &S.flags.error; S.strips.timeout_ns = 2000000000ull;
+    EmuSlab *nb[2] = {up, dn};
+    float *nb_x[2] = {up_xout, dn_xout};
+    for (int dir = 0; dir < 2; ++dir) {
+        if (!nb[dir]) continue;
+        StripPort &P = S.strips.port[dir];
+        P.rows = strip; P.xpeer = nb_x[dir]; P.peer_row_base = nb[dir]->row_base;
+        P.inbox = &S.flags.strip_inbox[dir]; P.seq = &S.flags.strip_seq[dir]; P.arrive = &S.flags.strip_arrive[dir];
+        P.nbr_inbox = &nb[dir]->flags.strip_inbox[1 - dir];
+    }
+    A.strips = (st_top > 0 || st_bot > 0) ? &S.strips : nullptr;
+    A.a_lo = std::max(S.own_lo + st_top, 1);
+    A.a_hi = std::min(S.own_hi - st_bot, N + 1);
+    A.write_top = (S.own_lo == 0); A.write_bot = (S.own_hi == G);
+    A.nbands = (G + VALID_W - 1) / VALID_W;
+    A.rhs_out = rhs_out; A.src_dt = src_dt;
+    A.alpha = alpha; A.div = make_div_const(beta);
+    {
+        const double F = 1.0 + 4.0 * fabs((double)alpha);
+        double g = F / fabs((double)beta) * 1.000001;
+        if (g < 1.0) g = 1.0;
+        double hi = (double)SF_DIV_HI / (F * 1.01);
+        for (int t = 0; t < sweeps; ++t) hi /= g;
+        A.hi_in = (float)hi;
+    }
+    A.sx = (b == 1) ? -1.0f : 1.0f;
+    A.sy = (b == 2) ? -1.0f : 1.0f;
+    const int n_strip_items = (st_top > 0 ? A.nbands : 0) + (st_bot > 0 ? A.nbands : 0);
+    const int rows = A.a_hi - A.a_lo;
+    int chunk = chunk_rows;
+    if (chunk <= 0) {
+        const bool heavy = sweeps >= 6;
+        const int slots = 148 * (heavy ? 3 : 4) * WPC;
+        int want = slots / A.nbands;
+        if (want < 1) want = 1;
+        chunk = (std::max(rows, 1) + want - 1) / want;
+        const int min_chunk = 2 * sweeps > 8 ? 2 * sweeps : 8;
+        if (chunk < min_chunk) chunk = min_chunk;
+    }
+    if (chunk > rows) chunk = std::max(rows, 1);
+    A.chunk_rows = chunk;
+    A.nchunks = rows > 0 ? (rows + chunk - 1) / chunk : 0;
+    int balanced = 0;
+    if (n_strip_items > 0 && balance) {
+        const int n = A.nchunks, n_short = (st_top > 0 ? 1 : 0) + (st_bot > 0 ? 1 : 0);
+        const int cost = 2 * (std::max(st_top, st_bot) + 2 * sweeps);
+        const int c1 = n > 0 ? (rows + n_short * cost + n - 1) / n : 0, c0 = c1 - cost;
+        const int min_chunk = 2 * sweeps > 8 ? 2 * sweeps : 8;
+        if (n > n_short && c0 >= min_chunk && c0 < 0x10000 && n_short * c0 + (n - n_short) * c1 >= rows) {
+            A.chunk_rows = c1;
+            A.skew = (unsigned)c0 | ((unsigned)n_short << 16);
+            A.skew_cpw = 0u;
+            balanced = 1;
+        }
+    }
+    const int items = std::max(n_strip_items, A.nbands * A.nchunks);
+    const int ctas = (items + WPC - 1) / WPC;
+    if (mode == MODE_PRESSURE) {
+        if (rhs_out) return -1;
+        if (run_T<MODE_PRESSURE, 2>(sweeps, A, ctas)) return -1;
+        return balanced;
+    }
+    if (rhs_out != nullptr) {
+        switch (sweeps) {
+            case 5: run_grid<5, MODE_STRICT, 8>(A, ctas); return balanced;
+            case 6: run_grid<6, MODE_STRICT, 8>(A, ctas); return balanced;
+            case 7: run_grid<7, MODE_STRICT, 8>(A, ctas); return balanced;
+        }
+        return -1;
+    }
+    if (run_T<MODE_STRICT, 2>(sweeps, A, ctas)) return -1;
+    return balanced;
+}
 }  // namespace
 }  // namespace sf
 
 extern "C" {
+// slab_lin_solve of csrc/sf_slab.cu on `world` slabs of one (N+2)^2 grid, fields given and returned as full grids.
+// fuse != 0: x is the source field (and the initial guess), x0 the RAW field, the first launch forms x0 + dt * x (VAR 8).
+// Returns the number of launches that ran with short chunks behind the strips (>= 0), or -1.
+int emu_slab_lin_solve(int N, int world, int b, float *x, const float *x0, float alpha, float beta, int iters, int T,
+                       int zero_guess, int chunk_rows, int balance, int fuse, float dt)
+{
+    using namespace sf;
+    const int G = N + 2, H = HALO_X;
+    const int mode = (alpha == 1.0f && beta == 4.0f) ? MODE_PRESSURE : MODE_STRICT;
+    int L = (iters + T - 1) / T;
+    if ((L & 1) && L + 1 <= iters) ++L;
+    std::vector<int> plan(L, iters / L);
+    for (int k = 0; k < iters % L; ++k) ++plan[k];
+    const int maxT = *std::max_element(plan.begin(), plan.end());
+    if (fuse && (zero_guess || plan[0] != maxT)) return -1;
+    std::vector<EmuSlab> S(world);
+    for (int r = 0; r < world; ++r) {
+        EmuSlab &s = S[r];
+        s.own_lo = (int)((long long)r * G / world); s.own_hi = (int)((long long)(r + 1) * G / world);
+        if (s.own_hi - s.own_lo < 2 * maxT) return -1;
+        s.row_base = s.own_lo - H; s.rows = s.own_hi - s.own_lo + 2 * H;
+        const size_t cells = (size_t)s.rows * G;
+        s.x.assign(cells, NAN); s.x0.assign(cells, NAN); s.scratch.assign(cells, NAN); s.rhs.assign(cells, NAN);
+        std::memset(&s.flags, 0, sizeof(s.flags));
+        // owned rows + what the exchange in front of the solve delivers: plan[0] ghost rows of the guess, maxT of the rhs
+        auto fill = [&](std::vector<float> &dst, const float *src, int ghost) {
+            for (int row = std::max(s.own_lo - ghost, 0); row < std::min(s.own_hi + ghost, G); ++row)
+                std::memcpy(&dst[(size_t)(row - s.row_base) * G], src + (size_t)row * G, (size_t)G * sizeof(float));
+        };
+        if (!zero_guess) fill(s.x, x, plan[0]);
+        fill(s.x0, x0, maxT);
+    }
+    int balanced = 0;
+    for (size_t k = 0; k < plan.size(); ++k) {
+        const int need = (k + 1 < plan.size()) ? plan[k + 1] : 1;
+        const int strip = std::max(need, plan[k]);
+        for (int r = 0; r < world; ++r) {
+            EmuSlab &s = S[r];
+            EmuSlab *up = r > 0 ? &S[r - 1] : nullptr, *dn = r + 1 < world ? &S[r + 1] : nullptr;
+            // every slab ping-pongs in step: the output field of this launch is the same one on all of them
+            auto out_of = [&](EmuSlab &t) { return (k % 2 == 0) ? t.scratch.data() : t.x.data(); };
+            auto in_of = [&](EmuSlab &t) { return (k % 2 == 0) ? t.x.data() : t.scratch.data(); };
+            const float *rhs = fuse ? (k == 0 ? s.x0.data() : s.rhs.data()) : s.x0.data();
+            const int rc = slab_launch(s, up, dn, out_of(s), up ? out_of(*up) : nullptr, dn ? out_of(*dn) : nullptr, in_of(s), rhs, N, b,
+                                       mode, alpha, beta, plan[k], strip, chunk_rows, balance,
+                                       (fuse && k == 0) ? s.rhs.data() : nullptr, dt, (zero_guess && k == 0) ? 1 : 0);
+            if (rc < 0) return -1;
+            balanced += rc;
+            if (s.flags.error) return -1;
+        }
+    }
+    for (int r = 0; r < world; ++r) {
+        EmuSlab &s = S[r];
+        const float *res = (plan.size() % 2 == 0) ? s.x.data() : s.scratch.data();
+        for (int row = s.own_lo; row < s.own_hi; ++row)
+            std::memcpy(x + (size_t)row * G, res + (size_t)(row - s.row_base) * G, (size_t)G * sizeof(float));
+    }
+    return balanced;
+}
 void emu_set_steal_variant(int on) { sf::g_steal_variant = on != 0; }
 void emu_set_wave_skew(int code) { sf::g_wave_skew = code; }
 int emu_ticket_words_nonzero() { return (sf::g_ticket[0] | sf::g_ticket[1] | sf::g_ticket[2] | sf::g_ticket[3]) != 0; }
