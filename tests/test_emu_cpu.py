@@ -124,6 +124,23 @@ def test_peer_slab_kernels_in_the_kernel_source(oracle):
                 assert n >= 0 and (n > 0) == (expect and balance == 1), (N, world, T, K, b, balance, n)
                 assert same(got, want_fused), ("fused", N, world, T, K, b, balance)
                 assert same(raw_in, raw)
+        if N == 254:   # the density solve's variants (work stealing, zero-row shortcut) on a compactly supported field: VAR 4 / 9
+            yy, xx = np.mgrid[0:G, 0:G]
+            raw = np.where(np.hypot(yy - G / 2, xx - G / 2) < 40, rng.uniform(0, 0.1, (G, G)), 0.0).astype(np.float32)
+            src = (raw * np.float32(0.5)).astype(np.float32)
+            rhs = raw.copy(); oracle.add_source(N, rhs, src, dt)
+            want_fused = src.copy(); oracle.diffuse(N, 0, want_fused, rhs, al, be, K)
+            want_plain = src.copy(); oracle.diffuse(N, 0, want_plain, raw, al, be, K)
+            L.emu_set_steal_variant(1)
+            try:
+                got = src.copy()
+                assert L.emu_slab_lin_solve(N, world, 0, p(got), p(raw), al, be, K, T, 0, chunk, 1, 0, 0.0) > 0
+                assert same(got, want_plain), ("stealing variant, plain", N, world)
+                got = src.copy()
+                assert L.emu_slab_lin_solve(N, world, 0, p(got), p(raw), al, be, K, T, 0, chunk, 1, 1, dt) > 0
+                assert same(got, want_fused), ("stealing variant, fused", N, world)
+            finally:
+                L.emu_set_steal_variant(0)
         # the pressure solve of project(): alpha = 1, beta = 4, implicit zero guess
         div = rng.uniform(-1, 1, (G, G)).astype(np.float32)
         want = np.zeros((G, G), np.float32); oracle.diffuse(N, 0, want, div, 1.0, 4.0, K)

@@ -235,6 +235,28 @@ int slab_launch(EmuSlab &S, EmuSlab *up, EmuSlab *dn, float *xout, float *up_xou
         if (run_T<MODE_PRESSURE, 2>(sweeps, A, ctas)) return -1;
         return balanced;
     }
+    if (g_steal_variant && A.nbands * A.nchunks > 1) {
+        // the work-stealing variants on slabs (VAR 4 / 9: the density solve).  As in launch(): warps run one after the other, nobody
+        // finds a range to take over; what runs is the variant's own streaming code behind the strips
+        static std::vector<char> ctl_mem;
+        const int capacity = 16384;
+        ctl_mem.assign(sizeof(StealCtl) + (size_t)capacity * sizeof(StealSlot), 0);
+        StealCtl *ctl = reinterpret_cast<StealCtl *>(ctl_mem.data());
+        ctl->min_pct = 30;
+        for (int k = 0; k < capacity; ++k) ctl->slots[k].pos = 0x3fffffff;
+        if (items > capacity) return -1;
+        A.steal = ctl;
+        if (rhs_out != nullptr) {
+            switch (sweeps) {
+                case 5: run_grid<5, MODE_STRICT, 9>(A, ctas); return balanced;
+                case 6: run_grid<6, MODE_STRICT, 9>(A, ctas); return balanced;
+                case 7: run_grid<7, MODE_STRICT, 9>(A, ctas); return balanced;
+            }
+            return -1;
+        }
+        if (run_T<MODE_STRICT, 4>(sweeps, A, ctas)) return -1;
+        return balanced;
+    }
     if (rhs_out != nullptr) {
         switch (sweeps) {
             case 5: run_grid<5, MODE_STRICT, 8>(A, ctas); return balanced;
