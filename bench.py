@@ -525,8 +525,8 @@ def run_ours(args):
     if world > 1:
         out["scaling_note"] = (f"strong scaling of the G={G} problem over {world} GPUs; the N=1 bench line runs G=8192 (the size the "
                                "metric is quoted on), so compare with the single-GPU time of THIS problem: the `scaling_base` object "
-                               "of the N=1 line (measured in that run), or profiles/r01_scaling/README.md "
-                               "(G=32768, K=40: 151.4 ms/step; G=16384, K=200: 156.6 ms/step)")
+                               "of the N=1 line (measured in that run; profiles/r02/final_c2a13ce_bench.json: 113.4 ms/step at "
+                               "G=32768, K=40), and `extra.config5.same_run_one_gpu` for G=16384, K=200")
 
     if world == 1 and not args.skip_extras:
         # ---- roofline of the dominant kernel: jacobi_stream_kernel, timed per lin_solve with CUDA events on
