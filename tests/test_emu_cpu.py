@@ -124,6 +124,13 @@ def test_peer_slab_kernels_in_the_kernel_source(oracle):
                 assert n >= 0 and (n > 0) == (expect and balance == 1), (N, world, T, K, b, balance, n)
                 assert same(got, want_fused), ("fused", N, world, T, K, b, balance)
                 assert same(raw_in, raw)
+        if N == 126:   # K = 40 as in the benchmark: launches of 7,7,7,7,6,6 sweeps, strips of 7 and 6 rows
+            src = rng.uniform(0, 1, (G, G)).astype(np.float32); raw = rng.uniform(-1, 1, (G, G)).astype(np.float32)
+            rhs = raw.copy(); oracle.add_source(N, rhs, src, dt)
+            want = src.copy(); oracle.diffuse(N, 2, want, rhs, al, be, 40)
+            got = src.copy()
+            assert L.emu_slab_lin_solve(N, world, 2, p(got), p(raw), al, be, 40, 7, 0, chunk, 1, 1, dt) >= 0
+            assert same(got, want), ("K = 40, fused", N, world)
         if N == 254:   # the density solve's variants (work stealing, zero-row shortcut) on a compactly supported field: VAR 4 / 9
             yy, xx = np.mgrid[0:G, 0:G]
             raw = np.where(np.hypot(yy - G / 2, xx - G / 2) < 40, rng.uniform(0, 0.1, (G, G)), 0.0).astype(np.float32)
