@@ -298,8 +298,8 @@ def test_peer_slabs_fused_add_source_matches_separate_pass(oracle_mt, world, N, 
 @pytest.mark.parametrize("world", [2, 3])
 def test_peer_slabs_short_chunks_behind_the_strips(oracle_mt, world):
     """SF_OPT_STRIP_BALANCE: the warps that computed a boundary strip take a shorter interior chunk.  With a mean chunk of 60
-    rows on slabs of 170-256 rows the short chunks are 18-40 rows (one per neighbour), the others 60-82: same bits as equal
-    chunks and as the oracle."""
+    rows on slabs of 170-256 rows (K = 20: launches of 5 sweeps, strips of 5 rows, cost 30 rows) the short chunks are 26-44 rows
+    (one per neighbour), the others 56-74: same bits as equal chunks and as the oracle."""
     from fluidsimulationcuda_b200 import solver as SF
     N, K = 510, 20
     for balance in (1, 0):
