@@ -109,7 +109,7 @@ def test_peer_slab_kernels_in_the_kernel_source(oracle):
     cases = [(126, 2, 6, 12, 0, False), (254, 2, 7, 14, 60, True), (382, 3, 5, 10, 40, True)]
     for N, world, T, K, chunk, expect in cases:
         G = N + 2
-        for b in (0, 1, 2):
+        for b in ((0, 1, 2) if N == 126 else (1,)):      # (the wall rules of all three field kinds on the small grid)
             src = rng.uniform(0, 1, (G, G)).astype(np.float32); raw = rng.uniform(-1, 1, (G, G)).astype(np.float32)
             rhs = raw.copy(); oracle.add_source(N, rhs, src, dt)
             want_fused = src.copy(); oracle.diffuse(N, b, want_fused, rhs, al, be, K)
